@@ -1,0 +1,45 @@
+"""Builds csrc/libfsb_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels)."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(CSRC, "libfsb_b200.so")
+SOURCES = ["fsb_abi.cu"]
+HEADERS = ["fsb_device.cuh", "fsb_state.h", "fsb_step.cuh", "fsb_aux.cuh", "../../include/fsb.h"]
+
+# -fmad=false: no implicit FMA contraction -- every fused operation in the kernels is an explicit
+# fma(), which is what makes results bit-identical to the CPU oracle.
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+    "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
+]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if force or needs_build():
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        cmd = [nvcc] + NVCC_FLAGS + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            print(res.stdout)
+            print(res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed building libfsb_b200.so")
+        with open(os.path.join(CSRC, "build.log"), "w") as f:
+            f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

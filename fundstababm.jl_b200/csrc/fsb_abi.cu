@@ -1,0 +1,873 @@
+// fsb_abi.cu -- host side of libfsb_b200.so: the C ABI of include/fsb.h.
+// Owns device memory, the stream, the launch schedule of the per-step kernel and the NCCL
+// communicator (libnccl is dlopen'ed on first use so the library has no link-time dependency).
+// There is no CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fsb.h"
+#include "fsb_aux.cuh"
+#include "fsb_state.h"
+#include "fsb_step.cuh"
+
+using namespace fsb;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return fail(FSB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---- NCCL through dlopen -------------------------------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int32_t nccl_load()
+{
+    if (g_nccl.lib) return FSB_OK;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(FSB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                             \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));         \
+    if (!g_nccl.field) return fail(FSB_ERR_NCCL, "libnccl lacks symbol %s", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommInitAll, "ncclCommInitAll");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.lib = h;
+    return FSB_OK;
+}
+#define NC(expr)                                                                                        \
+    do {                                                                                                \
+        ncclResult_t r_ = (expr);                                                                       \
+        if (r_ != ncclSuccess) return fail(FSB_ERR_NCCL, "%s: %s", #expr, g_nccl.GetErrorString(r_));   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+struct fsb_engine {
+    DevState d{};
+    fsb_config cfg{};
+    std::vector<DevPoint> points;
+    std::vector<void *> allocs;
+    int64_t device_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int grid = 0, block = 256, smem_bytes = 0, init_smem = 0;
+    int launch_parity = 0;
+    bool log_built = false, state_set = false;
+    int64_t t_done = 0;  // last simulated t (0 = none since init/upload)
+    int64_t words_per_point = 0;
+    unsigned long long *stats_dev = nullptr;
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1;
+    // last-run timing
+    double last_total_ms = 0.0;
+    int64_t last_launches = 0;
+    // host mirrors of the per-replication pointer tables
+    std::vector<const double *> z_mkt, z_stock, u_review;
+    std::vector<const fsb_tape_rec *> ev_tape;
+    std::vector<long long> ev_n;
+    std::vector<int> trace_slot;
+    int n_trace_slots = 0;
+    // device pointer tables
+    const double **z_mkt_d = nullptr, **z_stock_d = nullptr, **u_review_d = nullptr;
+    const fsb_tape_rec **ev_tape_d = nullptr;
+    long long *ev_n_d = nullptr;
+    int *trace_slot_d = nullptr;
+    double *st_zmkt = nullptr, *st_zstock = nullptr, *st_urev = nullptr;
+};
+
+template <class T>
+static int32_t dalloc(fsb_engine *e, T **out, size_t count, bool zero = true)
+{
+    void *p = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CU(cudaMalloc(&p, bytes));
+    if (zero) CU(cudaMemset(p, 0, bytes));
+    e->allocs.push_back(p);
+    e->device_bytes += static_cast<int64_t>(bytes);
+    *out = static_cast<T *>(p);
+    return FSB_OK;
+}
+#define TRY(expr)                    \
+    do {                             \
+        int32_t rc_ = (expr);        \
+        if (rc_ != FSB_OK) return rc_; \
+    } while (0)
+
+extern "C" int32_t fsb_version(void) { return FSB_VERSION; }
+extern "C" const char *fsb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int64_t fsb_stats_words_per_point(const fsb_engine *e)
+{
+    return e ? e->words_per_point : 0;
+}
+extern "C" int64_t fsb_device_bytes(const fsb_engine *e) { return e ? e->device_bytes : 0; }
+
+extern "C" uint64_t fsb_tape_key(int32_t site, int64_t t, int64_t a, int64_t b)
+{
+    return (static_cast<uint64_t>(site & 0xff) << 56) | (static_cast<uint64_t>(t & 0xffffff) << 32) |
+           (static_cast<uint64_t>(a & 0xffff) << 16) | static_cast<uint64_t>(b & 0xffff);
+}
+
+static int32_t check_params(const fsb_params *p, int32_t n_points)
+{
+    if (!p || n_points < 1) return fail(FSB_ERR_BAD_PARAMS, "need at least one Params point");
+    for (int i = 0; i < n_points; ++i) {
+        const fsb_params &q = p[i];
+        if (q.bigk < 1 || q.bigm < 1 || q.bign < q.bigk) return fail(FSB_ERR_BAD_PARAMS, "point %d: need bign >= bigk >= 1, bigm >= 1", i);
+        if (!(0 < q.perf_lo && q.perf_lo <= q.perf_hi && q.perf_hi < q.bigt)) return fail(FSB_ERR_BAD_PARAMS, "point %d: need 0 < perfwindow[1] <= perfwindow[end] < bigt", i);
+        if (q.psize_lo < 1 || q.psize_lo > q.psize_hi) return fail(FSB_ERR_BAD_PARAMS, "point %d: bad portfsizerange", i);
+        if (q.cap_lo < 0 || q.cap_lo > q.cap_hi) return fail(FSB_ERR_BAD_PARAMS, "point %d: bad invcaprange", i);
+        if (q.n_impact < 1 || q.n_vol < 1 || !q.impact_values || !q.vol_values) return fail(FSB_ERR_BAD_PARAMS, "point %d: empty impactrange/stockvolrange", i);
+        if (!(q.reviewprobability >= 0.0 && q.reviewprobability <= 1.0)) return fail(FSB_ERR_BAD_PARAMS, "point %d: reviewprobability is not a probability", i);
+        if (q.bigm != p[0].bigm || q.bign != p[0].bign || q.bigt != p[0].bigt || q.bigk != p[0].bigk || q.perf_hi != p[0].perf_hi)
+            return fail(FSB_ERR_BAD_PARAMS, "point %d: shapes (bigm,bign,bigt,bigk,perfwindow[end]) must agree across sweep points", i);
+        if (q.bign > 65535 || q.bigm > 65535 || q.bigt >= (1 << 24)) return fail(FSB_ERR_BAD_PARAMS, "point %d: shape exceeds tape key range", i);
+    }
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb_config *cfg, fsb_engine **out)
+{
+    if (!out || !cfg) return fail(FSB_ERR_BAD_PARAMS, "null argument");
+    *out = nullptr;
+    TRY(check_params(pts, n_points));
+    if (cfg->n_reps < 1) return fail(FSB_ERR_BAD_PARAMS, "n_reps must be >= 1");
+    if (cfg->reps_per_point > 0 && (cfg->rep_offset + cfg->n_reps + cfg->reps_per_point - 1) / cfg->reps_per_point > n_points)
+        return fail(FSB_ERR_BAD_PARAMS, "replication range maps beyond the %d sweep points", n_points);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FSB_ERR_CUDA, "no CUDA device: libfsb_b200 has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(FSB_ERR_BAD_PARAMS, "device %d out of range (%d devices)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    fsb_engine *e = new fsb_engine();
+    e->cfg = *cfg;
+    DevState &d = e->d;
+    const fsb_params &p0 = pts[0];
+    d.K = static_cast<int>(p0.bigk); d.M = static_cast<int>(p0.bigm); d.N = static_cast<int>(p0.bign);
+    d.T = static_cast<int>(p0.bigt); d.W = static_cast<int>(p0.perf_hi);
+    d.Mp = (d.M + 1) & ~1;
+    d.keep_history = cfg->keep_history ? 1 : 0;
+    d.hist_cols = d.keep_history ? d.T : 2 * (d.W + 1);
+    d.mkt_len = d.keep_history ? d.T : 2;
+    d.R = cfg->n_reps; d.rep_offset = cfg->rep_offset; d.reps_per_point = cfg->reps_per_point; d.n_points = n_points;
+    d.h_stride = ((static_cast<long long>(d.K) * d.Mp + 15) / 16) * 16;
+    d.p_stride = static_cast<long long>(d.hist_cols) * d.Mp;
+    // event capacity: reviewers ~ Binomial(N, p); mean + 12 sd + 16
+    double pmax = 0.0;
+    for (int i = 0; i < n_points; ++i) pmax = std::max(pmax, pts[i].reviewprobability);
+    const double mean = d.N * pmax;
+    int cap = cfg->event_capacity > 0 ? cfg->event_capacity : static_cast<int>(std::ceil(mean + 12.0 * std::sqrt(mean * (1.0 - pmax)) + 16.0));
+    cap = std::min(std::max(cap, 8), d.N);
+    cap = std::max(cap, std::min(d.N, 8));
+    d.cap_ev = (cap + 7) & ~7;
+    d.cap_log = cfg->log_capacity > 0 ? std::max(cfg->log_capacity, d.K + 1) : d.K + 1024;
+    d.cap_trace = cfg->trace_capacity > 0 ? cfg->trace_capacity : 1 << 20;
+    e->block = cfg->block_threads > 0 ? ((cfg->block_threads + 31) / 32) * 32 : 256;
+    if (e->block > 256) e->block = 256;
+    // shared memory: shrink the pass-2 column chunk until the layout fits
+    int smem_max = 0;
+    CU(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+    d.cmax = 8;
+    SmemLayout L = make_layout(d.K, d.Mp, d.cap_ev, d.cmax, e->block / 32);
+    while (L.bytes + 64 > std::min(smem_max, 100 * 1024) && d.cmax > 1) {
+        d.cmax >>= 1;
+        L = make_layout(d.K, d.Mp, d.cap_ev, d.cmax, e->block / 32);
+    }
+    if (L.bytes + 64 > smem_max) { delete e; return fail(FSB_ERR_BAD_PARAMS, "shapes need %d bytes of shared memory per CTA (> %d)", L.bytes, smem_max); }
+    e->smem_bytes = L.bytes;
+    e->init_smem = (d.W + 2 + d.K) * 8;
+    CU(cudaFuncSetAttribute(fsb_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_bytes));
+    if (e->init_smem > 48 * 1024) CU(cudaFuncSetAttribute(fsb_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->init_smem));
+    int sms = 0, occ = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fsb_step_kernel, e->block, e->smem_bytes));
+    if (occ < 1) { delete e; return fail(FSB_ERR_CUDA, "step kernel cannot be resident (smem %d)", e->smem_bytes); }
+    if (cfg->blocks_per_sm > 0) occ = std::min(occ, cfg->blocks_per_sm);
+    e->grid = static_cast<int>(std::min<long long>(d.R, static_cast<long long>(sms) * occ));
+
+    // points + tables
+    std::vector<double> tables;
+    for (int i = 0; i < n_points; ++i) {
+        const fsb_params &q = pts[i];
+        DevPoint dp{};
+        dp.marketstartval = q.marketstartval; dp.drift = q.drift; dp.marketvol = q.marketvol;
+        dp.betamean = q.betamean; dp.betastd = q.betastd; dp.stockstartval = q.stockstartval;
+        dp.reviewprob = q.reviewprobability; dp.thresholdmean = q.thresholdmean; dp.thresholdstd = q.thresholdstd;
+        dp.perf_lo = static_cast<int>(q.perf_lo); dp.perf_hi = static_cast<int>(q.perf_hi);
+        dp.cap_lo = static_cast<int>(q.cap_lo); dp.cap_hi = static_cast<int>(q.cap_hi);
+        dp.psize_lo = static_cast<int>(q.psize_lo); dp.psize_hi = static_cast<int>(std::min<int64_t>(q.psize_hi, 1 << 30));
+        dp.n_impact = static_cast<int>(q.n_impact); dp.n_vol = static_cast<int>(q.n_vol);
+        dp.impact_off = static_cast<int>(tables.size());
+        tables.insert(tables.end(), q.impact_values, q.impact_values + q.n_impact);
+        dp.vol_off = static_cast<int>(tables.size());
+        tables.insert(tables.end(), q.vol_values, q.vol_values + q.n_vol);
+        e->points.push_back(dp);
+    }
+    auto cleanup = [&](int32_t rc) { fsb_destroy(e); return rc; };
+#define A(field, count) do { int32_t rc_ = dalloc(e, &d.field, (count)); if (rc_ != FSB_OK) return cleanup(rc_); } while (0)
+    const size_t R = static_cast<size_t>(d.R);
+    A(H, R * d.h_stride);
+    A(P, R * d.p_stride);
+    A(beta, R * d.Mp); A(vol, R * d.Mp); A(impact, R * d.Mp);
+    if (d.keep_history) A(volume, R * d.T * d.Mp);
+    A(market, R * d.mkt_len);
+    A(pos, R * d.N); A(horizon, R * d.N);
+    A(stake, R * d.N); A(amount, R * d.N); A(threshold, R * d.N);
+    A(nav_open, R * d.K); A(nav_close, R * d.K); A(cap0, R * d.K);
+    A(hzero, R * d.K); A(live_row, R * d.K);
+    A(log_n, R);
+    A(log_liquidated, R * d.cap_log); A(log_replacedby, R * d.cap_log); A(log_failtime, R * d.cap_log);
+    A(log_ninv, R * d.cap_log); A(log_nstocks, R * d.cap_log);
+    A(log_size, R * d.cap_log); A(log_liquidity, R * d.cap_log);
+    A(err, R); A(cnt, R * kCnt);
+    A(mkt_peak, R); A(mkt_dd, R);
+    A(flow_hist, R * kFlowBins);
+    A(scratch, static_cast<size_t>(e->grid) * d.cap_ev * d.Mp);
+    A(queue, 2);
+#undef A
+    {
+        DevPoint *pd = nullptr; double *td = nullptr;
+        if (dalloc(e, &pd, e->points.size()) != FSB_OK || dalloc(e, &td, tables.size()) != FSB_OK) return cleanup(FSB_ERR_CUDA);
+        if (cudaMemcpy(pd, e->points.data(), e->points.size() * sizeof(DevPoint), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(td, tables.data(), tables.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+            return cleanup(fail(FSB_ERR_CUDA, "cannot upload parameter tables"));
+        d.points = pd; d.tables = td;
+    }
+    e->words_per_point = FSB_STATS_HEADER + (d.T + 1) + FSB_STATS_LIQ_BINS + FSB_STATS_DD_BINS + FSB_STATS_FLOW_BINS;
+    if (dalloc(e, &e->stats_dev, static_cast<size_t>(n_points) * e->words_per_point) != FSB_OK) return cleanup(FSB_ERR_CUDA);
+    e->z_mkt.assign(R, nullptr); e->z_stock.assign(R, nullptr); e->u_review.assign(R, nullptr);
+    e->ev_tape.assign(R, nullptr); e->ev_n.assign(R, 0); e->trace_slot.assign(R, -1);
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess)
+        return cleanup(fail(FSB_ERR_CUDA, "cannot create stream/events"));
+    *out = e;
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_destroy(fsb_engine *e)
+{
+    if (!e) return FSB_OK;
+    cudaSetDevice(e->cfg.device);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (void *p : e->allocs) cudaFree(p);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    delete e;
+    return FSB_OK;
+}
+
+static int32_t check_rep(fsb_engine *e, int64_t rep)
+{
+    if (!e) return fail(FSB_ERR_BAD_PARAMS, "null engine");
+    if (rep < 0 || rep >= e->d.R) return fail(FSB_ERR_RANGE, "replication %lld out of range [0,%lld)", (long long)rep, e->d.R);
+    CU(cudaSetDevice(e->cfg.device));
+    return FSB_OK;
+}
+
+// ---- device initialisation ------------------------------------------------------------------
+extern "C" int32_t fsb_init_device(fsb_engine *e, uint64_t seed)
+{
+    if (!e) return fail(FSB_ERR_BAD_PARAMS, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    e->d.seed = seed;
+    fsb_init_kernel<<<static_cast<unsigned>(e->d.R), 256, e->init_smem, e->stream>>>(e->d);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    e->log_built = false;
+    e->state_set = true;
+    e->t_done = 0;
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_set_seed(fsb_engine *e, uint64_t seed)
+{
+    if (!e) return fail(FSB_ERR_BAD_PARAMS, "null engine");
+    e->d.seed = seed;
+    return FSB_OK;
+}
+
+// ---- upload of the reference's structs (column-major, src/types.jl:15-50) ---------------------
+extern "C" int32_t fsb_upload_state(fsb_engine *e, int64_t rep, const double *market, const double *stock_value,
+                                    const double *beta, const double *vol, const double *impact, const double *volume,
+                                    const double *inv_assets, const int64_t *horizon, const double *threshold,
+                                    const double *holdings, const double *stakes, const double *fund_value)
+{
+    TRY(check_rep(e, rep));
+    if (!market || !stock_value || !beta || !vol || !impact || !inv_assets || !horizon || !threshold || !holdings || !stakes)
+        return fail(FSB_ERR_BAD_PARAMS, "fsb_upload_state: null array");
+    const DevState &d = e->d;
+    const int K = d.K, M = d.M, N = d.N, T = d.T, Mp = d.Mp, W = d.W;
+    // investors: exactly one position per investor (SURVEY.md 3.2 invariant)
+    std::vector<int> pos(N), hz(N);
+    std::vector<double> amount(N), stake(N), thr(threshold, threshold + N);
+    for (int n = 0; n < N; ++n) {
+        int where = -1, count = 0;
+        for (int c = 0; c <= K; ++c) {
+            const double a = inv_assets[n + static_cast<size_t>(N) * c];
+            if (a != 0.0) { where = c; ++count; }
+        }
+        if (count > 1) return fail(FSB_ERR_BAD_STATE, "investor %d holds %d positions; the engine needs at most one", n + 1, count);
+        pos[n] = (where < 0) ? K : where;
+        amount[n] = (where < 0) ? 0.0 : inv_assets[n + static_cast<size_t>(N) * where];
+        if (amount[n] < 0.0) return fail(FSB_ERR_BAD_STATE, "investor %d has a negative position", n + 1);
+        stake[n] = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double sv = stakes[k + static_cast<size_t>(K) * n];
+            if (sv != 0.0) {
+                if (k != pos[n]) return fail(FSB_ERR_BAD_STATE, "investor %d has a stake in fund %d but its position is in %d", n + 1, k + 1, pos[n] + 1);
+                stake[n] = sv;
+            }
+        }
+        if (horizon[n] < 1 || horizon[n] > W) return fail(FSB_ERR_BAD_STATE, "investor %d: horizon %lld outside 1..%d", n + 1, (long long)horizon[n], W);
+        hz[n] = static_cast<int>(horizon[n]);
+    }
+    // holdings -> [K][Mp] asset-fastest
+    std::vector<double> H(static_cast<size_t>(d.h_stride), 0.0);
+    std::vector<unsigned char> hzero(K);
+    std::vector<double> cap0(K);
+    for (int k = 0; k < K; ++k) {
+        bool nz = false;
+        for (int m = 0; m < M; ++m) {
+            const double h = holdings[k + static_cast<size_t>(K) * m];
+            H[static_cast<size_t>(k) * Mp + m] = h;
+            nz = nz || (h != 0.0);
+        }
+        hzero[k] = nz ? 0 : 1;
+        if (fund_value) cap0[k] = fund_value[k];
+        else {
+            double c = 0.0;
+            for (int n = 0; n < N; ++n) c += inv_assets[n + static_cast<size_t>(N) * k];
+            cap0[k] = c;
+        }
+    }
+    // prices: columns are contiguous in Julia's M x T layout; market value != 0 marks a produced column
+    std::vector<double> P(static_cast<size_t>(d.p_stride), 0.0), mk(d.mkt_len, 0.0), volm;
+    int64_t t_last = 0;
+    for (int t = 1; t <= T; ++t) {
+        const bool produced = (t <= W + 1) || market[t - 1] != 0.0;
+        if (!produced) continue;
+        t_last = t;
+        for (int m = 0; m < M; ++m) P[static_cast<size_t>(pcol(d, t)) * Mp + m] = stock_value[m + static_cast<size_t>(M) * (t - 1)];
+        mk[mslot(d, t)] = market[t - 1];
+    }
+    if (d.keep_history && volume) {
+        volm.assign(static_cast<size_t>(T) * Mp, 0.0);
+        for (int t = 1; t <= T; ++t)
+            for (int m = 0; m < M; ++m) volm[static_cast<size_t>(t - 1) * Mp + m] = volume[m + static_cast<size_t>(M) * (t - 1)];
+    }
+    std::vector<double> b(Mp, 0.0), v(Mp, 0.0), im(Mp, 0.0);
+    std::copy(beta, beta + M, b.begin()); std::copy(vol, vol + M, v.begin()); std::copy(impact, impact + M, im.begin());
+    std::vector<int> live(K);
+    for (int k = 0; k < K; ++k) live[k] = k;
+    double peak = 0.0;
+    for (int t = 1; t <= T; ++t) peak = std::max(peak, market[t - 1]);
+    const double zero = 0.0;
+    const int izero = 0;
+    std::vector<int> zeros_cnt(kCnt + kFlowBins, 0);
+#define UP(dst, src, count) CU(cudaMemcpy((dst), (src), (count), cudaMemcpyHostToDevice))
+    UP(d.H + rep * d.h_stride, H.data(), H.size() * 8);
+    UP(d.P + rep * d.p_stride, P.data(), P.size() * 8);
+    UP(d.beta + rep * Mp, b.data(), Mp * 8); UP(d.vol + rep * Mp, v.data(), Mp * 8); UP(d.impact + rep * Mp, im.data(), Mp * 8);
+    if (d.keep_history && volume) UP(d.volume + rep * static_cast<long long>(T) * Mp, volm.data(), volm.size() * 8);
+    UP(d.market + rep * d.mkt_len, mk.data(), mk.size() * 8);
+    UP(d.pos + rep * N, pos.data(), N * 4); UP(d.horizon + rep * N, hz.data(), N * 4);
+    UP(d.stake + rep * N, stake.data(), N * 8); UP(d.amount + rep * N, amount.data(), N * 8); UP(d.threshold + rep * N, thr.data(), N * 8);
+    UP(d.cap0 + rep * K, cap0.data(), K * 8);
+    UP(d.hzero + rep * K, hzero.data(), K); UP(d.live_row + rep * K, live.data(), K * 4);
+    UP(d.mkt_peak + rep, &mk[mslot(d, static_cast<int>(std::max<int64_t>(t_last, 1)))], 8);
+    UP(d.mkt_dd + rep, &zero, 8);
+    UP(d.err + rep, &izero, 4); UP(d.log_n + rep, &izero, 4);
+    UP(d.cnt + rep * kCnt, zeros_cnt.data(), kCnt * 4);
+    UP(d.flow_hist + rep * kFlowBins, zeros_cnt.data(), kFlowBins * 4);
+#undef UP
+    CU(cudaMemset(d.nav_open + rep * K, 0, K * 8));
+    CU(cudaMemset(d.nav_close + rep * K, 0, K * 8));
+    (void)peak;
+    e->log_built = false;
+    e->state_set = true;
+    e->t_done = 0;
+    return FSB_OK;
+}
+
+// ---- tapes / trace ------------------------------------------------------------------------------
+static int32_t push_tables(fsb_engine *e)
+{
+    DevState &d = e->d;
+    const size_t R = static_cast<size_t>(d.R);
+    if (!e->z_mkt_d) {
+        TRY(dalloc(e, &e->z_mkt_d, R)); TRY(dalloc(e, &e->z_stock_d, R)); TRY(dalloc(e, &e->u_review_d, R));
+        TRY(dalloc(e, &e->ev_tape_d, R)); TRY(dalloc(e, &e->ev_n_d, R));
+    }
+    CU(cudaMemcpy(e->z_mkt_d, e->z_mkt.data(), R * sizeof(void *), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->z_stock_d, e->z_stock.data(), R * sizeof(void *), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->u_review_d, e->u_review.data(), R * sizeof(void *), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->ev_tape_d, e->ev_tape.data(), R * sizeof(void *), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->ev_n_d, e->ev_n.data(), R * sizeof(long long), cudaMemcpyHostToDevice));
+    d.z_mkt = e->z_mkt_d; d.z_stock = e->z_stock_d; d.u_review = e->u_review_d;
+    d.ev_tape = e->ev_tape_d; d.ev_n = e->ev_n_d;
+    d.any_tape = 1;
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_set_dense_tape(fsb_engine *e, int64_t rep, const double *z_mkt, const double *z_stock, const double *u_review)
+{
+    TRY(check_rep(e, rep));
+    const DevState &d = e->d;
+    auto up = [&](const double *src, size_t count, const double **slot) -> int32_t {
+        if (!src) { *slot = nullptr; return FSB_OK; }
+        double *p = nullptr;
+        TRY(dalloc(e, &p, count, false));
+        CU(cudaMemcpy(p, src, count * 8, cudaMemcpyHostToDevice));
+        *slot = p;
+        return FSB_OK;
+    };
+    TRY(up(z_mkt, d.T, &e->z_mkt[rep]));
+    TRY(up(z_stock, static_cast<size_t>(d.M) * d.T, &e->z_stock[rep]));
+    TRY(up(u_review, static_cast<size_t>(d.N) * d.T, &e->u_review[rep]));
+    return push_tables(e);
+}
+
+extern "C" int32_t fsb_set_event_tape(fsb_engine *e, int64_t rep, const fsb_tape_rec *recs, int64_t n)
+{
+    TRY(check_rep(e, rep));
+    if (n < 0 || (n > 0 && !recs)) return fail(FSB_ERR_BAD_PARAMS, "bad event tape");
+    for (int64_t i = 1; i < n; ++i)
+        if (recs[i - 1].key >= recs[i].key) return fail(FSB_ERR_BAD_PARAMS, "event tape must be strictly sorted by key");
+    fsb_tape_rec *p = nullptr;
+    TRY(dalloc(e, &p, static_cast<size_t>(std::max<int64_t>(n, 1)), false));
+    if (n) CU(cudaMemcpy(p, recs, n * sizeof(fsb_tape_rec), cudaMemcpyHostToDevice));
+    e->ev_tape[rep] = p;  // non-null pointer == tape mode for this replication, even when empty
+    e->ev_n[rep] = n;
+    return push_tables(e);
+}
+
+extern "C" int32_t fsb_set_trace(fsb_engine *e, int64_t rep, int32_t on)
+{
+    TRY(check_rep(e, rep));
+    DevState &d = e->d;
+    if (!on) {
+        e->trace_slot[rep] = -1;
+    } else if (e->trace_slot[rep] < 0) {
+        // grow the slot arrays by one (rare, host-driven)
+        const int ns = e->n_trace_slots + 1;
+        double *nav = nullptr, *ps = nullptr, *pr = nullptr; fsb_trace_rec *recs = nullptr; int *tn = nullptr;
+        const size_t kt = static_cast<size_t>(d.K) * d.T, mt = static_cast<size_t>(d.M) * d.T;
+        TRY(dalloc(e, &nav, ns * kt)); TRY(dalloc(e, &ps, ns * mt)); TRY(dalloc(e, &pr, ns * mt));
+        TRY(dalloc(e, &recs, static_cast<size_t>(ns) * d.cap_trace)); TRY(dalloc(e, &tn, ns));
+        if (e->n_trace_slots) {
+            const int os = e->n_trace_slots;
+            CU(cudaMemcpy(nav, d.tr_nav, os * kt * 8, cudaMemcpyDeviceToDevice));
+            CU(cudaMemcpy(ps, d.tr_psell, os * mt * 8, cudaMemcpyDeviceToDevice));
+            CU(cudaMemcpy(pr, d.tr_presp, os * mt * 8, cudaMemcpyDeviceToDevice));
+            CU(cudaMemcpy(recs, d.tr_recs, static_cast<size_t>(os) * d.cap_trace * sizeof(fsb_trace_rec), cudaMemcpyDeviceToDevice));
+            CU(cudaMemcpy(tn, d.tr_n, os * 4, cudaMemcpyDeviceToDevice));
+        }
+        d.tr_nav = nav; d.tr_psell = ps; d.tr_presp = pr; d.tr_recs = recs; d.tr_n = tn;
+        e->trace_slot[rep] = e->n_trace_slots;
+        e->n_trace_slots = ns;
+    }
+    if (!e->trace_slot_d) TRY(dalloc(e, &e->trace_slot_d, static_cast<size_t>(d.R)));
+    CU(cudaMemcpy(e->trace_slot_d, e->trace_slot.data(), d.R * 4, cudaMemcpyHostToDevice));
+    d.trace_slot = e->trace_slot_d;
+    return FSB_OK;
+}
+
+// ---- the hot path -----------------------------------------------------------------------------
+static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32_t selector, int32_t flags)
+{
+    if (!e) return fail(FSB_ERR_BAD_PARAMS, "null engine");
+    const DevState &d = e->d;
+    if (selector < 0 || selector > 3) return fail(FSB_ERR_BAD_SELECTOR, "Please specify a valid fund selection method (best, goodenough, probabilistic, random)");
+    if (!e->state_set) return fail(FSB_ERR_BAD_STATE, "no state: call fsb_upload_state or fsb_init_device first");
+    if (t_first < d.W + 2 || t_last > d.T) return fail(FSB_ERR_RANGE, "time range [%lld,%lld] outside [%d,%d]", (long long)t_first, (long long)t_last, d.W + 2, d.T);
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaEventRecord(e->ev0, e->stream));
+    e->last_launches = 0;
+    if (!e->log_built) {
+        fsb_build_log_kernel<<<static_cast<unsigned>(d.R), 256, 0, e->stream>>>(d);
+        CU(cudaGetLastError());
+        e->log_built = true;
+        ++e->last_launches;
+    }
+    if (t_last >= t_first) {
+        CU(cudaMemsetAsync(d.queue, 0, 2 * sizeof(int), e->stream));
+        const int spl = std::max(1, e->cfg.steps_per_launch);
+        for (int64_t t = t_first; t <= t_last; t += spl) {
+            StepArgs a{static_cast<int>(t), static_cast<int>(std::min<int64_t>(spl, t_last - t + 1)), selector, flags};
+            fsb_step_kernel<<<e->grid, e->block, e->smem_bytes, e->stream>>>(d, a, e->launch_parity);
+            e->launch_parity ^= 1;
+            ++e->last_launches;
+        }
+        CU(cudaGetLastError());
+        e->t_done = t_last;
+    }
+    CU(cudaEventRecord(e->ev1, e->stream));
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_sync(fsb_engine *e)
+{
+    if (!e) return fail(FSB_ERR_BAD_PARAMS, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_total_ms = ms;
+    else (void)cudaGetLastError();
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_run_async(fsb_engine *e, int64_t t_first, int64_t t_last, int32_t selector, int32_t flags)
+{
+    return run_enqueue(e, t_first, t_last, selector, flags);
+}
+
+extern "C" int32_t fsb_run(fsb_engine *e, int64_t t_first, int64_t t_last, int32_t selector, int32_t flags)
+{
+    TRY(run_enqueue(e, t_first, t_last, selector, flags));
+    TRY(fsb_sync(e));
+    // surface replication errors (capacity overflow, Q6, tape problems) as a status
+    std::vector<int> err(static_cast<size_t>(e->d.R));
+    CU(cudaMemcpy(err.data(), e->d.err, err.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < err.size(); ++r)
+        if (err[r] & ~FSB_REP_TRACE_OVERFLOW)
+            return fail(FSB_ERR_REPLICATION, "replication %zu raised error flags 0x%x (see fsb_rep_status)", r, err[r]);
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_run_step_hosttape(fsb_engine *e, int64_t t, int32_t selector, int32_t flags, const double *z_mkt,
+                                         const double *z_stock, const double *u_review, double *nav_open_out)
+{
+    if (!e || !z_mkt || !z_stock || !u_review) return fail(FSB_ERR_BAD_PARAMS, "null argument");
+    DevState &d = e->d;
+    CU(cudaSetDevice(e->cfg.device));
+    const size_t R = static_cast<size_t>(d.R);
+    if (!e->st_zmkt) {
+        TRY(dalloc(e, &e->st_zmkt, R, false)); TRY(dalloc(e, &e->st_zstock, R * d.M, false)); TRY(dalloc(e, &e->st_urev, R * d.N, false));
+    }
+    CU(cudaMemcpyAsync(e->st_zmkt, z_mkt, R * 8, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->st_zstock, z_stock, R * d.M * 8, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->st_urev, u_review, R * d.N * 8, cudaMemcpyHostToDevice, e->stream));
+    d.st_zmkt = e->st_zmkt; d.st_zstock = e->st_zstock; d.st_urev = e->st_urev;
+    d.step_tape = 1;
+    const int spl = e->cfg.steps_per_launch;
+    e->cfg.steps_per_launch = 1;
+    const int32_t rc = run_enqueue(e, t, t, selector, flags);
+    e->cfg.steps_per_launch = spl;
+    d.step_tape = 0;
+    TRY(rc);
+    if (nav_open_out) CU(cudaMemcpyAsync(nav_open_out, d.nav_open, R * d.K * 8, cudaMemcpyDeviceToHost, e->stream));
+    return fsb_sync(e);
+}
+
+extern "C" int32_t fsb_last_run_timing(fsb_engine *e, double *total_ms, double *step_kernel_ms, int64_t *launches)
+{
+    if (!e) return fail(FSB_ERR_BAD_PARAMS, "null engine");
+    if (total_ms) *total_ms = e->last_total_ms;
+    if (step_kernel_ms) *step_kernel_ms = e->last_total_ms;
+    if (launches) *launches = e->last_launches;
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_rep_status(fsb_engine *e, int32_t *flags)
+{
+    if (!e || !flags) return fail(FSB_ERR_BAD_PARAMS, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaMemcpy(flags, e->d.err, e->d.R * 4, cudaMemcpyDeviceToHost));
+    return FSB_OK;
+}
+
+// ---- downloads ----------------------------------------------------------------------------------
+extern "C" int32_t fsb_download_compact(fsb_engine *e, int64_t rep, double *holdings, double *price_now, int64_t *inv_fund,
+                                        double *inv_amount, double *inv_stake, double *nav_open, double *nav_close,
+                                        double *market_now)
+{
+    TRY(check_rep(e, rep));
+    const DevState &d = e->d;
+    const int K = d.K, M = d.M, N = d.N, Mp = d.Mp;
+    const int t_now = static_cast<int>(e->t_done > 0 ? e->t_done : d.W + 1);
+    if (holdings) {
+        std::vector<double> H(static_cast<size_t>(K) * Mp);
+        CU(cudaMemcpy(H.data(), d.H + rep * d.h_stride, H.size() * 8, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < K; ++k)
+            for (int m = 0; m < M; ++m) holdings[k + static_cast<size_t>(K) * m] = H[static_cast<size_t>(k) * Mp + m];
+    }
+    if (price_now) CU(cudaMemcpy(price_now, d.P + rep * d.p_stride + static_cast<long long>(pcol(d, t_now)) * Mp, M * 8, cudaMemcpyDeviceToHost));
+    if (inv_fund) {
+        std::vector<int> pos(N);
+        CU(cudaMemcpy(pos.data(), d.pos + rep * N, N * 4, cudaMemcpyDeviceToHost));
+        for (int n = 0; n < N; ++n) inv_fund[n] = pos[n] + 1;
+    }
+    if (inv_amount) CU(cudaMemcpy(inv_amount, d.amount + rep * N, N * 8, cudaMemcpyDeviceToHost));
+    if (inv_stake) CU(cudaMemcpy(inv_stake, d.stake + rep * N, N * 8, cudaMemcpyDeviceToHost));
+    if (nav_open) CU(cudaMemcpy(nav_open, d.nav_open + rep * K, K * 8, cudaMemcpyDeviceToHost));
+    if (nav_close) CU(cudaMemcpy(nav_close, d.nav_close + rep * K, K * 8, cudaMemcpyDeviceToHost));
+    if (market_now) CU(cudaMemcpy(market_now, d.market + rep * d.mkt_len + mslot(d, t_now), 8, cudaMemcpyDeviceToHost));
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_download_state(fsb_engine *e, int64_t rep, double *market, double *stock_value, double *beta, double *vol,
+                                      double *impact, double *volume, double *inv_assets, int64_t *horizon, double *threshold,
+                                      double *holdings, double *stakes, double *fund_value)
+{
+    TRY(check_rep(e, rep));
+    const DevState &d = e->d;
+    if (!d.keep_history) return fail(FSB_ERR_NO_HISTORY, "fsb_download_state needs an engine created with keep_history=1");
+    const int K = d.K, M = d.M, N = d.N, T = d.T, Mp = d.Mp;
+    if (market) CU(cudaMemcpy(market, d.market + rep * d.mkt_len, T * 8, cudaMemcpyDeviceToHost));
+    if (stock_value || volume) {
+        std::vector<double> buf(static_cast<size_t>(T) * Mp);
+        if (stock_value) {
+            CU(cudaMemcpy(buf.data(), d.P + rep * d.p_stride, buf.size() * 8, cudaMemcpyDeviceToHost));
+            for (int t = 0; t < T; ++t)
+                for (int m = 0; m < M; ++m) stock_value[m + static_cast<size_t>(M) * t] = buf[static_cast<size_t>(t) * Mp + m];
+        }
+        if (volume) {
+            CU(cudaMemcpy(buf.data(), d.volume + rep * static_cast<long long>(T) * Mp, buf.size() * 8, cudaMemcpyDeviceToHost));
+            for (int t = 0; t < T; ++t)
+                for (int m = 0; m < M; ++m) volume[m + static_cast<size_t>(M) * t] = buf[static_cast<size_t>(t) * Mp + m];
+        }
+    }
+    if (beta) CU(cudaMemcpy(beta, d.beta + rep * Mp, M * 8, cudaMemcpyDeviceToHost));
+    if (vol) CU(cudaMemcpy(vol, d.vol + rep * Mp, M * 8, cudaMemcpyDeviceToHost));
+    if (impact) CU(cudaMemcpy(impact, d.impact + rep * Mp, M * 8, cudaMemcpyDeviceToHost));
+    std::vector<int> pos(N), hz(N);
+    std::vector<double> amount(N), stake(N);
+    CU(cudaMemcpy(pos.data(), d.pos + rep * N, N * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hz.data(), d.horizon + rep * N, N * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(amount.data(), d.amount + rep * N, N * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(stake.data(), d.stake + rep * N, N * 8, cudaMemcpyDeviceToHost));
+    if (inv_assets) {
+        std::fill(inv_assets, inv_assets + static_cast<size_t>(N) * (K + 1), 0.0);
+        for (int n = 0; n < N; ++n) inv_assets[n + static_cast<size_t>(N) * pos[n]] = amount[n];
+    }
+    if (horizon) for (int n = 0; n < N; ++n) horizon[n] = hz[n];
+    if (threshold) CU(cudaMemcpy(threshold, d.threshold + rep * N, N * 8, cudaMemcpyDeviceToHost));
+    if (stakes) {
+        std::fill(stakes, stakes + static_cast<size_t>(K) * N, 0.0);
+        for (int n = 0; n < N; ++n) if (pos[n] < K) stakes[pos[n] + static_cast<size_t>(K) * n] = stake[n];
+    }
+    if (holdings) TRY(fsb_download_compact(e, rep, holdings, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+    if (fund_value) {
+        double *out = nullptr;
+        CU(cudaMalloc(&out, static_cast<size_t>(K) * T * 8));
+        fsb_fund_value_kernel<<<148, 256, 0, e->stream>>>(d, rep, static_cast<int>(e->t_done), out);
+        std::vector<double> buf(static_cast<size_t>(K) * T);
+        cudaError_t ce = cudaStreamSynchronize(e->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpy(buf.data(), out, buf.size() * 8, cudaMemcpyDeviceToHost);
+        cudaFree(out);
+        if (ce != cudaSuccess) return fail(FSB_ERR_CUDA, "fund value download: %s", cudaGetErrorString(ce));
+        for (int k = 0; k < K; ++k)
+            for (int t = 0; t < T; ++t) fund_value[k + static_cast<size_t>(K) * t] = buf[static_cast<size_t>(k) * T + t];
+        if (e->t_done == 0) {  // before any step the reference still holds the capital in column 1
+            std::vector<double> c0(K);
+            CU(cudaMemcpy(c0.data(), d.cap0 + rep * K, K * 8, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < K; ++k) fund_value[k] = c0[k];
+        }
+    }
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_download_log(fsb_engine *e, int64_t rep, int64_t *n_rows, int64_t *liquidated, int64_t *replacedby,
+                                    double *initialsize, double *liquidity, int64_t *failtime, int64_t *ninvestors,
+                                    int64_t *nstocks)
+{
+    TRY(check_rep(e, rep));
+    const DevState &d = e->d;
+    if (!e->log_built) {  // the reference builds the log at the top of modelrun; do the same on demand
+        if (!e->state_set) return fail(FSB_ERR_BAD_STATE, "no state");
+        fsb_build_log_kernel<<<static_cast<unsigned>(d.R), 256, 0, e->stream>>>(d);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(e->stream));
+        e->log_built = true;
+    }
+    int rows = 0;
+    CU(cudaMemcpy(&rows, d.log_n + rep, 4, cudaMemcpyDeviceToHost));
+    if (n_rows) *n_rows = rows;
+    const long long lb = rep * d.cap_log;
+    auto geti = [&](const int *src, int64_t *dst) -> int32_t {
+        if (!dst) return FSB_OK;
+        std::vector<int> b(rows);
+        CU(cudaMemcpy(b.data(), src + lb, rows * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < rows; ++i) dst[i] = b[i];
+        return FSB_OK;
+    };
+    TRY(geti(d.log_liquidated, liquidated)); TRY(geti(d.log_replacedby, replacedby)); TRY(geti(d.log_failtime, failtime));
+    TRY(geti(d.log_ninv, ninvestors)); TRY(geti(d.log_nstocks, nstocks));
+    if (initialsize) CU(cudaMemcpy(initialsize, d.log_size + lb, rows * 8, cudaMemcpyDeviceToHost));
+    if (liquidity) CU(cudaMemcpy(liquidity, d.log_liquidity + lb, rows * 8, cudaMemcpyDeviceToHost));
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_download_trace(fsb_engine *e, int64_t rep, double *nav_open, double *p_sell, double *p_resp,
+                                      fsb_trace_rec *recs, int64_t *n_recs)
+{
+    TRY(check_rep(e, rep));
+    const DevState &d = e->d;
+    const int slot = e->trace_slot[rep];
+    if (slot < 0) return fail(FSB_ERR_BAD_PARAMS, "replication %lld is not traced", (long long)rep);
+    const size_t kt = static_cast<size_t>(d.K) * d.T, mt = static_cast<size_t>(d.M) * d.T;
+    if (nav_open) CU(cudaMemcpy(nav_open, d.tr_nav + slot * kt, kt * 8, cudaMemcpyDeviceToHost));
+    if (p_sell) CU(cudaMemcpy(p_sell, d.tr_psell + slot * mt, mt * 8, cudaMemcpyDeviceToHost));
+    if (p_resp) CU(cudaMemcpy(p_resp, d.tr_presp + slot * mt, mt * 8, cudaMemcpyDeviceToHost));
+    int n = 0;
+    CU(cudaMemcpy(&n, d.tr_n + slot, 4, cudaMemcpyDeviceToHost));
+    if (recs) CU(cudaMemcpy(recs, d.tr_recs + static_cast<size_t>(slot) * d.cap_trace, static_cast<size_t>(n) * sizeof(fsb_trace_rec), cudaMemcpyDeviceToHost));
+    if (n_recs) *n_recs = n;
+    return FSB_OK;
+}
+
+// ---- statistics + NCCL ---------------------------------------------------------------------------
+extern "C" int32_t fsb_comm_unique_id(uint8_t id[128])
+{
+    TRY(nccl_load());
+    ncclUniqueId uid;
+    NC(g_nccl.GetUniqueId(&uid));
+    static_assert(sizeof(uid) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id, &uid, 128);
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_comm_init_rank(fsb_engine *e, int32_t n_ranks, int32_t rank, const uint8_t id[128])
+{
+    if (!e) return fail(FSB_ERR_BAD_PARAMS, "null engine");
+    TRY(nccl_load());
+    CU(cudaSetDevice(e->cfg.device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    NC(g_nccl.CommInitRank(&e->comm, n_ranks, uid, rank));
+    e->n_ranks = n_ranks;
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_comm_init_all(fsb_engine **engines, int32_t n)
+{
+    if (!engines || n < 1) return fail(FSB_ERR_BAD_PARAMS, "bad engine list");
+    TRY(nccl_load());
+    std::vector<int> devs(n);
+    std::vector<ncclComm_t> comms(n);
+    for (int i = 0; i < n; ++i) devs[i] = engines[i]->cfg.device;
+    NC(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; ++i) { engines[i]->comm = comms[i]; engines[i]->n_ranks = n; }
+    return FSB_OK;
+}
+
+static int32_t stats_local(fsb_engine *e)
+{
+    const DevState &d = e->d;
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaMemsetAsync(e->stats_dev, 0, static_cast<size_t>(d.n_points) * e->words_per_point * 8, e->stream));
+    if (!e->log_built) {
+        fsb_build_log_kernel<<<static_cast<unsigned>(d.R), 256, 0, e->stream>>>(d);
+        e->log_built = true;
+    }
+    fsb_stats_kernel<<<static_cast<unsigned>(d.R), 128, 0, e->stream>>>(d, e->stats_dev, e->words_per_point);
+    CU(cudaGetLastError());
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_stats(fsb_engine *e, uint64_t *out)
+{
+    if (!e || !out) return fail(FSB_ERR_BAD_PARAMS, "null argument");
+    TRY(stats_local(e));
+    const size_t words = static_cast<size_t>(e->d.n_points) * e->words_per_point;
+    if (e->comm)  // the single collective of the whole run
+        NC(g_nccl.AllReduce(e->stats_dev, e->stats_dev, words, ncclUint64, ncclSum, e->comm, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(out, e->stats_dev, words * 8, cudaMemcpyDeviceToHost));
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_stats_all(fsb_engine **engines, int32_t n, uint64_t *out)
+{
+    if (!engines || n < 1 || !out) return fail(FSB_ERR_BAD_PARAMS, "null argument");
+    for (int i = 0; i < n; ++i) TRY(stats_local(engines[i]));
+    const size_t words = static_cast<size_t>(engines[0]->d.n_points) * engines[0]->words_per_point;
+    if (n > 1) {
+        for (int i = 0; i < n; ++i) if (!engines[i]->comm) return fail(FSB_ERR_NCCL, "call fsb_comm_init_all first");
+        NC(g_nccl.GroupStart());
+        for (int i = 0; i < n; ++i) {
+            CU(cudaSetDevice(engines[i]->cfg.device));
+            NC(g_nccl.AllReduce(engines[i]->stats_dev, engines[i]->stats_dev, words, ncclUint64, ncclSum, engines[i]->comm, engines[i]->stream));
+        }
+        NC(g_nccl.GroupEnd());
+    }
+    for (int i = 0; i < n; ++i) {
+        CU(cudaSetDevice(engines[i]->cfg.device));
+        CU(cudaStreamSynchronize(engines[i]->stream));
+    }
+    CU(cudaSetDevice(engines[0]->cfg.device));
+    CU(cudaMemcpy(out, engines[0]->stats_dev, words * 8, cudaMemcpyDeviceToHost));
+    return FSB_OK;
+}
+
+// ---- debug --------------------------------------------------------------------------------------
+extern "C" int32_t fsb_debug_draws(fsb_engine *e, uint64_t seed, uint32_t rep, uint32_t site, uint32_t a, uint32_t b,
+                                   uint32_t idx0, int32_t n, int32_t kind, uint32_t n_discrete, double *out)
+{
+    if (!e || !out || n < 1) return fail(FSB_ERR_BAD_PARAMS, "bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    double *dv = nullptr;
+    CU(cudaMalloc(&dv, static_cast<size_t>(n) * 8));
+    fsb_debug_draws_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(seed, rep, site, a, b, idx0, n, kind, n_discrete, dv);
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpy(out, dv, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dv);
+    if (ce != cudaSuccess) return fail(FSB_ERR_CUDA, "debug draws: %s", cudaGetErrorString(ce));
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_debug_dot(fsb_engine *e, const double *x, const double *y, int64_t n, double *out)
+{
+    if (!e || !x || !y || !out || n < 1) return fail(FSB_ERR_BAD_PARAMS, "bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    const size_t np = static_cast<size_t>((n + 1) & ~1LL);
+    double *dx = nullptr, *dy = nullptr, *dr = nullptr;
+    CU(cudaMalloc(&dx, np * 8)); CU(cudaMalloc(&dy, np * 8)); CU(cudaMalloc(&dr, 8));
+    cudaMemset(dx, 0, np * 8); cudaMemset(dy, 0, np * 8);
+    cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice); cudaMemcpy(dy, y, n * 8, cudaMemcpyHostToDevice);
+    fsb_debug_dot_kernel<<<1, 32, 0, e->stream>>>(dx, dy, static_cast<int>(n), dr);
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpy(out, dr, 8, cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dy); cudaFree(dr);
+    if (ce != cudaSuccess) return fail(FSB_ERR_CUDA, "debug dot: %s", cudaGetErrorString(ce));
+    return FSB_OK;
+}

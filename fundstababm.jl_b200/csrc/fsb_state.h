@@ -1,0 +1,83 @@
+// fsb_state.h -- structure-of-arrays device state of the engine (replication x fund x asset).
+// One DevState is passed by value to every kernel.  See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <cstdint>
+#include "../../include/fsb.h"
+
+namespace fsb {
+
+struct DevPoint {  // one sweep point = one Params (src/params.jl:4-31), shapes excluded
+    double marketstartval, drift, marketvol, betamean, betastd, stockstartval;
+    double reviewprob, thresholdmean, thresholdstd;
+    int perf_lo, perf_hi, cap_lo, cap_hi, psize_lo, psize_hi;
+    int n_impact, n_vol, impact_off, vol_off;  // offsets into DevState::tables
+};
+
+constexpr int kFlowBins = FSB_STATS_FLOW_BINS;
+constexpr int kCnt = 8;  // per-replication counters, see CNT_*
+enum { CNT_REVIEWS = 0, CNT_DIVEST = 1, CNT_REINVEST = 2, CNT_STEPS = 3, CNT_FLOOR = 4, CNT_RESPAWN = 5 };
+
+struct DevState {
+    // shapes
+    int K, M, N, T, W;
+    int Mp;         // row pitch of holdings / price columns: M rounded up to even (16-byte rows)
+    int hist_cols;  // price columns kept per replication: T (keep_history) or 2(W+1)
+    int mkt_len;    // T (keep_history) or 2
+    int keep_history;
+    int cap_ev, cap_log, cap_trace, cmax;
+    int n_points;
+    long long R, rep_offset, reps_per_point;
+    long long h_stride;  // doubles per replication in H
+    long long p_stride;  // doubles per replication in P
+    unsigned long long seed;
+    // fund x asset
+    double *H;  // [R][K][Mp] holdings, asset fastest
+    // asset
+    double *P;       // [R][hist_cols][Mp] price history (burn-in 1..W+1, then ring or full)
+    double *beta, *vol, *impact;  // [R][Mp]
+    double *volume;  // [R][T][Mp] or null
+    double *market;  // [R][mkt_len]
+    // investor SoA (one position per investor: fund id, K = cash)
+    int *pos, *horizon;                 // [R][N]
+    double *stake, *amount, *threshold; // [R][N]
+    // fund
+    double *nav_open, *nav_close, *cap0;  // [R][K]
+    unsigned char *hzero;                 // [R][K] holdings row is all zero
+    int *live_row;                        // [R][K] log row currently describing slot k
+    // liquidation log, functions.jl:452-456
+    int *log_n;                                              // [R]
+    int *log_liquidated, *log_replacedby, *log_failtime, *log_ninv, *log_nstocks;  // [R][cap_log]
+    double *log_size, *log_liquidity;                        // [R][cap_log]
+    // status / statistics inputs
+    int *err;         // [R] FSB_REP_* bits
+    int *cnt;         // [R][kCnt]
+    double *mkt_peak, *mkt_dd;  // [R]
+    int *flow_hist;   // [R][kFlowBins]
+    // tapes (null = Philox)
+    const double *const *z_mkt, *const *z_stock, *const *u_review;  // [R] device pointers
+    const fsb_tape_rec *const *ev_tape;                              // [R]
+    const long long *ev_n;                                           // [R]
+    int any_tape;
+    // batched one-step tape fed from host buffers each step (fsb_run_step_hosttape): [R], [R][M], [R][N]
+    const double *st_zmkt, *st_zstock, *st_urev;
+    int step_tape;
+    // trace
+    const int *trace_slot;  // [R] -1 = not traced
+    double *tr_nav, *tr_psell, *tr_presp;  // [slots][K*T], [slots][M*T]
+    fsb_trace_rec *tr_recs;                // [slots][cap_trace]
+    int *tr_n;                             // [slots]
+    // per-CTA scratch + work queue
+    double *scratch;  // [grid][cap_ev][Mp] order rows
+    int *queue;       // [2] dynamic work counters (double buffered across launches)
+    const DevPoint *points;
+    const double *tables;
+};
+
+__host__ __device__ inline int pcol(const DevState &s, int t)  // 1-based t -> column slot
+{
+    if (s.keep_history || t <= s.W + 1) return t - 1;
+    return (s.W + 1) + ((t - 1) % (s.W + 1));
+}
+__host__ __device__ inline int mslot(const DevState &s, int t) { return s.keep_history ? t - 1 : (t & 1); }
+
+}  // namespace fsb

@@ -185,23 +185,31 @@ uint32_t orc_draw_discrete(uint64_t seed, uint32_t rep, uint32_t site, uint32_t 
 /* ------------------------------------------------------------------------------------------
  * canonical reductions
  * ---------------------------------------------------------------------------------------- */
-double orc_dot4(const double *x, int64_t sx, const double *y, int64_t sy, int64_t n)
+/* lane-strided partial chains (lane l of 32 owns elements 64i+2l, 64i+2l+1, ascending) followed by
+ * the xor-butterfly tree 16,8,4,2,1 -- the order a warp reading a row with 128-bit loads produces */
+static double warp_tree(double a[32])
 {
-    double a[4] = { 0.0, 0.0, 0.0, 0.0 };
-    for (int64_t i = 0; i < n; ++i) a[i & 3] = fma(x[i * sx], y[i * sy], a[i & 3]);
-    return (a[0] + a[1]) + (a[2] + a[3]);
+    for (int s = 16; s >= 1; s >>= 1)
+        for (int l = 0; l < s; ++l) a[l] = a[l] + a[l + s];
+    return a[0];
 }
-static double sum4(const double *x, int64_t sx, int64_t n)
+double orc_dotw(const double *x, int64_t sx, const double *y, int64_t sy, int64_t n)
 {
-    double a[4] = { 0.0, 0.0, 0.0, 0.0 };
-    for (int64_t i = 0; i < n; ++i) a[i & 3] = a[i & 3] + x[i * sx];
-    return (a[0] + a[1]) + (a[2] + a[3]);
+    double a[32] = { 0.0 };
+    for (int64_t e = 0; e < n; ++e) { int l = (int)((e & 63) >> 1); a[l] = fma(x[e * sx], y[e * sy], a[l]); }
+    return warp_tree(a);
 }
-static double sumprod4(const double *x, int64_t sx, const double *y, int64_t sy, int64_t n)
+static double sumw(const double *x, int64_t sx, int64_t n)
 {
-    double a[4] = { 0.0, 0.0, 0.0, 0.0 };
-    for (int64_t i = 0; i < n; ++i) { double p = x[i * sx] * y[i * sy]; a[i & 3] = a[i & 3] + p; }
-    return (a[0] + a[1]) + (a[2] + a[3]);
+    double a[32] = { 0.0 };
+    for (int64_t e = 0; e < n; ++e) { int l = (int)((e & 63) >> 1); a[l] = a[l] + x[e * sx]; }
+    return warp_tree(a);
+}
+static double sumprodw(const double *x, int64_t sx, const double *y, int64_t sy, int64_t n)
+{
+    double a[32] = { 0.0 };
+    for (int64_t e = 0; e < n; ++e) { int l = (int)((e & 63) >> 1); double p = x[e * sx] * y[e * sy]; a[l] = a[l] + p; }
+    return warp_tree(a);
 }
 
 /* Julia's isless for Float64: total order, -0.0 < +0.0, NaN last */
@@ -407,7 +415,7 @@ static void stockmove(orc_world *w, int64_t t, const double *z)
 void orc_fundrevalue(orc_world *w, int64_t k)
 {
     for (int64_t t = 1; t <= w->T; ++t)
-        V_(w, k, t) = orc_dot4(&H_(w, k, 0), w->K, &P_(w, 0, t), 1, w->M);
+        V_(w, k, t) = orc_dotw(&H_(w, k, 0), w->K, &P_(w, 0, t), 1, w->M);
 }
 
 /* NAV of fund k against price column col with CURRENT holdings (Q2: constant-composition
@@ -415,7 +423,7 @@ void orc_fundrevalue(orc_world *w, int64_t k)
 static double nav(orc_world *w, int64_t k, int64_t col)
 {
     if (w->faithful) return V_(w, k, col);
-    return orc_dot4(&H_(w, k, 0), w->K, &P_(w, 0, col), 1, w->M);
+    return orc_dotw(&H_(w, k, 0), w->K, &P_(w, 0, col), 1, w->M);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -445,7 +453,7 @@ void orc_fundvalinit(orc_world *w, int64_t horizon)
 {
     for (int64_t t = 2; t <= horizon + 1; ++t)
         for (int64_t k = 0; k < w->K; ++k)
-            V_(w, k, t) = orc_dot4(&H_(w, k, 0), w->K, &P_(w, 0, t), 1, w->M);
+            V_(w, k, t) = orc_dotw(&H_(w, k, 0), w->K, &P_(w, 0, t), 1, w->M);
 }
 
 int orc_initialise(orc_world *w)
@@ -571,7 +579,7 @@ static void executeorder_sell_phase(orc_world *w, int64_t t, const double *order
     for (int64_t m = 0; m < M; ++m) old[m] = P_(w, m, t);
     marketmake_phase(w, t, order_values, norders, 0);
     for (int64_t m = 0; m < M; ++m) ratio[m] = P_(w, m, t) / old[m];
-    for (int64_t r = 0; r < norders; ++r) cash_out[r] = -sumprod4(order_values + r * M, 1, ratio, 1, M);
+    for (int64_t r = 0; r < norders; ++r) cash_out[r] = -sumprodw(order_values + r * M, 1, ratio, 1, M);
     free(old); free(ratio);
 }
 void orc_executeorder_sell(orc_world *w, int64_t t, const double *order_values, int64_t norders, double *cash_out)
@@ -609,7 +617,7 @@ static void disburse_shares_at(orc_world *w, const int64_t *funds, int64_t norde
         int64_t f = funds[r];
         for (int64_t m = 0; m < w->M; ++m) H_(w, f, m) = H_(w, f, m) + shares[r * w->M + m];
         if (w->faithful) orc_fundrevalue(w, f);
-        if (t_now > 0) w->nav_close[f] = orc_dot4(&H_(w, f, 0), w->K, &P_(w, 0, t_now), 1, w->M);
+        if (t_now > 0) w->nav_close[f] = orc_dotw(&H_(w, f, 0), w->K, &P_(w, 0, t_now), 1, w->M);
     }
 }
 void orc_disburse_shares(orc_world *w, const int64_t *funds, int64_t norders, const double *shares)
@@ -645,9 +653,9 @@ static double calc_liquidity(orc_world *w, int64_t k, int64_t col)
     int64_t M = w->M;
     double *wt = (double *)zalloc(8 * M);
     for (int64_t m = 0; m < M; ++m) wt[m] = H_(w, k, m) * P_(w, m, col);
-    double s = sum4(wt, 1, M);
+    double s = sumw(wt, 1, M);
     for (int64_t m = 0; m < M; ++m) wt[m] = (wt[m] / s) * w->impact[m];
-    double liq = sum4(wt, 1, M);
+    double liq = sumw(wt, 1, M);
     free(wt);
     return liq;
 }
@@ -672,7 +680,7 @@ int orc_respawn(orc_world *w, int64_t t, double *buy_values, int64_t *buy_funds,
     const orc_params *p = &w->p;
     int64_t *spawn = (int64_t *)zalloc(8 * K), neggs = 0;
     for (int64_t k = 0; k < K; ++k)
-        if (sum4(&H_(w, k, 0), K, M) == 0.0) spawn[neggs++] = k;       /* :279 */
+        if (sumw(&H_(w, k, 0), K, M) == 0.0) spawn[neggs++] = k;       /* :279 */
     int64_t *pot = (int64_t *)zalloc(8 * N), npot = 0;
     for (int64_t n = 0; n < N; ++n)
         if (A_(w, n, K) > 0.0) pot[npot++] = n;                         /* :281 */
@@ -735,11 +743,11 @@ int orc_respawn(orc_world *w, int64_t t, double *buy_values, int64_t *buy_funds,
         w->log_cols[1][idx_old] = (double)(w->log_rows + 1);
         w->log_cols[4][idx_old] = (double)t;
         /* new row, :311-318 */
-        double fundsize = sum4(bo, 1, M);
+        double fundsize = sumw(bo, 1, M);
         int64_t nst = 0;
         for (int64_t m = 0; m < M; ++m) nst += (bo[m] > 0.0);
         for (int64_t m = 0; m < M; ++m) units[m] = (bo[m] / fundsize) * w->impact[m];
-        double liq = sum4(units, 1, M);
+        double liq = sumw(units, 1, M);
         log_push(w, 0, 0, fundsize, liq, 0, 1, (double)nst);
     }
     free(spawn); free(pot); free(units);
@@ -821,7 +829,7 @@ int orc_reinvest(orc_world *w, int64_t t, int selector, double *buy_values, int6
         }
         emit(w, t, ORC_EV_CHOICE, reinv, choice, injection);
         A_(w, reinv, choice) = injection; A_(w, reinv, K) = 0.0;        /* :358-359 */
-        double fundval = orc_dot4(&H_(w, choice, 0), K, &P_(w, 0, t), 1, M);     /* :360 */
+        double fundval = orc_dotw(&H_(w, choice, 0), K, &P_(w, 0, t), 1, M);     /* :360 */
         double newcapital = fundval + injection;
         for (int64_t n = 0; n < N; ++n) {                               /* :363-366 */
             double sv = S_(w, choice, n) * fundval;

@@ -16,9 +16,11 @@
  * summation order of BLAS/Base.sum (replaced by one canonical order, see below).
  *
  * Canonical FP order (shared by oracle and CUDA engine so that results are bit-identical):
- *   dot4(x,y,n)     = (a0+a1)+(a2+a3),  a_j = fma-chain over i == j (mod 4), ascending, from +0.0
- *   sum4(x,n)       = same tree with a_j += x_i
- *   sumprod4(x,y,n) = same tree with a_j += fl(x_i*y_i)     (reference materialises x.*y first)
+ *   dotw(x,y,n)     : 32 partial fma-chains from +0.0, chain l owning elements 64i+2l and 64i+2l+1
+ *                     (ascending), combined by the xor-butterfly tree 16,8,4,2,1 -- the order a
+ *                     warp produces when it reads a row with 128-bit loads and shuffles
+ *   sumw(x,n)       : same tree with a_l += x_e
+ *   sumprodw(x,y,n) : same tree with a_l += fl(x_e*y_e)     (reference materialises x.*y first)
  *   sums over orders (column sums)      : sequential in order-row order, from +0.0
  *   sums over a fund's investors (stakes): sequential in ascending investor id, from +0.0
  */
@@ -143,7 +145,7 @@ double orc_draw_normal(uint64_t seed, uint32_t rep, uint32_t site, uint32_t a, u
 double orc_draw_uniform(uint64_t seed, uint32_t rep, uint32_t site, uint32_t a, uint32_t b, uint32_t idx);
 uint32_t orc_draw_discrete(uint64_t seed, uint32_t rep, uint32_t site, uint32_t a, uint32_t b,
                            uint32_t idx, uint32_t n);
-double orc_dot4(const double *x, int64_t sx, const double *y, int64_t sy, int64_t n);
+double orc_dotw(const double *x, int64_t sx, const double *y, int64_t sy, int64_t n);
 
 #ifdef __cplusplus
 }

@@ -110,8 +110,8 @@ def lib():
             getattr(L, name).argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_draw_discrete.restype = C.c_uint32
         L.orc_draw_discrete.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
-        L.orc_dot4.restype = C.c_double
-        L.orc_dot4.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]
+        L.orc_dotw.restype = C.c_double
+        L.orc_dotw.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]
         _LIB = L
     return _LIB
 
@@ -351,7 +351,7 @@ def draw_discrete(seed, rep, site, a, b, idx, n):
     return lib().orc_draw_discrete(seed, rep, site, a, b, idx, n)
 
 
-def dot4(x, y):
+def dotw(x, y):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)
-    return lib().orc_dot4(x.ctypes.data, 1, y.ctypes.data, 1, len(x))
+    return lib().orc_dotw(x.ctypes.data, 1, y.ctypes.data, 1, len(x))

@@ -1,0 +1,369 @@
+"""Parity tests proper: the CUDA engine, called through the C ABI (ctypes), against the CPU
+oracle on the same seeded inputs.  Bar (BASELINE.json north_star): discrete outcomes bit-exact;
+FP64 NAVs, prices and flows within 1e-12 relative -- the engine and the oracle share one
+canonical operation order, so these tests demand bit-equality and fall back to 1e-12 nowhere.
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x5EEDFACE12345
+
+
+@pytest.fixture(scope="module")
+def tiny_engine(fsb):
+    eng = fsb.Engine(H.small_params(fsb), 1, keep_history=True)
+    yield eng
+    eng.close()
+
+
+def test_library_loaded_is_in_tree(fsb):
+    import os
+    so = fsb._lib.so_path()
+    assert os.path.exists(so) and "fundstababm.jl_b200/csrc" in so
+    assert fsb._lib.lib().fsb_version() == 100
+
+
+def test_device_draws_bit_exact(tiny_engine, orc):
+    """Philox4x32-10 + deterministic inverse-normal on the device == oracle, bit for bit."""
+    for site, a, b in ((17, 102, 0), (4, 55, 0), (21, 1349, 3), (22, 7, 0)):
+        n = 4096
+        dn = tiny_engine.debug_draws(SEED, 12345, site, a, b, 0, n, 0)
+        du = tiny_engine.debug_draws(SEED, 12345, site, a, b, 0, n, 1)
+        dd = tiny_engine.debug_draws(SEED, 12345, site, a, b, 0, n, 2, 250)
+        on = np.array([orc.draw_normal(SEED, 12345, site, a, b, i) for i in range(n)])
+        ou = np.array([orc.draw_uniform(SEED, 12345, site, a, b, i) for i in range(n)])
+        od = np.array([orc.draw_discrete(SEED, 12345, site, a, b, i, 250) for i in range(n)], dtype=np.float64)
+        assert H.eq(dn, on) and H.eq(du, ou) and H.eq(dd, od)
+    # extreme uniforms exercise all three AS241 branches
+    assert abs(dn).max() > 3.0
+
+
+def test_canonical_dot_bit_exact(tiny_engine, orc):
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 5, 63, 64, 65, 250, 251, 5000):
+        x = rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4, n)
+        y = rng.standard_normal(n)
+        assert tiny_engine.debug_dot(x, y) == orc.dotw(x, y)
+
+
+@pytest.mark.parametrize("shape", [dict(), dict(bigm=10, bigk=5, bign=33), dict(bigm=3, bigk=2, bign=4, portfsizerange=(1, 3)),
+                                   dict(bigm=70, bigk=9, bign=64, portfsizerange=(1, 70))])
+def test_init_device_matches_oracle(fsb, orc, shape):
+    p = H.small_params(fsb, **shape)
+    with fsb.Engine(p, 3, rep_offset=5, keep_history=True) as eng:
+        eng.init_device(SEED)
+        for r in range(3):
+            w = orc.World(p, seed=SEED, rep=5 + r)
+            w.initialise()
+            st = eng.download_state(r)
+            H.assert_state_equal(st, w, fund_value=False)
+            # funds.value right after initialise: column 1 is the capital, burn-in columns are
+            # sum(holdings .* price) in the reference and a fused dot here (<= 1e-12 relative)
+            assert H.eq(st["fund_value"][:, 0], w.fund_value[:, 0])
+            np.testing.assert_allclose(st["fund_value"], w.fund_value, rtol=1e-12, atol=0)
+            w.build_log()
+            H.assert_log_equal(eng.download_log(r), w.log())
+            w.close()
+
+
+@pytest.mark.parametrize("selector", ["probabilistic", "best", "goodenough", "random"])
+@pytest.mark.parametrize("shape", [dict(), dict(bigm=11, bigk=5, bign=50, reviewprobability=0.3),
+                                   dict(bigm=64, bigk=3, bign=12, portfsizerange=(1, 2), reviewprobability=0.5)])
+def test_trajectory_small_worlds(fsb, orc, selector, shape):
+    """Whole runs of small worlds (many respawns, shared funds, odd M): every trace point equal."""
+    p = H.small_params(fsb, **shape)
+    R = 4
+    t0, t1 = p.perfwindow[-1] + 2, p.bigt
+    with fsb.Engine(p, R, rep_offset=100, keep_history=True) as eng:
+        eng.init_device(SEED)
+        for r in range(R):
+            eng.set_trace(r)
+        eng.run(selector=selector)
+        for r in range(R):
+            w = H.oracle_world(orc, p, SEED, 100 + r)
+            assert w.modelrun(selector=selector) == 0
+            w.finalise_fund_value(t1)
+            H.assert_state_equal(eng.download_state(r), w)
+            H.assert_log_equal(eng.download_log(r), w.log())
+            H.assert_trace_equal(eng.download_trace(r), w, (t0, t1))
+            c = eng.download_compact(r)
+            assert H.eq(c["nav_close"], w.nav_close)
+            w.close()
+
+
+def test_upload_path_equals_device_init_path(fsb, orc):
+    """Drop-in mode: upload the reference-layout structs of an initialised world, run, download."""
+    p = H.small_params(fsb)
+    w = H.oracle_world(orc, p, SEED, 7)
+    market, stocks, investors, funds = H.structs_from_world(fsb, w)
+    log = fsb.Func.modelrun(market, stocks, investors, funds, p, "probabilistic", seed=SEED, rep=7, as_dataframe=False)
+    assert w.modelrun(selector="probabilistic") == 0
+    w.finalise_fund_value(p.bigt)
+    st = dict(market=market.value, stock_value=stocks.value, beta=stocks.beta, vol=stocks.vol, impact=stocks.impact,
+              volume=stocks.volume, inv_assets=investors.assets, horizon=investors.horizon,
+              threshold=investors.threshold, holdings=funds.holdings, stakes=funds.stakes, fund_value=funds.value)
+    H.assert_state_equal(st, w)
+    H.assert_log_equal(log, w.log())
+    # the runtime invariant check of src/functions.jl:432-444 gives the same verdict on both
+    ost = H.structs_from_world(fsb, w)
+    assert fsb.Func.boundstest(market, stocks, investors, funds) == fsb.Func.boundstest(*ost)
+    w.close()
+
+
+def test_stop_and_resume_equals_single_run(fsb, orc):
+    p = H.small_params(fsb)
+    t0 = p.perfwindow[-1] + 2
+    with fsb.Engine(p, 2, keep_history=True) as a, fsb.Engine(p, 2, keep_history=True) as b:
+        a.init_device(SEED)
+        b.init_device(SEED)
+        a.run()
+        b.run(t0, 30)
+        b.run(31, 31)
+        b.run(32, p.bigt)
+        for r in range(2):
+            sa, sb = a.download_state(r), b.download_state(r)
+            for k in sa:
+                assert H.eq(sa[k], sb[k]), k
+
+
+def test_ring_history_equals_full_history(fsb):
+    """keep_history=0 (burn-in + ring of W+1 columns) gives the same trajectory as the full history."""
+    p = H.small_params(fsb)
+    with fsb.Engine(p, 3, keep_history=True) as a, fsb.Engine(p, 3, keep_history=False) as b:
+        a.init_device(SEED)
+        b.init_device(SEED)
+        a.run()
+        b.run()
+        for r in range(3):
+            ca, cb = a.download_compact(r), b.download_compact(r)
+            for k in ca:
+                assert H.eq(ca[k], cb[k]), k
+            la, lb = a.download_log(r), b.download_log(r)
+            for k in la:
+                assert H.eq(la[k], lb[k]), k
+
+
+def test_steps_per_launch_is_invisible(fsb):
+    p = H.small_params(fsb)
+    with fsb.Engine(p, 5) as a, fsb.Engine(p, 5, steps_per_launch=7) as b:
+        a.init_device(SEED)
+        b.init_device(SEED)
+        a.run()
+        b.run()
+        for r in range(5):
+            ca, cb = a.download_compact(r), b.download_compact(r)
+            for k in ca:
+                assert H.eq(ca[k], cb[k]), k
+        assert a.stats_raw().tolist() == b.stats_raw().tolist()
+
+
+def test_sharding_invariance(fsb):
+    """Philox counters use GLOBAL replication ids: any sharding gives identical replications and
+    the integer ensemble statistics add up exactly (the N>1 contract of SURVEY.md 8e)."""
+    p = H.small_params(fsb)
+    with fsb.Engine(p, 8) as full, fsb.Engine(p, 3, rep_offset=0) as s0, fsb.Engine(p, 5, rep_offset=3) as s1:
+        for e in (full, s0, s1):
+            e.init_device(SEED)
+            e.run()
+        for r in range(8):
+            cf = full.download_compact(r)
+            cs = s0.download_compact(r) if r < 3 else s1.download_compact(r - 3)
+            for k in cf:
+                assert H.eq(cf[k], cs[k]), k
+        assert H.eq(full.stats_raw(), s0.stats_raw() + s1.stats_raw())
+
+
+def test_dense_tape_equivalence_mode(fsb, orc):
+    """Equivalence mode: the exogenous shocks come from a tape (here produced by numpy, standing in
+    for a Julia recorder) and are fed to both implementations."""
+    p = H.small_params(fsb)
+    rng = np.random.default_rng(11)
+    z_mkt = rng.standard_normal(p.bigt)
+    z_stock = rng.standard_normal((p.bigm, p.bigt))
+    u_review = rng.random((p.bign, p.bigt))
+    w = H.oracle_world(orc, p, SEED, 0)
+    market, stocks, investors, funds = H.structs_from_world(fsb, w)
+    w.set_dense_tape(z_mkt, z_stock, u_review)
+    assert w.modelrun(selector="probabilistic") == 0
+    w.finalise_fund_value(p.bigt)
+    fsb.Func.modelrun(market, stocks, investors, funds, p, "probabilistic", seed=SEED, rep=0,
+                      dense_tape=dict(z_mkt=z_mkt, z_stock=z_stock, u_review=u_review))
+    assert H.eq(stocks.value, w.stock_value) and H.eq(funds.holdings, w.holdings)
+    assert H.eq(funds.value, w.fund_value) and H.eq(investors.assets, w.inv_assets)
+    w.close()
+
+
+def test_event_tape_forces_choices_and_anchors(fsb, orc):
+    """Event tape: replay the oracle's own anchors / portfolio picks / fund choices as a tape."""
+    p = H.small_params(fsb)
+    w = H.oracle_world(orc, p, SEED, 3)
+    market, stocks, investors, funds = H.structs_from_world(fsb, w)
+    assert w.modelrun(selector="probabilistic") == 0
+    w.finalise_fund_value(p.bigt)
+    recs, ordinal, pick_j = [], {}, {}
+    for e in w.trace():
+        t = int(e["t"])
+        if e["kind"] == orc.EV_SPAWN:
+            i = ordinal.get(t, 0)
+            ordinal[t] = i + 1
+            recs.append((fsb._lib.TAPE_ANCHOR, t, i, 0, float(e["b"])))
+            pick_j[t] = (i, 0)
+        elif e["kind"] == orc.EV_SPAWN_N:
+            recs.append((fsb._lib.TAPE_RPSIZE, t, pick_j[t][0], 0, float(e["b"])))
+        elif e["kind"] == orc.EV_PICK:
+            i, j = pick_j[t]
+            recs.append((fsb._lib.TAPE_RPPICK, t, i, j, float(e["b"])))
+            pick_j[t] = (i, j + 1)
+        elif e["kind"] == orc.EV_CHOICE:
+            recs.append((fsb._lib.TAPE_CHOICE_IDX, t, int(e["a"]), 0, float(e["b"])))
+    assert len(recs) > 10
+    # a different seed: only the shocks/reviews come from Philox, so feed those as a dense tape too
+    T, M, N = p.bigt, p.bigm, p.bign
+    z_mkt = np.array([0.0] + [orc.draw_normal(SEED, 3, 16, t, 0, 0) for t in range(1, T + 1)])[1:]
+    z_stock = np.array([[orc.draw_normal(SEED, 3, 17, t, 0, m) for t in range(1, T + 1)] for m in range(M)])
+    u_review = np.array([[orc.draw_uniform(SEED, 3, 18, t, 0, n) for t in range(1, T + 1)] for n in range(N)])
+    fsb.Func.modelrun(market, stocks, investors, funds, p, "random", seed=999, rep=77,
+                      dense_tape=dict(z_mkt=z_mkt, z_stock=z_stock, u_review=u_review), event_tape=recs)
+    assert H.eq(stocks.value, w.stock_value) and H.eq(funds.holdings, w.holdings)
+    assert H.eq(investors.assets, w.inv_assets) and H.eq(funds.stakes, w.stakes)
+    w.close()
+
+
+def test_default_shape_trajectories(fsb, orc):
+    """BASELINE configs[0]/[1] shape: K=M=250, N=1000, T=1350, full 1249-step horizon."""
+    p = fsb.Params.default()
+    R = 3
+    with fsb.Engine(p, R, rep_offset=4000, keep_history=True) as eng:
+        eng.init_device(SEED)
+        eng.set_trace(1)
+        eng.run()
+        for r in range(R):
+            w = H.oracle_world(orc, p, SEED, 4000 + r, trace=(r == 1))
+            assert w.modelrun() == 0
+            w.finalise_fund_value(p.bigt)
+            H.assert_state_equal(eng.download_state(r), w)
+            H.assert_log_equal(eng.download_log(r), w.log())
+            if r == 1:
+                H.assert_trace_equal(eng.download_trace(r), w, (p.perfwindow[-1] + 2, p.bigt))
+            w.close()
+
+
+def test_batch_properties_and_sampled_oracle(fsb, orc):
+    """A larger batch (ring history): size-independent invariants for every replication plus
+    bit-exact comparison of a sample against the oracle."""
+    p = fsb.Params.default()
+    R, t_last = 512, 160
+    with fsb.Engine(p, R, rep_offset=10_000) as eng:
+        eng.init_device(SEED)
+        eng.run(t_last=t_last)
+        assert not eng.rep_status().any()
+        st = eng.stats()[0]
+        assert st["replications"] == R and st["error_replications"] == 0
+        assert st["replication_steps"] == R * (t_last - 101)
+        assert st["reinvestments"] <= st["divestments"] <= st["reviews"]
+        assert st["funds_ever"] == R * p.bigk + st["liquidations"]
+        assert st["flow_hist"].sum() == st["replication_steps"]
+        for r in list(range(0, R, 37)) + [R - 1]:
+            c = eng.download_compact(r)
+            assert ((c["inv_fund"] >= 0) & (c["inv_fund"] <= p.bigk)).all()
+            assert not ((c["inv_fund"] == p.bigk) & (c["inv_amount"] > 0)).any()   # no cash left at step end
+            sums = np.bincount(c["inv_fund"], weights=c["inv_stake"], minlength=p.bigk + 1)[: p.bigk]
+            if not np.isnan(c["price_now"]).any():
+                np.testing.assert_allclose(sums[sums > 0], 1.0, rtol=0, atol=1e-12)   # stakes sum to one per fund
+            assert not (c["holdings"] < 0).any() and not (c["price_now"] <= 0).any()
+        for r in (0, 255, 511):
+            w = H.oracle_world(orc, p, SEED, 10_000 + r, trace=False)
+            assert w.modelrun(t_last=t_last) == 0
+            c = eng.download_compact(r)
+            assert H.eq(c["holdings"], w.holdings)
+            assert H.eq(c["price_now"], w.stock_value[:, t_last - 1])
+            assert H.eq(c["nav_close"], w.nav_close)
+            H.assert_log_equal(eng.download_log(r), w.log())
+            w.close()
+
+
+def test_statistics_match_oracle_logs(fsb, orc):
+    p = H.small_params(fsb)
+    R = 6
+    with fsb.Engine(p, R) as eng:
+        eng.init_device(SEED)
+        eng.run()
+        st = eng.stats()[0]
+    liq, rows, floors, divs, revs, reinv = 0, 0, 0, 0, 0, 0
+    fail_hist = np.zeros(p.bigt + 1, dtype=np.int64)
+    for r in range(R):
+        w = H.oracle_world(orc, p, SEED, r)
+        assert w.modelrun() == 0
+        log, tr = w.log(), w.trace()
+        liq += int(log["liquidated"].sum())
+        rows += len(log["liquidated"])
+        floors += w.floor_hits()
+        revs += int((tr["kind"] == orc.EV_REVIEWER).sum())
+        divs += int((tr["kind"] == orc.EV_DIVEST).sum())
+        reinv += int((tr["kind"] == orc.EV_CHOICE).sum())
+        np.add.at(fail_hist, log["failtime"][log["liquidated"] == 1], 1)
+        w.close()
+    assert (st["liquidations"], st["funds_ever"], st["floor_hits"]) == (liq, rows, floors)
+    assert (st["reviews"], st["divestments"], st["reinvestments"]) == (revs, divs, reinv)
+    assert H.eq(st["failtime_hist"], fail_hist)
+    assert st["liquidations_per_replication_hist"].sum() == R and st["market_drawdown_hist"].sum() == R
+
+
+def test_calibrate_sweep_points_are_independent(fsb):
+    """configs[4] in miniature: a sweep engine gives, per point, the statistics a single-point
+    engine gives for the same global replication ids."""
+    base = H.small_params(fsb)
+    pts = fsb.grid(base, thresholdstd=(0.02, 0.1), impactscale=(1.0, 4.0))
+    reps = 5
+    stats = fsb.calibrate(pts, reps, seed=SEED)
+    assert len(stats) == 4
+    for i, pt in enumerate(pts):
+        with fsb.Engine([base] * i + [pt], reps, rep_offset=i * reps, reps_per_point=reps) as eng:
+            eng.init_device(SEED)
+            eng.run()
+            single = eng.stats()[i]
+        for k, v in stats[i].items():
+            assert H.eq(v, single[k]), (i, k)
+    assert stats[0]["divestments"] != stats[1]["divestments"] or stats[0]["liquidations"] != stats[2]["liquidations"]
+
+
+def test_error_behaviour(fsb):
+    p = H.small_params(fsb)
+    L = fsb._lib
+    with fsb.Engine(p, 2, keep_history=True) as eng:
+        with pytest.raises(L.FsbError) as ei:      # no state yet
+            eng.run()
+        assert ei.value.code == L.ERR_BAD_STATE
+        eng.init_device(SEED)
+        assert L.lib().fsb_run(eng.handle, 9, 20, 7, 0) == L.ERR_BAD_SELECTOR      # Q9
+        assert L.lib().fsb_run(eng.handle, 3, 20, 2, 0) == L.ERR_RANGE
+        with pytest.raises(ValueError):
+            fsb.Func.modelrun(*fsb.Types.allocate(p), p)                            # default "bestperformer" (Q9)
+        with pytest.raises(L.FsbError) as ei:
+            eng.download_state(5)
+        assert ei.value.code == L.ERR_RANGE
+    with fsb.Engine(p, 1) as eng:
+        eng.init_device(SEED)
+        with pytest.raises(L.FsbError) as ei:
+            eng.download_state(0)
+        assert ei.value.code == L.ERR_NO_HISTORY
+    # capacity overflow is an error, never a silent drop
+    with fsb.Engine(H.small_params(fsb, reviewprobability=0.9), 2, event_capacity=8) as eng:
+        eng.init_device(SEED)
+        with pytest.raises(L.FsbError) as ei:
+            eng.run()
+        assert ei.value.code == L.ERR_REPLICATION
+        assert (eng.rep_status() & L.REP_EVENT_OVERFLOW).all()
+    # an uploaded state with two positions for one investor is rejected
+    market, stocks, investors, funds = fsb.Types.allocate(p)
+    investors.assets[0, 0] = 1.0
+    investors.assets[0, 1] = 1.0
+    investors.horizon[:] = 1
+    with fsb.Engine(p, 1, keep_history=True) as eng:
+        with pytest.raises(L.FsbError) as ei:
+            eng.upload_state(0, market, stocks, investors, funds)
+        assert ei.value.code == L.ERR_BAD_STATE
