@@ -1,0 +1,27 @@
+"""Small driver for ncu: a few launches of the per-step kernel at the default shape."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from __graft_entry__ import load_package  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--reps", type=int, default=4096)
+ap.add_argument("--steps", type=int, default=8)
+ap.add_argument("--t0", type=int, default=102)
+ap.add_argument("--steps-per-launch", type=int, default=1)
+ap.add_argument("--blocks-per-sm", type=int, default=0)
+ap.add_argument("--block-threads", type=int, default=0)
+a = ap.parse_args()
+fsb = load_package()
+p = fsb.Params.default()
+with fsb.Engine(p, a.reps, steps_per_launch=a.steps_per_launch, blocks_per_sm=a.blocks_per_sm,
+                block_threads=a.block_threads) as eng:
+    eng.init_device(7)
+    if a.t0 > 102:
+        eng.run(102, a.t0 - 1)
+    eng.run(a.t0, a.t0 + a.steps - 1)
+    ms, _, n = eng.last_run_timing()
+    print(f"reps={a.reps} steps={a.steps} launches={n} total_ms={ms:.3f} per_launch_ms={ms / n:.4f} "
+          f"fund_steps_per_s={a.reps * p.bigk * a.steps / (ms * 1e-3):.4e}")
