@@ -205,11 +205,12 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     // shared memory: shrink the pass-2 column chunk until the layout fits
     int smem_max = 0;
     CU(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
-    d.cmax = 8;
-    SmemLayout L = make_layout(d.K, d.Mp, d.cap_ev, d.cmax, e->block / 32);
-    while (L.bytes + 64 > std::min(smem_max, 100 * 1024) && d.cmax > 1) {
-        d.cmax >>= 1;
-        L = make_layout(d.K, d.Mp, d.cap_ev, d.cmax, e->block / 32);
+    if (d.K >= 32768) { delete e; return fail(FSB_ERR_BAD_PARAMS, "bigk must be < 32768 (16-bit fund ids in shared memory)"); }
+    d.cmax = kMaxCols;
+    SmemLayout L = make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax, e->block / 32);
+    while (L.bytes + 64 > std::min(smem_max, 74 * 1024) && d.cmax > 1) {  // aim at 3 CTAs per SM
+        --d.cmax;
+        L = make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax, e->block / 32);
     }
     if (L.bytes + 64 > smem_max) { delete e; return fail(FSB_ERR_BAD_PARAMS, "shapes need %d bytes of shared memory per CTA (> %d)", L.bytes, smem_max); }
     e->smem_bytes = L.bytes;
@@ -252,7 +253,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     A(pos, R * d.N); A(horizon, R * d.N);
     A(stake, R * d.N); A(amount, R * d.N); A(threshold, R * d.N);
     A(nav_open, R * d.K); A(nav_close, R * d.K); A(cap0, R * d.K);
-    A(hzero, R * d.K); A(live_row, R * d.K);
+    A(hzero, R * d.K); A(stakeless, R * d.K); A(live_row, R * d.K);
     A(log_n, R);
     A(log_liquidated, R * d.cap_log); A(log_replacedby, R * d.cap_log); A(log_failtime, R * d.cap_log);
     A(log_ninv, R * d.cap_log); A(log_nstocks, R * d.cap_log);
@@ -398,6 +399,14 @@ extern "C" int32_t fsb_upload_state(fsb_engine *e, int64_t rep, const double *ma
     std::copy(beta, beta + M, b.begin()); std::copy(vol, vol + M, v.begin()); std::copy(impact, impact + M, im.begin());
     std::vector<int> live(K);
     for (int k = 0; k < K; ++k) live[k] = k;
+    // respawn trigger of functions.jl:471: sum(stakes[k,:]) == 0, summed in ascending investor order
+    std::vector<unsigned char> stakeless(K);
+    for (int k = 0; k < K; ++k) {
+        double c = 0.0;
+        for (int n = 0; n < N; ++n)
+            if (pos[n] == k) c = c + stake[n];
+        stakeless[k] = (c == 0.0) ? 1 : 0;
+    }
     double peak = 0.0;
     for (int t = 1; t <= T; ++t) peak = std::max(peak, market[t - 1]);
     const double zero = 0.0;
@@ -412,7 +421,7 @@ extern "C" int32_t fsb_upload_state(fsb_engine *e, int64_t rep, const double *ma
     UP(d.pos + rep * N, pos.data(), N * 4); UP(d.horizon + rep * N, hz.data(), N * 4);
     UP(d.stake + rep * N, stake.data(), N * 8); UP(d.amount + rep * N, amount.data(), N * 8); UP(d.threshold + rep * N, thr.data(), N * 8);
     UP(d.cap0 + rep * K, cap0.data(), K * 8);
-    UP(d.hzero + rep * K, hzero.data(), K); UP(d.live_row + rep * K, live.data(), K * 4);
+    UP(d.hzero + rep * K, hzero.data(), K); UP(d.stakeless + rep * K, stakeless.data(), K); UP(d.live_row + rep * K, live.data(), K * 4);
     UP(d.mkt_peak + rep, &mk[mslot(d, static_cast<int>(std::max<int64_t>(t_last, 1)))], 8);
     UP(d.mkt_dd + rep, &zero, 8);
     UP(d.err + rep, &izero, 4); UP(d.log_n + rep, &izero, 4);

@@ -94,6 +94,14 @@ __global__ void __launch_bounds__(256) fsb_init_kernel(const DevState s)
     __syncthreads();
     // fundstakeinit! (:111-117)
     for (int n = tid; n < N; n += NT) stake[n] = amount[n] / capk[pos[n]];
+    __syncthreads();
+    // stakeless[k] = (sum(stakes[k,:]) == 0), the respawn trigger of :471, kept incrementally by the step kernel
+    for (int k = tid; k < K; k += NT) {
+        double c2 = 0.0;
+        for (int n = 0; n < N; ++n)
+            if (pos[n] == k) c2 = c2 + stake[n];
+        s.stakeless[r * K + k] = (c2 == 0.0) ? 1 : 0;
+    }
     // fundholdinit! (:119-133): each thread owns a fund's row, picks applied in draw order
     for (int k = tid; k < K; k += NT) {
         const int nk = pt.psize_lo + static_cast<int>(draw_discrete(rng, SITE_INIT_PSIZE, 0, 0, static_cast<uint32_t>(k), static_cast<uint32_t>(pt.psize_hi - pt.psize_lo + 1)));
@@ -117,35 +125,37 @@ __global__ void __launch_bounds__(256) fsb_build_log_kernel(const DevState s)
 {
     const long long r = blockIdx.x;
     const int K = s.K, M = s.M, N = s.N, Mp = s.Mp;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, j = lane & 7, ngroups = blockDim.x >> 3, gid = threadIdx.x >> 3;
     const double *H = s.H + r * s.h_stride;
     const double *P1 = s.P + r * s.p_stride;  // column 1
     const double *impact = s.impact + r * Mp;
     const int *pos = s.pos + r * N;
     const double *stake = s.stake + r * N;
     const long long lb = r * s.cap_log;
-    for (int k = warp; k < K; k += nwarps) {
-        const double *row = H + static_cast<long long>(k) * Mp;
+    for (int kb = (threadIdx.x >> 5) * 4; kb < K; kb += ngroups) {  // warp-uniform: 4 funds per warp
+        const int k = kb + (lane >> 3);
+        const bool on = k < K;
+        const double *row = H + static_cast<long long>(on ? k : kb) * Mp;
         // calc_liquidity (:324-330)
+        const double tot = sumprod8(row, P1, M, j, on);
         double acc = 0.0;
         int nst = 0;
-        for (int e = 2 * lane; e < M; e += 64) {
-            acc = acc + row[e] * P1[e];
-            nst += (row[e] > 0.0);
-            if (e + 1 < M) { acc = acc + row[e + 1] * P1[e + 1]; nst += (row[e + 1] > 0.0); }
-        }
-        const double tot = warp_tree(acc);
-        acc = 0.0;
-        for (int e = 2 * lane; e < M; e += 64) {
-            acc = acc + ((row[e] * P1[e]) / tot) * impact[e];
-            if (e + 1 < M) acc = acc + ((row[e + 1] * P1[e + 1]) / tot) * impact[e + 1];
-        }
-        const double liq = warp_tree(acc);
-        nst = __reduce_add_sync(0xffffffffu, nst);
+        if (on)
+            for (int e = 2 * j; e < M; e += 16) {
+                acc = acc + ((row[e] * P1[e]) / tot) * impact[e];
+                nst += (row[e] > 0.0);
+                if (e + 1 < M) { acc = acc + ((row[e + 1] * P1[e + 1]) / tot) * impact[e + 1]; nst += (row[e + 1] > 0.0); }
+            }
+        const double liq = tree8(acc);
         int ninv = 0;
-        for (int n = lane; n < N; n += 32) ninv += (pos[n] == k && stake[n] > 0.0);
-        ninv = __reduce_add_sync(0xffffffffu, ninv);
-        if (lane == 0) {
+        if (on)
+            for (int n = j; n < N; n += 8) ninv += (pos[n] == k && stake[n] > 0.0);
+#pragma unroll
+        for (int sft = 4; sft >= 1; sft >>= 1) {
+            nst += __shfl_xor_sync(0xffffffffu, nst, sft);
+            ninv += __shfl_xor_sync(0xffffffffu, ninv, sft);
+        }
+        if (on && j == 0) {
             s.log_liquidated[lb + k] = 0;
             s.log_replacedby[lb + k] = 0;
             s.log_size[lb + k] = s.cap0[r * K + k];
@@ -156,6 +166,7 @@ __global__ void __launch_bounds__(256) fsb_build_log_kernel(const DevState s)
             s.live_row[r * K + k] = k;
         }
     }
+    (void)gid;
     if (threadIdx.x == 0) s.log_n[r] = K;
 }
 
@@ -221,16 +232,19 @@ __global__ void fsb_stats_kernel(const DevState s, unsigned long long *out, long
 // ------------------------------------------------------------------------------------------------
 __global__ void fsb_fund_value_kernel(const DevState s, long long r, int t_now, double *out)
 {
-    const int lane = threadIdx.x & 31;
-    const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const int j = threadIdx.x & 7;
+    const long long wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = (gridDim.x * blockDim.x) >> 5;
     const double *H = s.H + r * s.h_stride;
     const double *P = s.P + r * s.p_stride;
-    for (long long q = wglobal; q < static_cast<long long>(s.K) * s.T; q += nw) {
-        const int k = static_cast<int>(q / s.T), col = static_cast<int>(q % s.T);  // col 0-based
-        double v = dotw(H + static_cast<long long>(k) * s.Mp, P + static_cast<long long>(col) * s.Mp, s.M, lane);
+    const long long total = static_cast<long long>(s.K) * s.T;
+    for (long long qb = wglobal * 4; qb < total; qb += nw * 4) {  // warp-uniform: 4 (fund, column) pairs per warp
+        const long long q = qb + ((threadIdx.x & 31) >> 3);
+        const bool on = q < total;
+        const int k = on ? static_cast<int>(q / s.T) : 0, col = on ? static_cast<int>(q % s.T) : 0;  // col 0-based
+        double v = dot8(H + static_cast<long long>(k) * s.Mp, P + static_cast<long long>(col) * s.Mp, s.M, j, on);
         if (col == t_now - 1) v = s.nav_close[r * s.K + k];
-        if (lane == 0) out[q] = v;
+        if (on && j == 0) out[q] = v;
     }
 }
 
@@ -251,7 +265,7 @@ __global__ void fsb_debug_draws_kernel(unsigned long long seed, uint32_t rep, ui
 
 __global__ void fsb_debug_dot_kernel(const double *x, const double *y, int n, double *out)
 {
-    const double v = dotw(x, y, n, threadIdx.x & 31);
+    const double v = dot8(x, y, n, threadIdx.x & 7);
     if (threadIdx.x == 0) *out = v;
 }
 

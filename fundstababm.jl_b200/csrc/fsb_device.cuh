@@ -165,53 +165,97 @@ __device__ __forceinline__ uint32_t draw_discrete(const Rng &g, uint32_t site, u
     return __umulhi(word_of(w, idx & 3), n);
 }
 
-// ---- canonical warp reductions -------------------------------------------------------------
-// lane l owns elements 64i+2l, 64i+2l+1 (ascending i) as one chain from +0.0; the 32 chains are
-// combined by the xor butterfly 16,8,4,2,1 (a+b == b+a bit-exactly, so every lane ends with the
-// same value).  All 32 lanes must call.
-__device__ __forceinline__ double warp_tree(double a)
+// ---- canonical reductions: groups of 8 lanes ---------------------------------------------------
+// A row of n doubles is read as double2 words; lane j (0..7) of a group owns words j, j+8, j+16, ...
+// (elements 16i+2j, 16i+2j+1, ascending) as one chain from +0.0; the 8 chains are combined by the
+// xor butterfly 4,2,1 (a+b == b+a bit-exactly, so every lane of the group ends with the same value).
+// A warp holds 4 independent groups (4 rows at once, 128 contiguous bytes per group and load).
+// All 32 lanes must call; `on` masks the loads of a group that has no row.
+__device__ __forceinline__ double tree8(double a)
 {
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) a = a + __shfl_xor_sync(0xffffffffu, a, s);
+    a = a + __shfl_xor_sync(0xffffffffu, a, 4);
+    a = a + __shfl_xor_sync(0xffffffffu, a, 2);
+    a = a + __shfl_xor_sync(0xffffffffu, a, 1);
     return a;
 }
 
-// x: 16-byte aligned row with an even number of allocated elements >= n; y likewise
-__device__ __forceinline__ double dotw(const double *__restrict__ x, const double *__restrict__ y, int n, int lane)
+// x, y: 16-byte aligned rows with an even number of allocated elements >= n
+__device__ __forceinline__ double dot8(const double *x, const double *y, int n, int j, bool on = true)
 {
     double acc = 0.0;
-    const double2 *x2 = reinterpret_cast<const double2 *>(x);
-    const double2 *y2 = reinterpret_cast<const double2 *>(y);
-    for (int e = 2 * lane; e < n; e += 64) {
-        const double2 xv = x2[e >> 1], yv = y2[e >> 1];
-        acc = fma(xv.x, yv.x, acc);
-        if (e + 1 < n) acc = fma(xv.y, yv.y, acc);
+    if (on) {
+        const double2 *x2 = reinterpret_cast<const double2 *>(x);
+        const double2 *y2 = reinterpret_cast<const double2 *>(y);
+        for (int e = 2 * j; e < n; e += 16) {
+            const double2 xv = x2[e >> 1], yv = y2[e >> 1];
+            acc = fma(xv.x, yv.x, acc);
+            if (e + 1 < n) acc = fma(xv.y, yv.y, acc);
+        }
     }
-    return warp_tree(acc);
+    return tree8(acc);
 }
-__device__ __forceinline__ double sumw(const double *__restrict__ x, int n, int lane)
+__device__ __forceinline__ double sum8(const double *x, int n, int j, bool on = true)
 {
     double acc = 0.0;
-    const double2 *x2 = reinterpret_cast<const double2 *>(x);
-    for (int e = 2 * lane; e < n; e += 64) {
-        const double2 xv = x2[e >> 1];
-        acc = acc + xv.x;
-        if (e + 1 < n) acc = acc + xv.y;
+    if (on) {
+        const double2 *x2 = reinterpret_cast<const double2 *>(x);
+        for (int e = 2 * j; e < n; e += 16) {
+            const double2 xv = x2[e >> 1];
+            acc = acc + xv.x;
+            if (e + 1 < n) acc = acc + xv.y;
+        }
     }
-    return warp_tree(acc);
+    return tree8(acc);
 }
-__device__ __forceinline__ double sumprodw(const double *__restrict__ x, const double *__restrict__ y, int n, int lane)
+__device__ __forceinline__ double sumprod8(const double *x, const double *y, int n, int j, bool on = true)
 {
     double acc = 0.0;
-    const double2 *x2 = reinterpret_cast<const double2 *>(x);
-    const double2 *y2 = reinterpret_cast<const double2 *>(y);
-    for (int e = 2 * lane; e < n; e += 64) {
-        const double2 xv = x2[e >> 1], yv = y2[e >> 1];
-        acc = acc + xv.x * yv.x;
-        if (e + 1 < n) acc = acc + xv.y * yv.y;
+    if (on) {
+        const double2 *x2 = reinterpret_cast<const double2 *>(x);
+        const double2 *y2 = reinterpret_cast<const double2 *>(y);
+        for (int e = 2 * j; e < n; e += 16) {
+            const double2 xv = x2[e >> 1], yv = y2[e >> 1];
+            acc = acc + xv.x * yv.x;
+            if (e + 1 < n) acc = acc + xv.y * yv.y;
+        }
     }
-    return warp_tree(acc);
+    return tree8(acc);
 }
+
+// ---- asynchronous-copy helpers (TMA unit, sm_90+) ----------------------------------------------
+__device__ __forceinline__ void l2_prefetch_bulk(const void *gptr, unsigned bytes)  // bytes % 16 == 0
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy completing on an mbarrier; dst/src 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Julia's isless on Float64: total order, -0.0 < +0.0, NaN last
 __device__ __forceinline__ bool jl_isless(double a, double b)

@@ -43,6 +43,7 @@ struct DevState {
     // fund
     double *nav_open, *nav_close, *cap0;  // [R][K]
     unsigned char *hzero;                 // [R][K] holdings row is all zero
+    unsigned char *stakeless;             // [R][K] sum(stakes[k,:]) == 0 (respawn trigger, functions.jl:471)
     int *live_row;                        // [R][K] log row currently describing slot k
     // liquidation log, functions.jl:452-456
     int *log_n;                                              // [R]

@@ -185,31 +185,33 @@ uint32_t orc_draw_discrete(uint64_t seed, uint32_t rep, uint32_t site, uint32_t 
 /* ------------------------------------------------------------------------------------------
  * canonical reductions
  * ---------------------------------------------------------------------------------------- */
-/* lane-strided partial chains (lane l of 32 owns elements 64i+2l, 64i+2l+1, ascending) followed by
- * the xor-butterfly tree 16,8,4,2,1 -- the order a warp reading a row with 128-bit loads produces */
-static double warp_tree(double a[32])
+/* 8 partial chains (chain j owns elements 16i+2j, 16i+2j+1, ascending, from +0.0) followed by the
+ * xor-butterfly tree 4,2,1 -- the order a group of 8 GPU lanes reading a row with 128-bit loads
+ * produces (the engine maps 4 such groups, i.e. 4 rows, onto one warp) */
+#define ORC_CHAINS 8
+static double chain_tree(double a[ORC_CHAINS])
 {
-    for (int s = 16; s >= 1; s >>= 1)
+    for (int s = ORC_CHAINS / 2; s >= 1; s >>= 1)
         for (int l = 0; l < s; ++l) a[l] = a[l] + a[l + s];
     return a[0];
 }
 double orc_dotw(const double *x, int64_t sx, const double *y, int64_t sy, int64_t n)
 {
-    double a[32] = { 0.0 };
-    for (int64_t e = 0; e < n; ++e) { int l = (int)((e & 63) >> 1); a[l] = fma(x[e * sx], y[e * sy], a[l]); }
-    return warp_tree(a);
+    double a[ORC_CHAINS] = { 0.0 };
+    for (int64_t e = 0; e < n; ++e) { int l = (int)((e & (2 * ORC_CHAINS - 1)) >> 1); a[l] = fma(x[e * sx], y[e * sy], a[l]); }
+    return chain_tree(a);
 }
 static double sumw(const double *x, int64_t sx, int64_t n)
 {
-    double a[32] = { 0.0 };
-    for (int64_t e = 0; e < n; ++e) { int l = (int)((e & 63) >> 1); a[l] = a[l] + x[e * sx]; }
-    return warp_tree(a);
+    double a[ORC_CHAINS] = { 0.0 };
+    for (int64_t e = 0; e < n; ++e) { int l = (int)((e & (2 * ORC_CHAINS - 1)) >> 1); a[l] = a[l] + x[e * sx]; }
+    return chain_tree(a);
 }
 static double sumprodw(const double *x, int64_t sx, const double *y, int64_t sy, int64_t n)
 {
-    double a[32] = { 0.0 };
-    for (int64_t e = 0; e < n; ++e) { int l = (int)((e & 63) >> 1); double p = x[e * sx] * y[e * sy]; a[l] = a[l] + p; }
-    return warp_tree(a);
+    double a[ORC_CHAINS] = { 0.0 };
+    for (int64_t e = 0; e < n; ++e) { int l = (int)((e & (2 * ORC_CHAINS - 1)) >> 1); double p = x[e * sx] * y[e * sy]; a[l] = a[l] + p; }
+    return chain_tree(a);
 }
 
 /* Julia's isless for Float64: total order, -0.0 < +0.0, NaN last */

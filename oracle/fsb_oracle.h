@@ -16,9 +16,9 @@
  * summation order of BLAS/Base.sum (replaced by one canonical order, see below).
  *
  * Canonical FP order (shared by oracle and CUDA engine so that results are bit-identical):
- *   dotw(x,y,n)     : 32 partial fma-chains from +0.0, chain l owning elements 64i+2l and 64i+2l+1
- *                     (ascending), combined by the xor-butterfly tree 16,8,4,2,1 -- the order a
- *                     warp produces when it reads a row with 128-bit loads and shuffles
+ *   dotw(x,y,n)     : 8 partial fma-chains from +0.0, chain j owning elements 16i+2j and 16i+2j+1
+ *                     (ascending), combined by the xor-butterfly tree 4,2,1 -- the order a group
+ *                     of 8 GPU lanes produces when it reads a row with 128-bit loads and shuffles
  *   sumw(x,n)       : same tree with a_l += x_e
  *   sumprodw(x,y,n) : same tree with a_l += fl(x_e*y_e)     (reference materialises x.*y first)
  *   sums over orders (column sums)      : sequential in order-row order, from +0.0
