@@ -248,12 +248,16 @@ def main():
     eng.stats_raw()  # warms NCCL up (the one collective) outside the timed region
     # ---- warm-up (W untimed steps) ------------------------------------------------------------
     if args.warmup:
-        eng.run(t_first, t_first + args.warmup - 1)
+        eng.run_async(t_first, t_first + args.warmup - 1)
+        eng.sync()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     t0 = time.perf_counter()
-    eng.run(t_first + args.warmup, t_first + total_days - 1)      # EXACTLY K steps, device-timed inside
+    # EXACTLY K steps, device-timed inside; a replication the model itself stops (Q6: functions.jl:282
+    # would throw) is frozen and counted in checks.error_replications, it does not abort the batch
+    eng.run_async(t_first + args.warmup, t_first + total_days - 1)
+    eng.sync()
     stats = eng.stats_raw()                                       # includes the single NCCL allreduce
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)

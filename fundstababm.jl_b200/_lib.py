@@ -33,6 +33,7 @@ EXPORTS = (
     "fsb_sync", "fsb_download_state", "fsb_download_compact", "fsb_download_log", "fsb_download_trace",
     "fsb_rep_status", "fsb_comm_unique_id", "fsb_comm_init_rank", "fsb_comm_init_all", "fsb_stats", "fsb_stats_all",
     "fsb_stats_words_per_point", "fsb_last_run_timing", "fsb_device_bytes", "fsb_debug_draws", "fsb_debug_dot",
+    "fsb_debug_phase_cycles",
 )
 
 
@@ -67,7 +68,8 @@ class FsbError(RuntimeError):
 
 
 def so_path() -> str:
-    return _build.SO
+    # FSB_LIB: an alternative build of the same library (kernel experiments under scripts/), never a fallback
+    return os.environ.get("FSB_LIB") or _build.SO
 
 
 def lib():
@@ -115,6 +117,7 @@ def lib():
         L.fsb_debug_draws.argtypes = [vp, u64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, i32, i32,
                                       C.c_uint32, vp]
         L.fsb_debug_dot.argtypes = [vp, vp, vp, i64, vp]
+        L.fsb_debug_phase_cycles.argtypes = [vp, vp, i32]
         _LIB = L
     return _LIB
 

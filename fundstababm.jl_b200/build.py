@@ -29,7 +29,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or needs_build():
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+        extra = os.environ.get("FSB_NVCC_EXTRA", "").split()  # e.g. -DFSB_PHASE_TIMING for scripts/phase_cycles.py
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or res.returncode != 0:
             print(res.stdout)

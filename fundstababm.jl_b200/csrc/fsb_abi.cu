@@ -90,6 +90,7 @@ struct fsb_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int grid = 0, block = 256, smem_bytes = 0, init_smem = 0;
     int launch_parity = 0;
+    bool fast = false;
     bool log_built = false, state_set = false;
     int64_t t_done = 0;  // last simulated t (0 = none since init/upload)
     int64_t words_per_point = 0;
@@ -215,11 +216,15 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     if (L.bytes + 64 > smem_max) { delete e; return fail(FSB_ERR_BAD_PARAMS, "shapes need %d bytes of shared memory per CTA (> %d)", L.bytes, smem_max); }
     e->smem_bytes = L.bytes;
     e->init_smem = (d.W + 2 + d.K) * 8;
-    CU(cudaFuncSetAttribute(fsb_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_bytes));
+    // FAST kernel: column pitch 256 doubles at compile time (192 < Mp <= 256 and K <= 256: the default shape)
+    e->fast = (L.cp == 256 && L.cpk == 256);
+    CU(cudaFuncSetAttribute(fsb_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_bytes));
+    CU(cudaFuncSetAttribute(fsb_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_bytes));
     if (e->init_smem > 48 * 1024) CU(cudaFuncSetAttribute(fsb_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->init_smem));
     int sms = 0, occ = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fsb_step_kernel, e->block, e->smem_bytes));
+    if (e->fast) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fsb_step_kernel<true>, e->block, e->smem_bytes));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fsb_step_kernel<false>, e->block, e->smem_bytes));
     if (occ < 1) { delete e; return fail(FSB_ERR_CUDA, "step kernel cannot be resident (smem %d)", e->smem_bytes); }
     if (cfg->blocks_per_sm > 0) occ = std::min(occ, cfg->blocks_per_sm);
     e->grid = static_cast<int>(std::min<long long>(d.R, static_cast<long long>(sms) * occ));
@@ -542,7 +547,8 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
         const int spl = std::max(1, e->cfg.steps_per_launch);
         for (int64_t t = t_first; t <= t_last; t += spl) {
             StepArgs a{static_cast<int>(t), static_cast<int>(std::min<int64_t>(spl, t_last - t + 1)), selector, flags};
-            fsb_step_kernel<<<e->grid, e->block, e->smem_bytes, e->stream>>>(d, a, e->launch_parity);
+            if (e->fast) fsb_step_kernel<true><<<e->grid, e->block, e->smem_bytes, e->stream>>>(d, a, e->launch_parity);
+            else fsb_step_kernel<false><<<e->grid, e->block, e->smem_bytes, e->stream>>>(d, a, e->launch_parity);
             e->launch_parity ^= 1;
             ++e->last_launches;
         }
@@ -849,6 +855,25 @@ extern "C" int32_t fsb_stats_all(fsb_engine **engines, int32_t n, uint64_t *out)
 }
 
 // ---- debug --------------------------------------------------------------------------------------
+// per-phase cycle counters of the step kernel (all zero unless built with -DFSB_PHASE_TIMING); reset = 1 clears them
+extern "C" int32_t fsb_debug_phase_cycles(fsb_engine *e, uint64_t out[32], int32_t reset)
+{
+    if (!e || !out) return fail(FSB_ERR_BAD_PARAMS, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < 32; ++i) out[i] = 0;
+#ifdef FSB_PHASE_TIMING
+    CU(cudaMemcpyFromSymbol(out, g_phase_cycles, 32 * sizeof(unsigned long long)));
+    if (reset) {
+        unsigned long long z[32] = {0};
+        CU(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)));
+    }
+#else
+    (void)reset;
+#endif
+    return FSB_OK;
+}
+
 extern "C" int32_t fsb_debug_draws(fsb_engine *e, uint64_t seed, uint32_t rep, uint32_t site, uint32_t a, uint32_t b,
                                    uint32_t idx0, int32_t n, int32_t kind, uint32_t n_discrete, double *out)
 {

@@ -24,6 +24,28 @@
 
 namespace fsb {
 
+// Optional per-phase cycle accounting (scripts/phase_cycles.py): build with -DFSB_PHASE_TIMING.
+// Thread 0 of every CTA adds the cycles since its previous mark to g_phase_cycles[id].
+#ifdef FSB_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[32];
+#define FSB_MARK(id)                                                                   \
+    do {                                                                               \
+        if (threadIdx.x == 0) {                                                        \
+            const long long now_ = clock64();                                          \
+            atomicAdd(&g_phase_cycles[id], static_cast<unsigned long long>(now_ - c.tmark)); \
+            c.tmark = now_;                                                            \
+        }                                                                              \
+    } while (0)
+#else
+#define FSB_MARK(id) do { } while (0)
+#endif
+
+// Holdings prefetch policy into L2 (experiments: -DFSB_PF_MODE=n): 0 none, 1 two rounds ahead of the
+// full pass, 2 the whole K x M block at the start of the step
+#ifndef FSB_PF_MODE
+#define FSB_PF_MODE 1
+#endif
+
 constexpr double kPriceFloor = 0.000000001;  // functions.jl:208-209 (Q10)
 constexpr int kMaxCols = 10;                 // horizon columns per full pass (template bound)
 
@@ -34,17 +56,18 @@ struct StepArgs {
 // shared-memory carve-up; sizes depend on the engine's shapes (host computes the same layout)
 struct SmemLayout {
     // doubles
-    int off_cols, off_vh, off_ratio, off_sellsum, off_nav, off_dstake, off_dcash, off_rinj, off_rfval, off_rncap, off_scal;
+    int off_cols, off_vh, off_ratio, off_sellsum, off_nav, off_stk, off_dstake, off_dcash, off_rinj, off_rfval, off_rncap, off_scal;
     // ints (after the doubles)
     int off_rev, off_rfund, off_dinv, off_dfund, off_cash, off_rchoice, off_rcol, off_hcols, off_eggs, off_wl, off_wcnt,
-        off_flags, off_nzf, off_pick, off_fmod, off_isc;
+        off_flags, off_nzf, off_pick, off_fmod, off_fsel, off_isc;
     // 16-bit words (after the ints), then bytes
     int off_pos16, off_hor16, off_sidx, off_stl;
-    int cp;     // column pitch in doubles: Mp rounded up to 16 (zero padded, so 8-lane loops need no tail)
-    int cpk;    // pitch of a staged column / key row: max(cp, kp2)
-    int kq;     // K rounded up to even
-    int kp2;    // K rounded up to a power of two (bitonic sort length)
+    int cp;     // column pitch in doubles: Mp rounded up to 128 (zero padded, so 8-lane loops need no tail)
+    int cpk;    // pitch of a staged column / probability row: max(cp, kp2)
+    int kq;     // pitch of a vh / key row: kp2
+    int kp2;    // K rounded up to a power of two >= 256 (bitonic sort length)
     int srows;  // order rows that fit in the (cols[2..], vh) region while it is not holding columns
+    int wsd;    // doubles of that region per warp (member lists of the stake sequence)
     int ndoubles, nints, nshorts;
     int bytes;
 };
@@ -52,25 +75,28 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap, int cmax, int nwarps)
 {
     SmemLayout L;
-    L.cp = (Mp + 15) & ~15;
-    int kp2 = 32;
+    L.cp = (Mp + 127) & ~127;
+    int kp2 = 256;
     while (kp2 < K) kp2 <<= 1;
     L.kp2 = kp2;
     L.cpk = L.cp > kp2 ? L.cp : kp2;
-    L.kq = (K + 1) & ~1;
+    L.kq = kp2;
     int d = 0;
     L.off_cols = d; d += (cmax + 2) * L.cpk;   // col 0: opening prices, col 1: current prices, 2..: staged history
     L.off_vh = d; d += cmax * L.kq;            // must follow cols (order rows span both)
     L.srows = (cmax * (L.cpk + L.kq)) / L.cp;
+    L.wsd = ((cmax * (L.cpk + L.kq)) / nwarps) & ~1;
     L.off_ratio = d; d += L.cp;
     L.off_sellsum = d; d += L.cp;
-    L.off_nav = d; d += L.kq;
+    L.off_nav = d; d += (K + 1) & ~1;
+    L.off_stk = d; d += (N + 1) & ~1;      // the stakes of the day (write-through copy of stake[])
     L.off_dstake = d; d += cap;
     L.off_dcash = d; d += cap;
     L.off_rinj = d; d += cap;
     L.off_rfval = d; d += cap;
     L.off_rncap = d; d += cap;
     L.off_scal = d; d += 8;
+    d = (d + 1) & ~1;
     L.ndoubles = d;
     int i = 0;
     L.off_rev = i; i += cap;
@@ -83,17 +109,18 @@ __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap,
     L.off_hcols = i; i += cap;
     L.off_eggs = i; i += cap;
     L.off_wl = i; i += nwarps * cap;
-    L.off_wcnt = i; i += nwarps;
+    L.off_wcnt = i; i += 2 * nwarps;
     L.off_flags = i; i += cap;
     L.off_nzf = i; i += cap;
     L.off_pick = i; i += L.cp;
     L.off_fmod = i; i += (K + 31) / 32;
+    L.off_fsel = i; i += (K + 31) / 32;
     L.off_isc = i; i += 16;
-    i = (i + 1) & ~1;
+    i = (i + 3) & ~3;  // 16-bit arrays start 16-byte aligned (int4 scans of pos16)
     L.nints = i;
     int h = 0;
-    L.off_pos16 = h; h += (N + 1) & ~1;
-    L.off_hor16 = h; h += (N + 1) & ~1;
+    L.off_pos16 = h; h += (N + 7) & ~7;  // padded with -1 to whole 16-byte words
+    L.off_hor16 = h; h += (N + 7) & ~7;
     L.off_sidx = h; h += cmax * kp2;
     L.nshorts = h;
     L.off_stl = 0;
@@ -103,14 +130,14 @@ __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap,
 
 struct Ctx {
     // shared
-    double *cols, *vh, *ratio, *sellsum, *nav, *d_stake, *d_cash, *r_inj, *r_fval, *r_ncap, *scal;
-    int *rev, *rfund, *d_inv, *d_fund, *cash, *r_choice, *r_col, *hcols, *eggs, *wl, *wcnt, *flags, *nzf, *pick, *fmod, *isc;
+    double *cols, *vh, *ratio, *sellsum, *nav, *stk, *d_stake, *d_cash, *r_inj, *r_fval, *r_ncap, *scal;
+    int *rev, *rfund, *d_inv, *d_fund, *cash, *r_choice, *r_col, *hcols, *eggs, *wl, *wcnt, *flags, *nzf, *pick, *fmod, *fsel, *isc;
     short *pos16;
     unsigned short *hor16, *sidx;
     unsigned char *stl;
     unsigned long long *mbar;
     unsigned mbar_phase;
-    int cp, cpk, kq, kp2, srows;
+    int cp, cpk, kq, kp2, srows, wsd;
     // replication
     double *H, *P, *beta, *vol, *impact, *volume, *market, *stake, *amount, *threshold, *nav_open, *nav_close;
     int *pos, *horizon, *live_row, *cnt;
@@ -125,10 +152,11 @@ struct Ctx {
     long long r;
     const DevPoint *pt;
     int tid, lane, warp, nwarps, nthreads;
+    long long tmark;
 };
 
 // isc[] slots
-enum { I_ND = 0, I_NCASH, I_NEGGS, I_ERR, I_TMP0, I_TMP1, I_TMP2, I_NCOLS };
+enum { I_ND = 0, I_NCASH, I_NEGGS, I_ERR, I_TMP0, I_TMP1, I_TMP2, I_NCOLS, I_IDLE };
 
 __device__ __forceinline__ double *p_open(const Ctx &c) { return c.cols; }
 __device__ __forceinline__ double *p_cur(const Ctx &c) { return c.cols + c.cpk; }
@@ -138,33 +166,43 @@ __device__ __forceinline__ double *order_row(const Ctx &c, int Mp, int o)
     return (o < c.srows) ? c.cols + 2 * c.cpk + o * c.cp : c.scratch + static_cast<long long>(o - c.srows) * Mp;
 }
 
-__device__ __forceinline__ bool tape_lookup(const Ctx &c, int site, int t, int a, int b, double *out)
+// (the two helpers below are real calls -- cold paths kept out of the instruction stream -- and take
+// plain values, so that the Ctx of the caller stays in registers)
+__device__ __noinline__ bool tape_lookup_raw(const fsb_tape_rec *tape, long long n_tape, int site, int t, int a, int b, double *out)
 {
     const unsigned long long key = (static_cast<unsigned long long>(site & 0xff) << 56) |
                                    (static_cast<unsigned long long>(t & 0xffffff) << 32) |
                                    (static_cast<unsigned long long>(a & 0xffff) << 16) |
                                    static_cast<unsigned long long>(b & 0xffff);
-    long long lo = 0, hi = c.n_tape - 1;
+    long long lo = 0, hi = n_tape - 1;
     while (lo <= hi) {
         const long long mid = (lo + hi) >> 1;
-        const unsigned long long k = c.tape[mid].key;
-        if (k == key) { *out = c.tape[mid].value; return true; }
+        const unsigned long long k = tape[mid].key;
+        if (k == key) { *out = tape[mid].value; return true; }
         if (k < key) lo = mid + 1; else hi = mid - 1;
     }
     return false;
 }
+__device__ __forceinline__ bool tape_lookup(const Ctx &c, int site, int t, int a, int b, double *out)
+{
+    return tape_lookup_raw(c.tape, c.n_tape, site, t, a, b, out);
+}
 
-__device__ __forceinline__ void trace_emit(const DevState &s, const Ctx &c, int t, int kind, int a, int b, double v)
+__device__ __noinline__ void trace_emit_raw(fsb_trace_rec *recs, int *n_ptr, int cap_trace, int *err_ptr, int t, int kind, int a, int b, double v)
 {
     // single-thread emission (callers guard on tid == 0 and c.trace >= 0)
-    const int n = s.tr_n[c.trace];
-    if (n < s.cap_trace) {
-        fsb_trace_rec *r = s.tr_recs + static_cast<long long>(c.trace) * s.cap_trace + n;
+    const int n = *n_ptr;
+    if (n < cap_trace) {
+        fsb_trace_rec *r = recs + n;
         r->t = t; r->kind = kind; r->a = a; r->b = b; r->v = v;
-        s.tr_n[c.trace] = n + 1;
+        *n_ptr = n + 1;
     } else {
-        atomicOr(&s.err[c.r], FSB_REP_TRACE_OVERFLOW);
+        atomicOr(err_ptr, FSB_REP_TRACE_OVERFLOW);
     }
+}
+__device__ __forceinline__ void trace_emit(const DevState &s, const Ctx &c, int t, int kind, int a, int b, double v)
+{
+    trace_emit_raw(s.tr_recs + static_cast<long long>(c.trace) * s.cap_trace, s.tr_n + c.trace, s.cap_trace, s.err + c.r, t, kind, a, b, v);
 }
 
 // Ordered compaction of {i in [0,n): pred(i)} into out[] (ascending i).  Each warp owns a
@@ -216,6 +254,13 @@ __device__ __forceinline__ void floor_account(const DevState &s, const Ctx &c, i
             for (int m = 0; m < s.M; ++m)
                 if (c.pick[m]) trace_emit(s, c, t, FSB_EV_FLOOR, m, phase, 0.0);
     }
+}
+
+// x / y, skipping the division routine's slow path for the very common zero numerator (assets a fund
+// does not hold): for 0 < y < inf the IEEE quotient of a zero is that same signed zero
+__device__ __forceinline__ double qdiv(double x, double y)
+{
+    return (x == 0.0 && y > 0.0 && y < 1.7976931348623157e308) ? x : x / y;
 }
 
 // order-preserving map Float64 -> uint64 under Julia's isless (-0.0 < +0.0, every NaN last and equal)
@@ -316,6 +361,20 @@ __device__ __forceinline__ int select_fund_prob(const DevState &s, const Ctx &c,
     double cp = 0.0;
     int i = 0;
     const int K = s.K;
+    while (i + 8 <= K) {  // 8 probabilities per trip (the adds stay sequential: same cp sequence)
+        double pv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pv[q] = pk[i + q];
+        bool stop = false;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (!stop) {
+                if (cp < u) { cp = cp + pv[q]; ++i; }
+                else stop = true;
+            }
+        }
+        if (stop) return (i > 0) ? i - 1 : 0;
+    }
     while (cp < u && i < K) {
         cp = cp + pk[i];
         ++i;
@@ -345,76 +404,205 @@ __device__ __forceinline__ void warp_bitonic(unsigned long long *keys, unsigned 
     }
 }
 
+// Rank of K <= 256 keys by ONE warp, in registers: 8 packed words per lane, word = key with its low
+// 8 bits replaced by the fund index, bitonic network over 256 words (21 in-lane + 15 shuffle stages).
+// Exact unless two DIFFERENT keys agree in their upper 56 bits and the index order contradicts them;
+// that is detected afterwards on neighbours (returns false: caller re-sorts exactly in shared memory).
+// On success writes prob[k] = rank_k / normaliser (Q14), rank = 1-based position in the stable order.
+__device__ __forceinline__ bool warp_rank256(const unsigned long long *keys, int K, double *prob, double normaliser, int lane)
+{
+    unsigned long long v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int e = lane * 8 + r;
+        const unsigned long long kk = (e < K) ? keys[e] : ~0ULL;
+        v[r] = (kk & ~0xffULL) | static_cast<unsigned long long>(e);
+    }
+    // stages (k2, j2): partner = e ^ j2, ascending iff (e & k2) == 0, e = 8 * lane + r.  j2 >= 8 crosses
+    // lanes (shuffle), j2 in {4, 2, 1} stays in the lane's registers.  Outer loops stay rolled (code size).
+#pragma unroll 1
+    for (int k2 = 2; k2 <= 256; k2 <<= 1) {
+#pragma unroll 1
+        for (int lm = k2 >> 4; lm > 0; lm >>= 1) {  // lm = j2 / 8
+            const bool up = (((lane * 8) & k2) == 0);
+            const bool lower = ((lane & lm) == 0);
+            const bool keepmin = (lower == up);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], lm);
+                const bool less = o < v[r];
+                v[r] = (less == keepmin) ? o : v[r];
+            }
+        }
+#pragma unroll
+        for (int j2 = 4; j2 > 0; j2 >>= 1) {
+            if (j2 < k2) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    if ((r & j2) == 0) {
+                        const bool up = (((lane * 8 + r) & k2) == 0);
+                        const unsigned long long a = v[r], b = v[r | j2];
+                        const bool sw = (a > b) == up;
+                        v[r] = sw ? b : a;
+                        v[r | j2] = sw ? a : b;
+                    }
+                }
+            }
+        }
+    }
+    // words that agree in their upper 56 bits were ordered by index; order them by their full keys
+    // (stable odd-even transposition sweeps over neighbours; such runs are short and rare)
+    auto wrong = [&](unsigned long long a, unsigned long long b) {
+        if ((a ^ b) >= 256ULL) return false;
+        const int ia = static_cast<int>(a & 0xff), ib = static_cast<int>(b & 0xff);
+        return ia < K && ib < K && keys[ia] > keys[ib];
+    };
+    for (int sweep = 0;; ++sweep) {
+        bool moved = false;
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) {
+            if (wrong(v[r], v[r + 1])) { const unsigned long long x = v[r]; v[r] = v[r + 1]; v[r + 1] = x; moved = true; }
+        }
+#pragma unroll
+        for (int r = 1; r < 7; r += 2) {
+            if (wrong(v[r], v[r + 1])) { const unsigned long long x = v[r]; v[r] = v[r + 1]; v[r + 1] = x; moved = true; }
+        }
+        const unsigned long long nxt = __shfl_down_sync(0xffffffffu, v[0], 1);
+        const unsigned long long prv = __shfl_up_sync(0xffffffffu, v[7], 1);
+        const bool sw_hi = (lane < 31) && wrong(v[7], nxt);
+        const bool sw_lo = (lane > 0) && wrong(prv, v[0]);
+        if (sw_hi) { v[7] = nxt; moved = true; }
+        if (sw_lo) { v[0] = prv; moved = true; }
+        if (!__any_sync(0xffffffffu, moved)) break;
+        if (sweep >= 300) return false;  // (cannot happen: a stable sort of <= 256 words needs < 256 sweeps)
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int idx = static_cast<int>(v[r] & 0xff);
+        if (idx < K) prob[idx] = static_cast<double>(lane * 8 + r + 1) / normaliser;
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the full pass: every holdings row against NC shared-memory columns starting at column `cb`.
 // 8 lanes per row, 4 rows per warp and round; lane j owns double2 words j, j+8, ... (the canonical
 // chains); the loop runs over the zero-padded pitch cp so that every lane does the same trip count
-// (fma(0, 0, acc) == acc exactly).  Results: column 0 -> nav_open (unless the row was modified
-// before this pass: its opening NAV was taken in the review pass), column 1 -> nav / nav_close,
-// column q >= 2 -> vh[q-2][k].
+// (fma(0, 0, acc) == acc exactly).  Holdings are loaded four words ahead of their use (register
+// double buffer) and rows are L2-prefetched two rounds ahead.  Results: column 0 -> nav_open (unless
+// the row was modified before this pass: its opening NAV was taken in the review pass), column 1 ->
+// nav / nav_close, column q >= 2 -> horizon return (nav - vh) / vh (:375-379), stored as the value
+// or, for the rank rule, as its order-preserving 64-bit key.
+// FAST: cp == cpk == 256 at compile time (column offsets become immediates).
 // ------------------------------------------------------------------------------------------------
-template <int NC>
-__device__ __forceinline__ void full_pass(const DevState &s, const Ctx &c, const int cb)
+template <int NC, bool FAST>
+__device__ __forceinline__ void full_pass(const DevState &s, const Ctx &c, const int cb, const int nreal, const bool want_keys)
 {
-    const int K = s.K, Mp = s.Mp, half = Mp >> 1, hp = c.cp >> 1;
+    // Each 8-lane group owns TWO rows per round (k and k + 4: 8 consecutive rows per warp), so that one
+    // 128-bit shared-memory load of a column word feeds four FMAs (the pass is bound by the shared-memory
+    // pipe otherwise: a 128-bit LDS costs 4 wavefronts however many lanes share its address).
+    const int K = s.K, Mp = s.Mp, half = Mp >> 1;
     const int j = c.lane & 7, g = c.lane >> 3;
-    const int rpr = c.nwarps * 4;
-    const double2 *colp = reinterpret_cast<const double2 *>(c.cols + cb * c.cpk);
-    const int cstride = c.cpk >> 1;
-    for (int kb = c.warp * 4; kb < K; kb += rpr) {
-        if (c.lane == 0) {
-            const int kpf = kb + 2 * rpr;
-            if (kpf < K) l2_prefetch_bulk(c.H + static_cast<long long>(kpf) * Mp, static_cast<unsigned>(min(4, K - kpf) * Mp * 8));
-        }
-        const int k = kb + g;
-        const bool on = k < K;
-        const double2 *row = reinterpret_cast<const double2 *>(c.H + static_cast<long long>(on ? k : kb) * Mp);
-        double acc[NC];
+    const int rpr = c.nwarps * 8;
+    const int cstride = (FAST ? 256 : c.cpk) >> 1;
+    const int nb = FAST ? 8 : (c.cp >> 5);  // batches of 2 words per lane and row (cp is a multiple of 128 doubles: nb % 4 == 0)
+    const double2 *colp = reinterpret_cast<const double2 *>(c.cols + cb * (FAST ? 256 : c.cpk)) + j;
+    auto rowptr = [&](int k) {
+        return reinterpret_cast<const double2 *>(c.H + static_cast<long long>(k < K ? k : 0) * Mp) + j;
+    };
+    auto ldb = [&](const double2 *ra, const double2 *rb, int b, double2(&h)[4]) {
 #pragma unroll
-        for (int q = 0; q < NC; ++q) acc[q] = 0.0;
-#pragma unroll 4
-        for (int e2 = j; e2 < hp; e2 += 8) {
-            const double2 h = (e2 < half) ? row[e2] : make_double2(0.0, 0.0);
+        for (int i = 0; i < 2; ++i) {
+            const int e2 = 16 * b + 8 * i;
+            const bool in = (e2 + j < half);
+            h[i] = in ? ra[e2] : make_double2(0.0, 0.0);
+            h[2 + i] = in ? rb[e2] : make_double2(0.0, 0.0);
+        }
+    };
+    auto comp = [&](const double2 *cp_, const double2(&h)[4], double(&acc)[2 * NC]) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
 #pragma unroll
             for (int q = 0; q < NC; ++q) {
-                const double2 p = colp[q * cstride + e2];
-                acc[q] = fma(h.x, p.x, acc[q]);
-                acc[q] = fma(h.y, p.y, acc[q]);
+                const double2 p = cp_[q * cstride + 8 * i];
+                acc[q] = fma(h[i].x, p.x, acc[q]);
+                acc[q] = fma(h[i].y, p.y, acc[q]);
+                acc[NC + q] = fma(h[2 + i].x, p.x, acc[NC + q]);
+                acc[NC + q] = fma(h[2 + i].y, p.y, acc[NC + q]);
             }
         }
+    };
+    int kb = c.warp * 8;
+    if (kb >= K) return;
+    const double2 *ra = rowptr(kb + g), *rb = rowptr(kb + 4 + g);
+    double2 h0[4], h1[4];
+    ldb(ra, rb, 0, h0);
+#pragma unroll 1
+    for (; kb < K; kb += rpr) {
+        if (c.lane == 0) {
+            const int kpf = kb + 2 * rpr;
+            if (FSB_PF_MODE == 1 && kpf < K) l2_prefetch_bulk(c.H + static_cast<long long>(kpf) * Mp, static_cast<unsigned>(min(8, K - kpf) * Mp * 8));
+        }
+        const int kn = (kb + rpr < K) ? kb + rpr : kb;
+        const double2 *rna = rowptr(kn + g), *rnb = rowptr(kn + 4 + g);
+        double acc[2 * NC];
 #pragma unroll
-        for (int q = 0; q < NC; ++q) {
-            const double v = tree8(acc[q]);
-            if (on && j == (q & 7)) {
+        for (int q = 0; q < 2 * NC; ++q) acc[q] = 0.0;
+#pragma unroll 1
+        for (int b = 0; b < nb; b += 2) {
+            ldb(ra, rb, b + 1, h1);
+            comp(colp + 16 * b, h0, acc);
+            if (b + 2 < nb) ldb(ra, rb, b + 2, h0); else ldb(rna, rnb, 0, h0);
+            comp(colp + 16 * b + 16, h1, acc);
+        }
+        ra = rna; rb = rnb;
+        // ---- epilogue: lane j of a group owns result columns j and j + 8 of both rows ---------------
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int k = kb + 4 * rr + g;
+            const bool on = k < K;
+            double m0 = 0.0, m1 = 0.0, navk = 0.0;
+#pragma unroll
+            for (int q = 0; q < NC; ++q) {
+                const double v = tree8(acc[rr * NC + q]);
+                if (q == 1) navk = v;
+                if (j == (q & 7)) { if (q < 8) m0 = v; else m1 = v; }
+            }
+            if (cb != 0) navk = c.nav[on ? k : 0];
+#pragma unroll
+            for (int part = 0; part < (NC > 8 ? 2 : 1); ++part) {
+                const int q = j + 8 * part;
+                const double v = part ? m1 : m0;
                 const int col = cb + q;
-                if (col == 0) {
-                    if (!((c.fmod[k >> 5] >> (k & 31)) & 1)) c.nav_open[k] = v;
-                } else if (col == 1) {
-                    c.nav[k] = v;
-                    c.nav_close[k] = v;
-                } else {
-                    c.vh[(col - 2) * c.kq + k] = v;
+                if (on && q < nreal) {
+                    if (col == 0) {
+                        if (!((c.fmod[k >> 5] >> (k & 31)) & 1)) c.nav_open[k] = v;
+                    } else if (col == 1) {
+                        c.nav[k] = v;
+                        c.nav_close[k] = v;
+                    } else {
+                        const double rho = (navk - v) / v;
+                        if (want_keys) reinterpret_cast<unsigned long long *>(c.vh)[(col - 2) * c.kq + k] = sort_key(rho);
+                        else c.vh[(col - 2) * c.kq + k] = rho;
+                    }
                 }
             }
         }
     }
 }
 
-__device__ __forceinline__ void full_pass_dispatch(const DevState &s, const Ctx &c, int cb, int nc)
+// nc columns are processed by the next even instantiation (one spare column of finite stale data is
+// multiplied and dropped: cols[] always holds cmax + 2 columns)
+template <bool FAST>
+__device__ __forceinline__ void full_pass_dispatch(const DevState &s, const Ctx &c, int cb, int nc, bool want_keys)
 {
-    switch (nc) {
-    case 1: full_pass<1>(s, c, cb); break;
-    case 2: full_pass<2>(s, c, cb); break;
-    case 3: full_pass<3>(s, c, cb); break;
-    case 4: full_pass<4>(s, c, cb); break;
-    case 5: full_pass<5>(s, c, cb); break;
-    case 6: full_pass<6>(s, c, cb); break;
-    case 7: full_pass<7>(s, c, cb); break;
-    case 8: full_pass<8>(s, c, cb); break;
-    case 9: full_pass<9>(s, c, cb); break;
-    case 10: full_pass<10>(s, c, cb); break;
-    case 11: full_pass<11>(s, c, cb); break;
-    default: full_pass<12>(s, c, cb); break;
+    switch ((nc + 1) >> 1) {
+    case 1: full_pass<2, FAST>(s, c, cb, nc, want_keys); break;
+    case 2: full_pass<4, FAST>(s, c, cb, nc, want_keys); break;
+    case 3: full_pass<6, FAST>(s, c, cb, nc, want_keys); break;
+    case 4: full_pass<8, FAST>(s, c, cb, nc, want_keys); break;
+    case 5: full_pass<10, FAST>(s, c, cb, nc, want_keys); break;
+    default: full_pass<12, FAST>(s, c, cb, nc, want_keys); break;
     }
 }
 
@@ -428,7 +616,7 @@ __device__ __forceinline__ void open_pass(const DevState &s, const Ctx &c)
     for (int kb = c.warp * 4; kb < K; kb += rpr) {
         if (c.lane == 0) {
             const int kpf = kb + 2 * rpr;
-            if (kpf < K) l2_prefetch_bulk(c.H + static_cast<long long>(kpf) * Mp, static_cast<unsigned>(min(4, K - kpf) * Mp * 8));
+            if (FSB_PF_MODE == 1 && kpf < K) l2_prefetch_bulk(c.H + static_cast<long long>(kpf) * Mp, static_cast<unsigned>(min(4, K - kpf) * Mp * 8));
         }
         const int k = kb + g;
         const bool on = k < K;
@@ -461,6 +649,7 @@ __device__ __forceinline__ int chunk_list_get(const Ctx &c, int cap, int i)
 // ------------------------------------------------------------------------------------------------
 // one time step of one replication
 // ------------------------------------------------------------------------------------------------
+template <bool FAST>
 __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int t, int selector, int flags)
 {
     const int K = s.K, M = s.M, N = s.N, Mp = s.Mp, cap = s.cap_ev;
@@ -475,12 +664,15 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
 
     // ---- L2 prefetch of the first two rounds of holdings rows (consumed by the full pass) ------
     if (lane == 0) {
-        const int rpr = c.nwarps * 4;
+        const int rpr = c.nwarps * 8;
         for (int q = 0; q < 2; ++q) {
-            const int kpf = c.warp * 4 + q * rpr;
-            if (kpf < K) l2_prefetch_bulk(c.H + static_cast<long long>(kpf) * Mp, static_cast<unsigned>(min(4, K - kpf) * Mp * 8));
+            const int kpf = c.warp * 8 + q * rpr;
+            if (FSB_PF_MODE == 1 && kpf < K) l2_prefetch_bulk(c.H + static_cast<long long>(kpf) * Mp, static_cast<unsigned>(min(8, K - kpf) * Mp * 8));
         }
     }
+
+    if (FSB_PF_MODE == 2)
+        for (int k = tid; k < K; k += NT) l2_prefetch_bulk(c.H + static_cast<long long>(k) * Mp, static_cast<unsigned>(Mp * 8));
 
     // ---- marketmove! (:13-17): every thread evaluates the same draw (no barrier) -----------------
     double mret;
@@ -522,16 +714,26 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
         reinterpret_cast<double2 *>(po)[m2] = v;
         reinterpret_cast<double2 *>(pc)[m2] = v;
     }
+    FSB_MARK(19);
     // ---- investor -> fund map, horizons and the stake-less flags into shared memory ---------------
-    for (int n = tid; n < N; n += NT) {
-        c.pos16[n] = static_cast<short>(c.pos[n]);
-        c.hor16[n] = static_cast<unsigned short>(c.horizon[n]);
-    }
-    for (int k = tid; k < K; k += NT) c.stl[k] = c.stakeless[k];
-    for (int q = tid; q < (K + 31) / 32; q += NT) c.fmod[q] = 0;
-    for (int q = tid; q < cap; q += NT) c.nzf[q] = 0;
     if (tid < 16) c.isc[tid] = 0;
+    {
+        int idle = 0;  // investors already in cash when the day starts (none in a run from initialise)
+        for (int n = tid; n < ((N + 7) & ~7); n += NT) {
+            const int f = (n < N) ? c.pos[n] : -1;
+            c.pos16[n] = static_cast<short>(f);
+            c.hor16[n] = static_cast<unsigned short>((n < N) ? c.horizon[n] : 0);
+            idle += (f == K);
+        }
+        idle = __reduce_add_sync(0xffffffffu, idle);
+        if (lane == 0) c.wcnt[c.nwarps + c.warp] = idle;
+    }
+    for (int n = tid; n < N; n += NT) c.stk[n] = c.stake[n];
+    for (int k = tid; k < K; k += NT) c.stl[k] = c.stakeless[k];
+    for (int q = tid; q < (K + 31) / 32; q += NT) { c.fmod[q] = 0; c.fsel[q] = 0; }
+    for (int q = tid; q < cap; q += NT) c.nzf[q] = 0;
 
+    FSB_MARK(20);
     // ---- drawreviewers (:147-151): ascending ids, per-warp chunks of the investor range ----------
     {
         const double rp = pt.reviewprob;
@@ -563,13 +765,15 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
         if (lane == 0) c.wcnt[c.warp] = cnt;
     }
     __syncthreads();  // B1: prices, maps and reviewer chunks visible
-    int nrev = 0;
+    FSB_MARK(1);
+    int nrev = 0, idle_cash = 0;
     {
         bool ovf = false;
         for (int w = 0; w < c.nwarps; ++w) {
             const int x = c.wcnt[w];
             ovf = ovf || (x > cap);
             nrev += x;
+            idle_cash += c.wcnt[c.nwarps + w];
         }
         if (ovf || nrev > cap) {  // uniform across the block
             if (tid == 0) atomicOr(&s.err[c.r], FSB_REP_EVENT_OVERFLOW);
@@ -586,10 +790,10 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
         const int n = on ? chunk_list_get(c, cap, i) : 0;
         const int f = c.pos16[n];
         bool valid = on && f < K;
-        double thr = 0.0;
-        if (valid) {
+        double thr = 0.0, amt = 0.0;
+        if (valid) {  // (loaded together with the row and the columns: one memory latency)
             thr = c.threshold[n];
-            valid = c.amount[n] > 0.0;
+            amt = c.amount[n];
         }
         const int h = c.hor16[n];
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
@@ -607,6 +811,7 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
             }
         }
         a0 = tree8(a0); a1 = tree8(a1); a2 = tree8(a2);
+        valid = valid && (amt > 0.0);
         if (on && j8 == 0) {
             int flag = 0;
             if (valid) {
@@ -620,6 +825,7 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
         }
     }
     __syncthreads();  // B2
+    FSB_MARK(2);
     // ordered compaction of the divestments, done redundantly (and identically) by every warp
     int nd = 0;
     for (int b = 0; b < nrev; b += 32) {
@@ -645,11 +851,13 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
             for (int o = 0; o < nd; ++o) trace_emit(s, c, t, FSB_EV_DIVEST, c.d_inv[o], c.d_fund[o], 0.0);
         }
     }
+    FSB_MARK(16);
     if (nd == 0) {  // :464 -- nothing else happens this step
         open_pass(s, c);
         for (int m2 = tid; m2 < half; m2 += NT) reinterpret_cast<double2 *>(Pt)[m2] = reinterpret_cast<const double2 *>(pc)[m2];
         if (tid == 0) s.flow_hist[c.r * kFlowBins] += 1;
         __syncthreads();
+        FSB_MARK(3);
         if (traced)
             for (int k = tid; k < K; k += NT)
                 s.tr_nav[static_cast<long long>(c.trace) * K * s.T + k + static_cast<long long>(K) * (t - 1)] = c.nav_open[k];
@@ -657,92 +865,147 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
     }
 
     // ---- liquidate! (:183-201), part 1: the stake sequence (sequential within a fund) ---------
-    for (int o = c.warp; o < nd; o += c.nwarps) {
-        const int f = c.d_fund[o];
-        bool leader = true;
-        for (int q = 0; q < o; ++q) leader = leader && (c.d_fund[q] != f);
-        if (!leader) continue;
-        double tot = 0.0;
-        for (int o2 = o; o2 < nd; ++o2) {
-            if (c.d_fund[o2] != f) continue;
-            const int inv = c.d_inv[o2];
-            const double sk = c.stake[inv];
-            __syncwarp();
-            if (lane == 0) { c.d_stake[o2] = sk; c.stake[inv] = 0.0; }
-            __syncwarp();
-            tot = 0.0;  // sum(stakes[fund,:]) in ascending investor order
-            for (int b = 0; b < N; b += 32) {
-                const int n = b + lane;
-                const bool mem = (n < N) && (c.pos16[n] == f);
-                const double v = mem ? c.stake[n] : 0.0;
-                unsigned m = __ballot_sync(0xffffffffu, mem);
-                while (m) {
-                    const int q = __ffs(m) - 1;
-                    m &= m - 1;
-                    tot = tot + __shfl_sync(0xffffffffu, v, q);
+    // one warp per distinct fund; the fund's members (ascending investor id) are gathered into a
+    // per-warp list (16-byte scans of the shared investor->fund map), summed in that order and
+    // renormalised from the list
+    if (c.warp == 1 % c.nwarps) {  // history columns of the leavers' horizons: wanted in L2 by the full pass
+        for (int o = lane; o < nd; o += 32)
+            l2_prefetch_bulk(c.P + static_cast<long long>(pcol(s, t - c.hor16[c.d_inv[o]])) * Mp, static_cast<unsigned>(Mp * 8));
+    }
+    FSB_MARK(17);
+    {
+        const int capm = (c.wsd * 2) / 3;
+        double *mv = c.cols + 2 * c.cpk + c.warp * c.wsd;
+        int *mn = reinterpret_cast<int *>(mv + capm);
+        for (int o = c.warp; o < nd; o += c.nwarps) {
+            const int f = c.d_fund[o];
+            bool leader = true;
+            for (int q = 0; q < o; ++q) leader = leader && (c.d_fund[q] != f);
+            if (!leader) continue;
+            double tot = 0.0;
+            for (int o2 = o; o2 < nd; ++o2) {
+                if (c.d_fund[o2] != f) continue;
+                const int inv = c.d_inv[o2];
+                const double sk = c.stk[inv];
+                __syncwarp();
+                if (lane == 0) { c.d_stake[o2] = sk; c.stk[inv] = 0.0; c.stake[inv] = 0.0; }
+                __syncwarp();
+                int cntm = 0;
+                for (int b = 0; b < N; b += 256) {
+                    const int n0 = b + 8 * lane;
+                    unsigned mask = 0;
+                    if (n0 < N) {
+                        const int4 w = *reinterpret_cast<const int4 *>(c.pos16 + n0);
+                        const int ws[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            mask |= (static_cast<short>(ws[q] & 0xffff) == f) ? (1u << (2 * q)) : 0u;
+                            mask |= (static_cast<short>(ws[q] >> 16) == f) ? (2u << (2 * q)) : 0u;
+                        }
+                    }
+                    const int cntl = __popc(mask);
+                    int incl = cntl;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int x = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += x;
+                    }
+                    int w = cntm + incl - cntl;
+                    while (mask) {
+                        const int q = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        if (w < capm) { mn[w] = n0 + q; mv[w] = c.stk[n0 + q]; }
+                        ++w;
+                    }
+                    cntm += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                __syncwarp();
+                // sum(stakes[fund,:]): members dealt round-robin to the 32 lanes, butterfly 16,8,4,2,1
+                tot = 0.0;
+                if (cntm <= capm) {
+                    for (int q = lane; q < cntm; q += 32) tot = tot + mv[q];
+#pragma unroll
+                    for (int sft = 16; sft >= 1; sft >>= 1) tot = tot + __shfl_xor_sync(0xffffffffu, tot, sft);
+                    if (tot > 0.0)
+                        for (int q = lane; q < cntm; q += 32) { const double sv = qdiv(mv[q], tot); c.stk[mn[q]] = sv; c.stake[mn[q]] = sv; }
+                } else {  // list does not fit: scan twice; member i of the fund goes to lane i % 32
+                    int seen = 0;
+                    for (int b = 0; b < N; b += 32) {
+                        const int n = b + lane;
+                        const bool mem = (n < N) && (c.pos16[n] == f);
+                        const double v = mem ? c.stk[n] : 0.0;
+                        unsigned m = __ballot_sync(0xffffffffu, mem);
+                        while (m) {
+                            const int q = __ffs(m) - 1;
+                            m &= m - 1;
+                            const double x = __shfl_sync(0xffffffffu, v, q);
+                            if ((seen & 31) == lane) tot = tot + x;
+                            ++seen;
+                        }
+                    }
+#pragma unroll
+                    for (int sft = 16; sft >= 1; sft >>= 1) tot = tot + __shfl_xor_sync(0xffffffffu, tot, sft);
+                    if (tot > 0.0) {
+                        for (int n = lane; n < N; n += 32)
+                            if (c.pos16[n] == f) { const double sv = qdiv(c.stk[n], tot); c.stk[n] = sv; c.stake[n] = sv; }
+                    }
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                const unsigned char sl = (tot == 0.0) ? 1 : 0;
+                c.stl[f] = sl;
+                c.stakeless[f] = sl;
+            }
+        }
+    }
+    FSB_MARK(18);
+    __syncthreads();  // B4
+    FSB_MARK(4);
+
+    // ---- liquidate! part 2 + trackvolume! (:467) + marketmake! (:205-211), one asset per thread ----
+    for (int m = tid; m < M; m += NT) {
+        const double p = pc[m];
+        double net = 0.0;
+        for (int o0 = 0; o0 < nd; o0 += 4) {
+            // rows of up to 4 orders are loaded together unless two of them sell the same fund
+            // (then the later one must see the earlier one's scaled holdings)
+            const int n4 = min(4, nd - o0);
+            int fq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) fq[q] = (q < n4) ? c.d_fund[o0 + q] : -1 - q;
+            const bool dup = (fq[1] == fq[0]) || (fq[2] == fq[0]) || (fq[2] == fq[1]) || (fq[3] == fq[0]) || (fq[3] == fq[1]) || (fq[3] == fq[2]);
+            double hq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)  // (a missing order re-reads the first row: no predicated array)
+                hq[q] = c.H[static_cast<long long>(fq[q] >= 0 ? fq[q] : fq[0]) * Mp + m];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < n4) {
+                    const int o = o0 + q;
+                    const double sk = c.d_stake[o];
+                    double *hpn = c.H + static_cast<long long>(fq[q]) * Mp + m;
+                    const double h = dup ? *hpn : hq[q];
+                    const double v = (-sk) * (h * p);
+                    order_row(c, Mp, o)[m] = v;
+                    net = net + v;
+                    const double hn = h * (1.0 - sk);
+                    *hpn = hn;
+                    if (hn != 0.0) c.nzf[o] = 1;
                 }
             }
-            if (tot > 0.0) {
-                for (int n = lane; n < N; n += 32)
-                    if (c.pos16[n] == f) c.stake[n] = c.stake[n] / tot;
-            }
-            __syncwarp();
         }
-        if (lane == 0) {
-            const unsigned char sl = (tot == 0.0) ? 1 : 0;
-            c.stl[f] = sl;
-            c.stakeless[f] = sl;
-        }
-    }
-    __syncthreads();  // B4
-
-    // ---- liquidate! part 2 + trackvolume! (:467) + marketmake! (:205-211), two assets per thread --
-    for (int m2 = tid; m2 < half; m2 += NT) {
-        const bool two = (2 * m2 + 1 < M);
-        const double2 p = reinterpret_cast<const double2 *>(pc)[m2];
-        double2 net = make_double2(0.0, 0.0);
-        for (int o = 0; o < nd; ++o) {
-            const int f = c.d_fund[o];
-            const double sk = c.d_stake[o];
-            double2 *hpn = reinterpret_cast<double2 *>(c.H + static_cast<long long>(f) * Mp) + m2;
-            const double2 h = *hpn;
-            double2 v, hn;
-            v.x = (-sk) * (h.x * p.x);
-            v.y = two ? (-sk) * (h.y * p.y) : 0.0;
-            reinterpret_cast<double2 *>(order_row(c, Mp, o))[m2] = v;
-            net.x = net.x + v.x;
-            net.y = net.y + v.y;
-            hn.x = h.x * (1.0 - sk);
-            hn.y = two ? h.y * (1.0 - sk) : 0.0;
-            *hpn = hn;
-            if (hn.x != 0.0 || hn.y != 0.0) c.nzf[o] = 1;
-        }
-        reinterpret_cast<double2 *>(c.sellsum)[m2] = net;
-        const double2 im = reinterpret_cast<const double2 *>(c.impact)[m2];
-        double2 v, ra;
-        int fl0 = 0, fl1 = 0;
-        v.x = (1.0 + net.x * im.x) * p.x;
-        if (v.x < kPriceFloor) { v.x = kPriceFloor; fl0 = 1; }
-        ra.x = v.x / p.x;  // priceratio, :217
-        v.y = 0.0; ra.y = 0.0;
-        if (two) {
-            v.y = (1.0 + net.y * im.y) * p.y;
-            if (v.y < kPriceFloor) { v.y = kPriceFloor; fl1 = 1; }
-            ra.y = v.y / p.y;
-        }
-        if (c.volume) {
-            double2 *vp = reinterpret_cast<double2 *>(c.volume + static_cast<long long>(t - 1) * Mp) + m2;
-            double2 vv = *vp;
-            vv.x -= net.x;
-            if (two) vv.y -= net.y;
-            *vp = vv;
-        }
-        c.pick[2 * m2] = fl0;
-        c.pick[2 * m2 + 1] = fl1;
-        reinterpret_cast<double2 *>(pc)[m2] = v;
-        reinterpret_cast<double2 *>(c.ratio)[m2] = ra;
+        c.sellsum[m] = net;
+        double v = (1.0 + net * c.impact[m]) * p;
+        int fl = 0;
+        if (v < kPriceFloor) { v = kPriceFloor; fl = 1; }
+        if (c.volume) c.volume[static_cast<long long>(t - 1) * Mp + m] -= net;
+        c.pick[m] = fl;
+        pc[m] = v;
+        c.ratio[m] = v / p;  // priceratio, :217
     }
     __syncthreads();  // B5
+    FSB_MARK(5);
     // ---- executeorder!(Sell) cash-outs (:218-222) and disburse! (:243-252), 8 lanes per order ----
     for (int ob = c.warp * 4; ob < nd; ob += c.nwarps * 4) {
         const int o = ob + g4;
@@ -779,13 +1042,20 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
     int dead_local = 0;
     for (int k = tid; k < K; k += NT) dead_local |= c.stl[k];
     const int any_dead = __syncthreads_or(dead_local);  // B6
+    FSB_MARK(6);
     if (traced && tid == 0)
         for (int o = 0; o < nd; ++o) trace_emit(s, c, t, FSB_EV_CASHOUT, c.d_inv[o], c.d_fund[o], c.d_cash[o]);
     if (traced)
         for (int m = tid; m < M; m += NT)
             s.tr_psell[static_cast<long long>(c.trace) * M * s.T + m + static_cast<long long>(M) * (t - 1)] = pc[m];
 
-    if (any_dead) {
+    int any_egg = 0;
+    if (any_dead) {  // Q5: the trigger is the stake sums, the candidates are the all-zero rows
+        int eg = 0;
+        for (int k = tid; k < K; k += NT) eg |= c.hzero[k];
+        any_egg = __syncthreads_or(eg);
+    }
+    if (any_egg) {
         // ---- respawn! (:275-321) ----------------------------------------------------------------
         const int neggs = block_compact(c, K, cap, c.eggs, [&](int k) { return c.hzero[k] != 0; });
         const int ncash = block_compact(c, N, cap, c.cash, [&](int n) { return c.pos16[n] == K && c.amount[n] > 0.0; });
@@ -812,6 +1082,7 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
                 c.pos[inv] = egg;      // :288-289 (amount keeps the capital)
                 c.pos16[inv] = static_cast<short>(egg);
                 c.stake[inv] = 1.0;    // :296
+                c.stk[inv] = 1.0;
                 c.stl[egg] = 0;
                 c.stakeless[egg] = 0;
                 int nk = 0;
@@ -884,11 +1155,11 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
                 for (int e = 2 * j8; e < M; e += 16) {
                     const double v0 = bo[e];
                     nst += (v0 > 0.0);
-                    acc = acc + (v0 / fundsize) * c.impact[e];
+                    acc = acc + qdiv(v0, fundsize) * c.impact[e];
                     if (e + 1 < M) {
                         const double v1 = bo[e + 1];
                         nst += (v1 > 0.0);
-                        acc = acc + (v1 / fundsize) * c.impact[e + 1];
+                        acc = acc + qdiv(v1, fundsize) * c.impact[e + 1];
                     }
                 }
                 const double liq = tree8(acc);
@@ -938,7 +1209,7 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
             pc[m] = v;
             for (int i = 0; i < neggs; ++i) {
                 double *hpn = c.H + static_cast<long long>(c.eggs[i]) * Mp + m;
-                const double hn = *hpn + order_row(c, Mp, i)[m] / v;
+                const double hn = *hpn + qdiv(order_row(c, Mp, i)[m], v);
                 *hpn = hn;
                 if (hn != 0.0) c.nzf[i] = 1;
             }
@@ -953,19 +1224,32 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
         for (int m = tid; m < M; m += NT)
             s.tr_presp[static_cast<long long>(c.trace) * M * s.T + m + static_cast<long long>(M) * (t - 1)] = pc[m];
 
+    FSB_MARK(7);
     // ---- cash holders (:481, :339) and their distinct horizons, by warp 0 ----------------------
     if (c.warp == 0) {
         int cnt = 0;
-        for (int b = 0; b < N; b += 32) {
-            const int n = b + lane;
-            bool p = (n < N) && (c.pos16[n] == K);
-            if (p) p = c.amount[n] > 0.0;
-            const unsigned m = __ballot_sync(0xffffffffu, p);
-            if (p) {
-                const int k = cnt + __popc(m & ((1u << lane) - 1u));
-                if (k < cap) c.cash[k] = n;
+        if (idle_cash == 0) {
+            // nobody was in cash when the day started: the cash holders are today's leavers (ascending
+            // ids already) that got a positive cash-out and were not used as respawn anchors
+            for (int b = 0; b < nd; b += 32) {
+                const int o = b + lane;
+                const bool p = (o < nd) && (c.pos16[c.d_inv[o]] == K) && (c.d_cash[o] > 0.0);
+                const unsigned m = __ballot_sync(0xffffffffu, p);
+                if (p) c.cash[cnt + __popc(m & ((1u << lane) - 1u))] = c.d_inv[o];
+                cnt += __popc(m);
             }
-            cnt += __popc(m);
+        } else {
+            for (int b = 0; b < N; b += 32) {
+                const int n = b + lane;
+                bool p = (n < N) && (c.pos16[n] == K);
+                if (p) p = c.amount[n] > 0.0;
+                const unsigned m = __ballot_sync(0xffffffffu, p);
+                if (p) {
+                    const int k = cnt + __popc(m & ((1u << lane) - 1u));
+                    if (k < cap) c.cash[k] = n;
+                }
+                cnt += __popc(m);
+            }
         }
         __syncwarp();
         if (lane == 0) {
@@ -983,6 +1267,7 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
         }
     }
     __syncthreads();  // B7
+    FSB_MARK(8);
     const int ncash = c.isc[I_NCASH];
     if (ncash > cap) {
         if (tid == 0) atomicOr(&s.err[c.r], FSB_REP_EVENT_OVERFLOW);
@@ -1010,45 +1295,42 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
             c.mbar_phase ^= 1u;
         }
         __syncthreads();  // B8 (pads; also orders the previous chunk's readers before this chunk's results)
-        full_pass_dispatch(s, c, c0 == 0 ? 0 : 2, c0 == 0 ? 2 + nc : nc);
-        __syncthreads();  // B9
+        FSB_MARK(9);
+        const bool prob = (selector == FSB_SEL_PROBABILISTIC);
+        full_pass_dispatch<FAST>(s, c, c0 == 0 ? 0 : 2, c0 == 0 ? 2 + nc : nc, prob);
+        __syncthreads();  // B9: vh[] holds the horizon returns (or their sort keys) of this chunk
+        FSB_MARK(10);
         if (nc > 0) {
-            // horizonreturncalc (:375-379) once per column, plus sortable keys for the rank rule
-            if (selector == FSB_SEL_PROBABILISTIC) {
-                for (int q = tid; q < nc * c.kp2; q += NT) {
-                    const int jc = q / c.kp2, k = q - jc * c.kp2;
-                    unsigned long long key = ~0ULL;
-                    if (k < K) {
-                        const double vhk = c.vh[jc * c.kq + k];
-                        key = sort_key((c.nav[k] - vhk) / vhk);
-                    }
-                    reinterpret_cast<unsigned long long *>(c.cols + (2 + jc) * c.cpk)[k] = key;
-                    c.sidx[jc * c.kp2 + k] = static_cast<unsigned short>(k);
-                }
-                __syncthreads();
+            if (prob) {
+                // rank rule: p_k = rank_k / (K(K+1)/2) per column, into the (now free) staged column
                 for (int jc = c.warp; jc < nc; jc += c.nwarps) {
-                    unsigned long long *keys = reinterpret_cast<unsigned long long *>(c.cols + (2 + jc) * c.cpk);
-                    unsigned short *idx = c.sidx + jc * c.kp2;
-                    warp_bitonic(keys, idx, c.kp2, lane);
-                    // p_k = rank_k / (K(K+1)/2) (Q14), rank = 1-based position in the stable ascending order
-                    for (int i = lane; i < K; i += 32) c.vh[jc * c.kq + idx[i]] = static_cast<double>(i + 1) / normaliser;
+                    unsigned long long *keys = reinterpret_cast<unsigned long long *>(c.vh) + jc * c.kq;
+                    double *prob_k = c.cols + (2 + jc) * c.cpk;
+                    bool done = false;
+                    if (c.kp2 == 256) done = warp_rank256(keys, K, prob_k, normaliser, lane);
+                    if (!done) {  // K > 256, or a 56-bit tie the packed sort cannot order: exact sort in shared memory
+                        unsigned short *idx = c.sidx + jc * c.kp2;
+                        for (int i = lane; i < c.kp2; i += 32) {
+                            if (i >= K) keys[i] = ~0ULL;
+                            idx[i] = static_cast<unsigned short>(i);
+                        }
+                        __syncwarp();
+                        warp_bitonic(keys, idx, c.kp2, lane);
+                        for (int i = lane; i < K; i += 32) prob_k[idx[i]] = static_cast<double>(i + 1) / normaliser;
+                    }
+                    __syncwarp();
+                    FSB_MARK(23);
+                    // the same warp samples the choice of every cash holder whose horizon is this column
+                    for (int i = lane; i < ncash; i += 32) {
+                        if (c.r_col[i] != c0 + jc) continue;
+                        int e = 0;
+                        const int choice = select_fund_prob(s, c, t, c.cash[i], prob_k, &e);
+                        c.r_choice[i] = choice;
+                        if (e) atomicOr(&c.isc[I_ERR], e);
+                    }
                 }
-                __syncthreads();
-                for (int i = tid; i < ncash; i += NT) {
-                    const int col = c.r_col[i];
-                    if (col < c0 || col >= c0 + nc) continue;
-                    int e = 0;
-                    const int choice = select_fund_prob(s, c, t, c.cash[i], c.vh + (col - c0) * c.kq, &e);
-                    c.r_choice[i] = choice;
-                    if (e) atomicOr(&c.isc[I_ERR], e);
-                }
+                FSB_MARK(11);
             } else {
-                for (int q = tid; q < nc * K; q += NT) {
-                    const int jc = q / K, k = q - jc * K;
-                    const double vhk = c.vh[jc * c.kq + k];
-                    c.vh[jc * c.kq + k] = (c.nav[k] - vhk) / vhk;
-                }
-                __syncthreads();
                 for (int i = c.warp; i < ncash; i += c.nwarps) {
                     const int col = c.r_col[i];
                     if (col < c0 || col >= c0 + nc) continue;
@@ -1061,6 +1343,7 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
                 }
             }
             __syncthreads();
+            FSB_MARK(12);
         }
     }
     if (traced)
@@ -1079,9 +1362,11 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
             c.r_fval[i] = fv;
             c.r_ncap[i] = fv + inj;
             c.stl[ch] = 1;  // cleared below by every member whose diluted stake is non-zero
+            atomicOr(reinterpret_cast<unsigned *>(&c.fsel[ch >> 5]), 1u << (ch & 31));
         }
         for (int o = tid; o < cap; o += NT) c.nzf[o] = 0;
         __syncthreads();  // B13
+        FSB_MARK(13);
         if (tid == 0) {
             c.cnt[CNT_REINVEST] += ncash;
             if (traced)
@@ -1090,6 +1375,8 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
         // stakes (:363-366), sequential over reinvestors per investor (Q7), parallel over investors
         for (int n = tid; n < N; n += NT) {
             int mypos = c.pos16[n];
+            // only cash holders and members of a chosen fund can be touched
+            if (mypos != K && !((c.fsel[mypos >> 5] >> (mypos & 31)) & 1)) continue;
             bool touched = false;
             for (int i = 0; i < ncash; ++i) {
                 const int ch = c.r_choice[i];
@@ -1098,68 +1385,72 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
             }
             if (!touched) continue;
             mypos = c.pos16[n];
-            double st = c.stake[n];
+            double st = c.stk[n];
             for (int i = 0; i < ncash; ++i) {
                 const int ch = c.r_choice[i];
                 if (c.cash[i] == n) {
                     mypos = ch;
                     st = c.r_inj[i] / c.r_ncap[i];
                 } else if (mypos == ch) {
-                    st = (st * c.r_fval[i]) / c.r_ncap[i];
+                    st = qdiv(st * c.r_fval[i], c.r_ncap[i]);
                 }
             }
             c.pos[n] = mypos;
             c.pos16[n] = static_cast<short>(mypos);
             c.stake[n] = st;
+            c.stk[n] = st;
             if (st != 0.0 && mypos < K) c.stl[mypos] = 0;
         }
-        // buy orders (:367-368), net demand, impact, shares (:229-239), holdings (:259)
-        for (int m2 = tid; m2 < half; m2 += NT) {
-            const bool two = (2 * m2 + 1 < M);
-            const double2 p = reinterpret_cast<const double2 *>(pc)[m2];
-            double2 net = make_double2(0.0, 0.0);
-            for (int i = 0; i < ncash; ++i) {
-                const double2 h = reinterpret_cast<const double2 *>(c.H + static_cast<long long>(c.r_choice[i]) * Mp)[m2];
-                const double fv = c.r_fval[i], inj = c.r_inj[i];
-                double2 v;
-                v.x = ((h.x * p.x) / fv) * inj;
-                v.y = two ? ((h.y * p.y) / fv) * inj : 0.0;
-                reinterpret_cast<double2 *>(order_row(c, Mp, i))[m2] = v;
-                net.x = net.x + v.x;
-                net.y = net.y + v.y;
+        FSB_MARK(24);
+        // buy orders (:367-368), net demand, impact, shares (:229-239), holdings (:259); one asset per thread
+        for (int m = tid; m < M; m += NT) {
+            const double p = pc[m];
+            double net = 0.0;
+            for (int i0 = 0; i0 < ncash; i0 += 4) {  // holdings do not change in this loop: 4 rows in flight
+                const int n4 = min(4, ncash - i0);
+                double hq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) hq[q] = c.H[static_cast<long long>(c.r_choice[q < n4 ? i0 + q : i0]) * Mp + m];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < n4) {
+                        const int i = i0 + q;
+                        const double v = qdiv(hq[q] * p, c.r_fval[i]) * c.r_inj[i];
+                        order_row(c, Mp, i)[m] = v;
+                        net = net + v;
+                    }
+                }
             }
-            if (c.volume && !(flags & FSB_RUN_NO_VOLUME_QUIRK)) {  // :484 (Q3)
-                double2 *vp = reinterpret_cast<double2 *>(c.volume + static_cast<long long>(t - 1) * Mp) + m2;
-                const double2 ss = reinterpret_cast<const double2 *>(c.sellsum)[m2];
-                double2 vv = *vp;
-                vv.x -= ss.x;
-                if (two) vv.y -= ss.y;
-                *vp = vv;
-            }
-            const double2 im = reinterpret_cast<const double2 *>(c.impact)[m2];
-            double2 v;
-            int fl0 = 0, fl1 = 0;
-            v.x = (1.0 + net.x * im.x) * p.x;
-            if (v.x < kPriceFloor) { v.x = kPriceFloor; fl0 = 1; }
-            v.y = 0.0;
-            if (two) {
-                v.y = (1.0 + net.y * im.y) * p.y;
-                if (v.y < kPriceFloor) { v.y = kPriceFloor; fl1 = 1; }
-            }
-            c.pick[2 * m2] = fl0;
-            c.pick[2 * m2 + 1] = fl1;
-            reinterpret_cast<double2 *>(pc)[m2] = v;
-            for (int i = 0; i < ncash; ++i) {
-                double2 *hpn = reinterpret_cast<double2 *>(c.H + static_cast<long long>(c.r_choice[i]) * Mp) + m2;
-                const double2 o = reinterpret_cast<const double2 *>(order_row(c, Mp, i))[m2];
-                double2 hn = *hpn;
-                hn.x = hn.x + o.x / v.x;
-                if (two) hn.y = hn.y + o.y / v.y;
-                *hpn = hn;
-                if (hn.x != 0.0 || hn.y != 0.0) c.nzf[i] = 1;
+            if (c.volume && !(flags & FSB_RUN_NO_VOLUME_QUIRK)) c.volume[static_cast<long long>(t - 1) * Mp + m] -= c.sellsum[m];  // :484 (Q3)
+            double v = (1.0 + net * c.impact[m]) * p;
+            int fl = 0;
+            if (v < kPriceFloor) { v = kPriceFloor; fl = 1; }
+            c.pick[m] = fl;
+            pc[m] = v;
+            for (int i0 = 0; i0 < ncash; i0 += 4) {
+                const int n4 = min(4, ncash - i0);
+                int fq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) fq[q] = (q < n4) ? c.r_choice[i0 + q] : -1 - q;
+                const bool dup = (fq[1] == fq[0]) || (fq[2] == fq[0]) || (fq[2] == fq[1]) || (fq[3] == fq[0]) || (fq[3] == fq[1]) || (fq[3] == fq[2]);
+                double hq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) hq[q] = c.H[static_cast<long long>(fq[q] >= 0 ? fq[q] : fq[0]) * Mp + m];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < n4) {
+                        const int i = i0 + q;
+                        double *hpn = c.H + static_cast<long long>(fq[q]) * Mp + m;
+                        const double hn = (dup ? *hpn : hq[q]) + qdiv(order_row(c, Mp, i)[m], v);
+                        *hpn = hn;
+                        if (hn != 0.0) c.nzf[i] = 1;
+                    }
+                }
             }
         }
+        FSB_MARK(25);
         __syncthreads();  // B14
+        FSB_MARK(14);
         // funds that received shares are revalued at the final prices (disburse! -> fundrevalue!)
         for (int ib = c.warp * 4; ib < ncash; ib += c.nwarps * 4) {
             const int i = ib + g4;
@@ -1183,12 +1474,14 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
     }
     for (int m2 = tid; m2 < half; m2 += NT) reinterpret_cast<double2 *>(Pt)[m2] = reinterpret_cast<const double2 *>(pc)[m2];
     __syncthreads();
+    FSB_MARK(15);
 }
 
 // ------------------------------------------------------------------------------------------------
 // kernel: persistent CTAs pull replications from a work counter
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) fsb_step_kernel(const DevState s, const StepArgs a, const int launch_parity)
+template <bool FAST>
+__global__ void __launch_bounds__(256, 2) fsb_step_kernel(const DevState s, const StepArgs a, const int launch_parity)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long r_sh;
@@ -1200,16 +1493,17 @@ __global__ void __launch_bounds__(256, 3) fsb_step_kernel(const DevState s, cons
     unsigned short *sh = reinterpret_cast<unsigned short *>(si + L.nints);
     Ctx c;
     c.cols = sd + L.off_cols; c.vh = sd + L.off_vh; c.ratio = sd + L.off_ratio; c.sellsum = sd + L.off_sellsum;
-    c.nav = sd + L.off_nav; c.d_stake = sd + L.off_dstake; c.d_cash = sd + L.off_dcash;
+    c.nav = sd + L.off_nav; c.stk = sd + L.off_stk; c.d_stake = sd + L.off_dstake; c.d_cash = sd + L.off_dcash;
     c.r_inj = sd + L.off_rinj; c.r_fval = sd + L.off_rfval; c.r_ncap = sd + L.off_rncap; c.scal = sd + L.off_scal;
     c.rev = si + L.off_rev; c.rfund = si + L.off_rfund; c.d_inv = si + L.off_dinv; c.d_fund = si + L.off_dfund;
     c.cash = si + L.off_cash; c.r_choice = si + L.off_rchoice; c.r_col = si + L.off_rcol; c.hcols = si + L.off_hcols;
     c.eggs = si + L.off_eggs; c.wl = si + L.off_wl; c.wcnt = si + L.off_wcnt; c.flags = si + L.off_flags;
-    c.nzf = si + L.off_nzf; c.pick = si + L.off_pick; c.fmod = si + L.off_fmod; c.isc = si + L.off_isc;
+    c.nzf = si + L.off_nzf; c.pick = si + L.off_pick; c.fmod = si + L.off_fmod; c.fsel = si + L.off_fsel; c.isc = si + L.off_isc;
     c.pos16 = reinterpret_cast<short *>(sh + L.off_pos16); c.hor16 = sh + L.off_hor16; c.sidx = sh + L.off_sidx;
     c.stl = reinterpret_cast<unsigned char *>(sh + L.nshorts);
-    c.cp = L.cp; c.cpk = L.cpk; c.kq = L.kq; c.kp2 = L.kp2; c.srows = L.srows;
+    c.cp = L.cp; c.cpk = L.cpk; c.kq = L.kq; c.kp2 = L.kp2; c.srows = L.srows; c.wsd = L.wsd;
     c.mbar = &mbar_sh; c.mbar_phase = 0;
+    c.tmark = clock64();
     c.tid = threadIdx.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5; c.nwarps = nwarps; c.nthreads = blockDim.x;
     c.scratch = s.scratch + static_cast<long long>(blockIdx.x) * s.cap_ev * s.Mp;
     c.rng.k0 = static_cast<uint32_t>(s.seed); c.rng.k1 = static_cast<uint32_t>(s.seed >> 32);
@@ -1251,7 +1545,8 @@ __global__ void __launch_bounds__(256, 3) fsb_step_kernel(const DevState s, cons
         }
         c.trace = s.trace_slot ? s.trace_slot[r] : -1;
         for (int q = 0; q < a.n_steps; ++q) {
-            step_replication(s, c, a.t_first + q, a.selector, a.flags);
+            FSB_MARK(0);
+            step_replication<FAST>(s, c, a.t_first + q, a.selector, a.flags);
             __syncthreads();
             if (s.err[r] & ~FSB_REP_TRACE_OVERFLOW) break;  // written by this CTA's thread 0 before the sync
         }

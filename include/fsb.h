@@ -209,6 +209,9 @@ int32_t fsb_debug_draws(fsb_engine *e, uint64_t seed, uint32_t rep, uint32_t sit
                         uint32_t idx0, int32_t n, int32_t kind /*0 normal 1 uniform 2 discrete*/,
                         uint32_t n_discrete, double *out);
 int32_t fsb_debug_dot(fsb_engine *e, const double *x, const double *y, int64_t n, double *out);
+/* cycles thread 0 of every CTA spent in each phase of the step kernel (profiling builds with
+ * -DFSB_PHASE_TIMING only; zeros otherwise); reset != 0 clears the counters */
+int32_t fsb_debug_phase_cycles(fsb_engine *e, uint64_t out[32], int32_t reset);
 
 #ifdef __cplusplus
 }

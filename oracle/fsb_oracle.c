@@ -545,8 +545,16 @@ void orc_liquidate(orc_world *w, int64_t col, const int64_t *div_inv, const int6
         double remainder = 1.0 - s;
         for (int64_t m = 0; m < M; ++m) H_(w, f, m) = H_(w, f, m) * remainder;
         S_(w, f, inv) = 0.0;
-        double tot = 0.0;
-        for (int64_t n = 0; n < N; ++n) tot = tot + S_(w, f, n);
+        /* sum(stakes[fund,:]): canonical order = the fund's investors (non-zero position in the fund,
+         * ascending id, the leaver included with its zeroed stake) dealt round-robin to 32 partial sums,
+         * combined by the butterfly tree 16,8,4,2,1 */
+        double part[32] = { 0.0 };
+        int64_t idx = 0;
+        for (int64_t n = 0; n < N; ++n)
+            if (A_(w, n, f) != 0.0) { part[idx & 31] = part[idx & 31] + S_(w, f, n); ++idx; }
+        for (int sft = 16; sft >= 1; sft >>= 1)
+            for (int l = 0; l < sft; ++l) part[l] = part[l] + part[l + sft];
+        double tot = part[0];
         if (tot > 0.0)
             for (int64_t n = 0; n < N; ++n) S_(w, f, n) = S_(w, f, n) / tot;
     }

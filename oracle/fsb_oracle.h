@@ -22,7 +22,8 @@
  *   sumw(x,n)       : same tree with a_l += x_e
  *   sumprodw(x,y,n) : same tree with a_l += fl(x_e*y_e)     (reference materialises x.*y first)
  *   sums over orders (column sums)      : sequential in order-row order, from +0.0
- *   sums over a fund's investors (stakes): sequential in ascending investor id, from +0.0
+ *   sum over a fund's investors (stakes, liquidate!): the fund's investors in ascending id dealt
+ *                     round-robin to 32 partial sums from +0.0, combined by the tree 16,8,4,2,1
  */
 #ifndef FSB_ORACLE_H
 #define FSB_ORACLE_H

@@ -20,8 +20,11 @@ with fsb.Engine(p, a.reps, steps_per_launch=a.steps_per_launch, blocks_per_sm=a.
                 block_threads=a.block_threads) as eng:
     eng.init_device(7)
     if a.t0 > 102:
-        eng.run(102, a.t0 - 1)
-    eng.run(a.t0, a.t0 + a.steps - 1)
+        eng.run_async(102, a.t0 - 1)
+        eng.sync()
+    eng.run_async(a.t0, a.t0 + a.steps - 1)  # replications the model itself stops (Q6) stay frozen, not fatal
+    eng.sync()
     ms, _, n = eng.last_run_timing()
+    nerr = int((eng.rep_status() != 0).sum())
     print(f"reps={a.reps} steps={a.steps} launches={n} total_ms={ms:.3f} per_launch_ms={ms / n:.4f} "
-          f"fund_steps_per_s={a.reps * p.bigk * a.steps / (ms * 1e-3):.4e}")
+          f"fund_steps_per_s={a.reps * p.bigk * a.steps / (ms * 1e-3):.4e} frozen_reps={nerr}")
