@@ -1,0 +1,114 @@
+# FundStabB200.jl -- the `ccall` glue a FundStabABM.jl maintainer adds to route the hot path
+# (Func.initialise, src/functions.jl:417; Func.modelrun, src/functions.jl:446) through
+# libfsb_b200.so (include/fsb.h).  No model logic lives here: every function marshals arrays that
+# Julia already stores column-major and turns a non-zero status into an error.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  The same symbols are
+# exercised from Python (fundstababm.jl_b200/_lib.py) by tests/.
+module FundStabB200
+
+const LIB = get(ENV, "FSB_LIB", "libfsb_b200.so")
+
+# mirrors `struct fsb_params` of include/fsb.h (Params.default, src/params.jl:4-31)
+struct FsbParams
+    bigm::Int64; bign::Int64; bigt::Int64; bigk::Int64
+    marketstartval::Float64; drift::Float64; marketvol::Float64
+    impact_values::Ptr{Float64}; n_impact::Int64
+    betamean::Float64; betastd::Float64; stockstartval::Float64
+    vol_values::Ptr{Float64}; n_vol::Int64
+    reviewprobability::Float64
+    perf_lo::Int64; perf_hi::Int64
+    cap_lo::Int64; cap_hi::Int64
+    thresholdmean::Float64; thresholdstd::Float64
+    psize_lo::Int64; psize_hi::Int64
+end
+
+# mirrors `struct fsb_config`
+struct FsbConfig
+    n_reps::Int64; rep_offset::Int64; reps_per_point::Int64
+    device::Int32; keep_history::Int32; event_capacity::Int32; log_capacity::Int32
+    trace_capacity::Int32; steps_per_launch::Int32; block_threads::Int32; blocks_per_sm::Int32
+end
+
+const SELECTORS = Dict("best" => 0, "goodenough" => 1, "probabilistic" => 2, "random" => 3)
+
+lasterror() = unsafe_string(ccall((:fsb_last_error, LIB), Cstring, ()))
+check(rc::Int32) = rc == 0 || error("libfsb_b200 error $rc: $(lasterror())")
+
+mutable struct Engine
+    handle::Ptr{Cvoid}
+    keep::Vector{Any}          # arrays the POD points to
+    function Engine(params; nreps=1, repoffset=0, device=0, keephistory=true)
+        imp = collect(Float64, params.impactrange)
+        vol = collect(Float64, params.stockvolrange)
+        p = FsbParams(params.bigm, params.bign, params.bigt, params.bigk,
+                      params.marketstartval, params.drift, params.marketvol,
+                      pointer(imp), length(imp), params.betamean, params.betastd, params.stockstartval,
+                      pointer(vol), length(vol), params.reviewprobability,
+                      first(params.perfwindow), last(params.perfwindow),
+                      params.invcaprange[1], params.invcaprange[2],
+                      params.thresholdmean, params.thresholdstd,
+                      first(params.portfsizerange), last(params.portfsizerange))
+        cfg = FsbConfig(nreps, repoffset, 0, device, keephistory ? 1 : 0, 0, 0, 0, 1, 0, 0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve imp vol check(ccall((:fsb_create, LIB), Int32,
+            (Ref{FsbParams}, Int32, Ref{FsbConfig}, Ref{Ptr{Cvoid}}), p, 1, cfg, h))
+        e = new(h[], Any[imp, vol])
+        finalizer(x -> (x.handle != C_NULL && ccall((:fsb_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle); x.handle = C_NULL), e)
+        return e
+    end
+end
+
+# Julia passes the struct fields directly: Matrix{Float64}/Vector{Float64}/Vector{Int64} are
+# column-major and rooted for the duration of the ccall.
+function upload!(e::Engine, market, stocks, investors, funds; rep=0)
+    check(ccall((:fsb_upload_state, LIB), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        e.handle, rep, market.value, stocks.value, stocks.beta, stocks.vol, stocks.impact, stocks.volume,
+        investors.assets, investors.horizon, investors.threshold, funds.holdings, funds.stakes, funds.value))
+end
+
+function download!(e::Engine, market, stocks, investors, funds; rep=0)
+    check(ccall((:fsb_download_state, LIB), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        e.handle, rep, market.value, stocks.value, stocks.beta, stocks.vol, stocks.impact, stocks.volume,
+        investors.assets, investors.horizon, investors.threshold, funds.holdings, funds.stakes, funds.value))
+end
+
+"Replacement for Func.initialise (src/functions.jl:417-430): Philox draws on the device."
+function initialise(market, stocks, investors, funds, params; seed=0, rep=0, device=0)
+    e = Engine(params; repoffset=rep, device=device)
+    check(ccall((:fsb_init_device, LIB), Int32, (Ptr{Cvoid}, UInt64), e.handle, seed))
+    download!(e, market, stocks, investors, funds)
+    finalize(e)
+end
+
+"Replacement for Func.modelrun (src/functions.jl:446-491); returns the log as a NamedTuple of columns (:452-456)."
+function modelrun(market, stocks, investors, funds, params, fundselector="bestperformer"; seed=0, rep=0, device=0)
+    haskey(SELECTORS, fundselector) || error("Please specify a valid fund selection method in reinvest!")  # Q9
+    e = Engine(params; repoffset=rep, device=device)
+    upload!(e, market, stocks, investors, funds)
+    check(ccall((:fsb_set_seed, LIB), Int32, (Ptr{Cvoid}, UInt64), e.handle, seed))
+    check(ccall((:fsb_run, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32, Int32),
+                e.handle, last(params.perfwindow) + 2, params.bigt, SELECTORS[fundselector], 0))
+    download!(e, market, stocks, investors, funds)
+    n = Ref{Int64}(0)
+    check(ccall((:fsb_download_log, LIB), Int32,
+        (Ptr{Cvoid}, Int64, Ref{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+        e.handle, 0, n, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL))
+    liquidated = zeros(Int64, n[]); replacedby = zeros(Int64, n[]); failtime = zeros(Int64, n[])
+    ninvestors = zeros(Int64, n[]); nstocks = zeros(Int64, n[])
+    initialsize = zeros(Float64, n[]); liquidity = zeros(Float64, n[])
+    check(ccall((:fsb_download_log, LIB), Int32,
+        (Ptr{Cvoid}, Int64, Ref{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+        e.handle, 0, n, liquidated, replacedby, initialsize, liquidity, failtime, ninvestors, nstocks))
+    finalize(e)
+    # wrap with DataFrame(...) where DataFrames is loaded: logisticregression (:846-856) and
+    # plot_liquidationcounts (:832) read exactly these column names
+    return (liquidated=liquidated, replacedby=replacedby, initialsize=initialsize, liquidity=liquidity,
+            failtime=failtime, ninvestors=ninvestors, nstocks=nstocks)
+end
+
+end # module

@@ -1,0 +1,90 @@
+"""Turns the scratch ncu outputs of scripts/gpu_check.sh (gpurun_out/) into the tracked summaries under
+profiles/:  <tag>_launches.csv (the launch list of the bench command), <tag>_step_kernel.md (selected
+counters of the full capture of the step kernel) and traffic_per_launch.json (DRAM bytes per
+replication-step, read by bench.py for roofline.traffic).
+    usage: python scripts/summarize_profile.py <tag> [reps-in-the-full-capture]"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+out, prof = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+os.makedirs(prof, exist_ok=True)
+
+# ---- launch list -------------------------------------------------------------------------------
+src = os.path.join(out, f"launches_{tag}.csv")
+if os.path.exists(src):
+    rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit()]
+    with open(os.path.join(prof, f"{tag}_launches.csv"), "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 6 --warmup 3 --no-cpu-baseline\n")
+        f.write("# per-launch times are cold-cache and serialised: compare shares, not absolutes\n")
+        f.write("id,kernel,grid,block,duration_ms\n")
+        tot, by = 0.0, {}
+        for r in rows:
+            ms = float(r[-1]) / 1e6
+            name = r[4].split("(")[0].replace("void ", "")
+            f.write(f"{r[0]},{name},{r[8].strip('()').split(',')[0]},{r[7].strip('()').split(',')[0]},{ms:.4f}\n")
+            tot += ms
+            by[name] = by.get(name, 0.0) + ms
+        f.write("# share of device time by kernel: " + ", ".join(f"{k} {100 * v / tot:.1f}%" for k, v in sorted(by.items(), key=lambda kv: -kv[1])) + "\n")
+    print("wrote", f"profiles/{tag}_launches.csv")
+
+# ---- full capture of the step kernel -------------------------------------------------------------
+rep = os.path.join(out, f"prof_{tag}_step.ncu-rep")
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+            "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__maximum_warps_per_active_cycle_pct",
+            "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
+            "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
+            "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.sum",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts.sum",
+            "sm__cycles_elapsed.max", "smsp__cycles_active.avg"]
+    stall = [h for h in hdr if h.startswith("smsp__average_warp") and "issue_stalled" in h and h.endswith("_per_warp_active.pct")]
+    lines = [f"# {tag}: ncu --set full --clock-control none of fsb_step_kernel", "",
+             f"Command: `python scripts/prof_step.py --reps {reps} --steps 3 --t0 300` (default Params shape, probabilistic selector); "
+             "one row per captured launch.  Numbers under a profiler are not bench values.", ""]
+    traffic = []
+    for r in rows[2:]:
+        lines.append(f"## launch {r[hdr.index('ID')]}: {r[hdr.index('Kernel Name')]}")
+        lines.append("")
+        lines.append("| metric | value | unit |")
+        lines.append("|---|---|---|")
+        vals = {}
+        for w in want + stall:
+            if w in hdr:
+                i = hdr.index(w)
+                vals[w] = r[i]
+                lines.append(f"| {w} | {r[i]} | {units[i]} |")
+
+        def num(key):
+            i = hdr.index(key)
+            v = float(r[i].replace(",", ""))
+            u = units[i].lower()
+            return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "tbyte": 1e12}.get(u, 1.0)
+        dram = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+        traffic.append(dram / reps)
+        inst = float(vals["smsp__inst_executed.sum"].replace(",", ""))
+        lines += ["", f"DRAM bytes per replication-step: {dram / reps / 1e3:.1f} KB (algorithmic: 528.0 KB); "
+                      f"warp instructions per replication-step: {inst / reps:.0f}", ""]
+    open(os.path.join(prof, f"{tag}_step_kernel.md"), "w").write("\n".join(lines) + "\n")
+    json.dump({"tag": tag, "dram_bytes_per_replication_step": sum(traffic) / len(traffic),
+               "source": f"profiles/{tag}_step_kernel.md (dram__bytes_read.sum + dram__bytes_write.sum over {reps} replication-steps per launch)"},
+              open(os.path.join(prof, "traffic_per_launch.json"), "w"), indent=1)
+    print("wrote", f"profiles/{tag}_step_kernel.md", "traffic/rep-step KB:", [round(t / 1e3, 1) for t in traffic])
+
+# ---- the bench line itself ---------------------------------------------------------------------
+for name in (f"bench_{tag}.json", f"bench_ref_{tag}.json"):
+    p = os.path.join(out, name)
+    if os.path.exists(p) and os.path.getsize(p):
+        open(os.path.join(prof, name), "w").write(open(p).read())
+        print("copied", name)
