@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -184,12 +185,12 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     const fsb_params &p0 = pts[0];
     d.K = static_cast<int>(p0.bigk); d.M = static_cast<int>(p0.bigm); d.N = static_cast<int>(p0.bign);
     d.T = static_cast<int>(p0.bigt); d.W = static_cast<int>(p0.perf_hi);
-    d.Mp = (d.M + 1) & ~1;
+    d.Mp = (d.M + 127) & ~127;  // 1 KiB row granules: no tails or masks in the 8-lane loops, rows start on 128-byte lines
     d.keep_history = cfg->keep_history ? 1 : 0;
     d.hist_cols = d.keep_history ? d.T : 2 * (d.W + 1);
     d.mkt_len = d.keep_history ? d.T : 2;
     d.R = cfg->n_reps; d.rep_offset = cfg->rep_offset; d.reps_per_point = cfg->reps_per_point; d.n_points = n_points;
-    d.h_stride = ((static_cast<long long>(d.K) * d.Mp + 15) / 16) * 16;
+    d.h_stride = ((static_cast<long long>((d.K + 3) & ~3) * d.Mp + 15) / 16) * 16;
     d.p_stride = static_cast<long long>(d.hist_cols) * d.Mp;
     // event capacity: reviewers ~ Binomial(N, p); mean + 12 sd + 16
     double pmax = 0.0;
@@ -201,30 +202,33 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     d.cap_ev = (cap + 7) & ~7;
     d.cap_log = cfg->log_capacity > 0 ? std::max(cfg->log_capacity, d.K + 1) : d.K + 1024;
     d.cap_trace = cfg->trace_capacity > 0 ? cfg->trace_capacity : 1 << 20;
-    e->block = cfg->block_threads > 0 ? ((cfg->block_threads + 31) / 32) * 32 : 256;
-    if (e->block > 256) e->block = 256;
-    // shared memory: shrink the pass-2 column chunk until the layout fits
-    int smem_max = 0;
+    e->block = cfg->block_threads > 0 ? ((cfg->block_threads + 31) / 32) * 32 : kStepThreads;
+    if (e->block > kStepThreads) e->block = kStepThreads;
+    // shared memory: the largest horizon-column chunk (2, 6, 10 or 14 columns) that leaves room for the
+    // wanted number of CTAs per SM
+    int smem_max = 0, smem_sm = 0;
     CU(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+    CU(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
     if (d.K >= 32768) { delete e; return fail(FSB_ERR_BAD_PARAMS, "bigk must be < 32768 (16-bit fund ids in shared memory)"); }
+    int want_ctas = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : 4;
+    if (const char *ev = getenv("FSB_CTAS_PER_SM")) want_ctas = std::max(1, atoi(ev));
+    const int budget = std::min(smem_max, smem_sm / want_ctas - 1024);
     d.cmax = kMaxCols;
+    if (const char *ev = getenv("FSB_CMAX")) d.cmax = std::min(kMaxCols, std::max(2, ((atoi(ev) + 2) / 4) * 4 - 2));
     SmemLayout L = make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax, e->block / 32);
-    while (L.bytes + 64 > std::min(smem_max, 74 * 1024) && d.cmax > 1) {  // aim at 3 CTAs per SM
-        --d.cmax;
+    while (L.bytes + 64 > budget && d.cmax > 2) {
+        d.cmax -= 4;
         L = make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax, e->block / 32);
     }
     if (L.bytes + 64 > smem_max) { delete e; return fail(FSB_ERR_BAD_PARAMS, "shapes need %d bytes of shared memory per CTA (> %d)", L.bytes, smem_max); }
     e->smem_bytes = L.bytes;
     e->init_smem = (d.W + 2 + d.K) * 8;
-    // FAST kernel: column pitch 256 doubles at compile time (192 < Mp <= 256 and K <= 256: the default shape)
-    e->fast = (L.cp == 256 && L.cpk == 256);
-    CU(cudaFuncSetAttribute(fsb_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_bytes));
-    CU(cudaFuncSetAttribute(fsb_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_bytes));
+    e->fast = (d.K <= 256);
+    CU(cudaFuncSetAttribute(fsb_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_bytes));
     if (e->init_smem > 48 * 1024) CU(cudaFuncSetAttribute(fsb_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->init_smem));
     int sms = 0, occ = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-    if (e->fast) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fsb_step_kernel<true>, e->block, e->smem_bytes));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fsb_step_kernel<false>, e->block, e->smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fsb_step_kernel, e->block, e->smem_bytes));
     if (occ < 1) { delete e; return fail(FSB_ERR_CUDA, "step kernel cannot be resident (smem %d)", e->smem_bytes); }
     if (cfg->blocks_per_sm > 0) occ = std::min(occ, cfg->blocks_per_sm);
     e->grid = static_cast<int>(std::min<long long>(d.R, static_cast<long long>(sms) * occ));
@@ -267,15 +271,21 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     A(mkt_peak, R); A(mkt_dd, R);
     A(flow_hist, R * kFlowBins);
     A(scratch, static_cast<size_t>(e->grid) * d.cap_ev * d.Mp);
+    A(keys, static_cast<size_t>(e->grid) * d.cmax * ((d.K + 3) & ~3));
     A(queue, 2);
 #undef A
     {
-        DevPoint *pd = nullptr; double *td = nullptr;
-        if (dalloc(e, &pd, e->points.size()) != FSB_OK || dalloc(e, &td, tables.size()) != FSB_OK) return cleanup(FSB_ERR_CUDA);
+        DevPoint *pd = nullptr; double *td = nullptr, *rt = nullptr;
+        if (dalloc(e, &pd, e->points.size()) != FSB_OK || dalloc(e, &td, tables.size()) != FSB_OK || dalloc(e, &rt, d.K) != FSB_OK) return cleanup(FSB_ERR_CUDA);
+        // rank probabilities of the rank rule: rank / normaliser in IEEE FP64, as functions.jl:405-406 divides
+        std::vector<double> ranktab(d.K);
+        const double normaliser = static_cast<double>(static_cast<long long>(d.K) * (d.K + 1) / 2);
+        for (int i = 0; i < d.K; ++i) ranktab[i] = static_cast<double>(i + 1) / normaliser;
         if (cudaMemcpy(pd, e->points.data(), e->points.size() * sizeof(DevPoint), cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(td, tables.data(), tables.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+            cudaMemcpy(td, tables.data(), tables.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(rt, ranktab.data(), ranktab.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
             return cleanup(fail(FSB_ERR_CUDA, "cannot upload parameter tables"));
-        d.points = pd; d.tables = td;
+        d.points = pd; d.tables = td; d.ranktab = rt;
     }
     e->words_per_point = FSB_STATS_HEADER + (d.T + 1) + FSB_STATS_LIQ_BINS + FSB_STATS_DD_BINS + FSB_STATS_FLOW_BINS;
     if (dalloc(e, &e->stats_dev, static_cast<size_t>(n_points) * e->words_per_point) != FSB_OK) return cleanup(FSB_ERR_CUDA);
@@ -547,8 +557,7 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
         const int spl = std::max(1, e->cfg.steps_per_launch);
         for (int64_t t = t_first; t <= t_last; t += spl) {
             StepArgs a{static_cast<int>(t), static_cast<int>(std::min<int64_t>(spl, t_last - t + 1)), selector, flags};
-            if (e->fast) fsb_step_kernel<true><<<e->grid, e->block, e->smem_bytes, e->stream>>>(d, a, e->launch_parity);
-            else fsb_step_kernel<false><<<e->grid, e->block, e->smem_bytes, e->stream>>>(d, a, e->launch_parity);
+            fsb_step_kernel<<<e->grid, e->block, e->smem_bytes, e->stream>>>(d, a, e->launch_parity);
             e->launch_parity ^= 1;
             ++e->last_launches;
         }

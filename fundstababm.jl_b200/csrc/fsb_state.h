@@ -20,7 +20,7 @@ enum { CNT_REVIEWS = 0, CNT_DIVEST = 1, CNT_REINVEST = 2, CNT_STEPS = 3, CNT_FLO
 struct DevState {
     // shapes
     int K, M, N, T, W;
-    int Mp;         // row pitch of holdings / price columns: M rounded up to even (16-byte rows)
+    int Mp;         // row pitch of holdings / price columns: M rounded up to a multiple of 128 (zero padded)
     int hist_cols;  // price columns kept per replication: T (keep_history) or 2(W+1)
     int mkt_len;    // T (keep_history) or 2
     int keep_history;
@@ -31,7 +31,7 @@ struct DevState {
     long long p_stride;  // doubles per replication in P
     unsigned long long seed;
     // fund x asset
-    double *H;  // [R][K][Mp] holdings, asset fastest
+    double *H;  // [R][K4][Mp] holdings, asset fastest; K4 = K rounded up to 4 (zero rows, never written)
     // asset
     double *P;       // [R][hist_cols][Mp] price history (burn-in 1..W+1, then ring or full)
     double *beta, *vol, *impact;  // [R][Mp]
@@ -68,7 +68,9 @@ struct DevState {
     fsb_trace_rec *tr_recs;                // [slots][cap_trace]
     int *tr_n;                             // [slots]
     // per-CTA scratch + work queue
-    double *scratch;  // [grid][cap_ev][Mp] order rows
+    double *scratch;  // [grid][cap_ev][Mp] order rows beyond the shared-memory ones
+    unsigned long long *keys;  // [grid][cmax][K4] horizon returns of the step being processed (per CTA, L2 resident)
+    const double *ranktab;     // [K] (i + 1) / (K (K + 1) / 2): rank probabilities of the rank rule (Q14)
     int *queue;       // [2] dynamic work counters (double buffered across launches)
     const DevPoint *points;
     const double *tables;

@@ -5,17 +5,24 @@
 // revaluation -> rank-based reinvestment -> buy impact.
 //
 // Schedule (DESIGN.md "The step kernel"): the K x M holdings cross HBM ONCE per step.
-//   1. shocks + reviewer draw (Philox), prices of the day and the investor->fund map go to shared memory
-//   2. "review pass": only the <= ~16 reviewed funds' rows are read, against 3 price columns each
-//      (today, t-h, h), 4 reviewers per warp (8 lanes each) -> divestments
-//   3. stake sequence, sale orders, net demand per asset, price impact, cash-outs (event sized)
-//   4. respawn (rare) and the cash holders' horizons -> up to cmax history columns staged in shared
-//      memory by bulk asynchronous copies (TMA unit)
-//   5. "full pass": every holdings row is read once (8 lanes per row, 128-byte requests, rows L2-
-//      prefetched two rounds ahead by bulk prefetches) and multiplied against 2 + ncols columns at
-//      once: NAV at the opening prices, NAV at the post-impact prices, back-cast NAVs per horizon
-//   6. ranks by an in-shared-memory bitonic sort per horizon column, fund choice, stake dilution,
-//      buy orders, impact, share disbursement (event sized)
+//   T0  shocks + reviewer draw (Philox), prices of the day and the investor->fund map go to shared memory
+//   T1  "review pass": only the <= ~16 reviewed funds' rows are read, against 3 price columns each
+//       (today, t-h, h), 4 reviewers per warp (8 lanes each) -> divestments
+//   T2  stake sequence, sale orders, net demand per asset, price impact, cash-outs (event sized)
+//   T3  respawn (0.23 per step) -> T4 the cash holders' distinct horizons: up to cmax history columns are
+//       staged in shared memory by bulk asynchronous copies (TMA unit)
+//   T5  "full pass": every holdings row is read once, 4 rows per warp and round.  A warp's four 8-lane
+//       groups own DIFFERENT COLUMNS (column q belongs to group q % 4), so one 128-bit shared-memory load
+//       of a column word feeds 8 FMAs and every quarter-warp reads distinct data; the holdings words are
+//       loaded straight from global memory through a 4-deep register ring, rows L2-prefetched two rounds
+//       ahead by bulk prefetches.  Results: NAV at the opening prices, NAV at the post-impact prices,
+//       back-cast returns per horizon (as order-preserving sort keys, into an L2-resident per-CTA scratch)
+//   T6  ranks per horizon by an in-register bitonic sort, fund choice, stake dilution, buy orders, impact,
+//       share disbursement (event sized)
+// Code layout: the step is a sequence of SMALL __noinline__ phase functions around one context struct
+// in shared memory.  A fully inlined step is ~26k SASS instructions; with 16 warps per SM in different
+// phases that thrashes the 32 KB instruction cache (ncu: stall_no_instruction dominant, icc hit rate 54 %),
+// so loops stay rolled and cold paths (respawn, traces, tapes) are out of line.
 // Everything variable-length is a fixed-capacity list in shared memory with an overflow flag that
 // raises FSB_REP_EVENT_OVERFLOW (never a silent drop).
 #pragma once
@@ -24,30 +31,13 @@
 
 namespace fsb {
 
-// Optional per-phase cycle accounting (scripts/phase_cycles.py): build with -DFSB_PHASE_TIMING.
-// Thread 0 of every CTA adds the cycles since its previous mark to g_phase_cycles[id].
-#ifdef FSB_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[32];
-#define FSB_MARK(id)                                                                   \
-    do {                                                                               \
-        if (threadIdx.x == 0) {                                                        \
-            const long long now_ = clock64();                                          \
-            atomicAdd(&g_phase_cycles[id], static_cast<unsigned long long>(now_ - c.tmark)); \
-            c.tmark = now_;                                                            \
-        }                                                                              \
-    } while (0)
-#else
-#define FSB_MARK(id) do { } while (0)
-#endif
-
-// Holdings prefetch policy into L2 (experiments: -DFSB_PF_MODE=n): 0 none, 1 two rounds ahead of the
-// full pass, 2 the whole K x M block at the start of the step
-#ifndef FSB_PF_MODE
-#define FSB_PF_MODE 1
-#endif
-
 constexpr double kPriceFloor = 0.000000001;  // functions.jl:208-209 (Q10)
-constexpr int kMaxCols = 10;                 // horizon columns per full pass (template bound)
+constexpr int kMaxCols = 14;                 // horizon columns per full pass (4 groups x 4 columns, minus the 2 price columns)
+constexpr int kPfAhead = 2;                  // holdings rounds prefetched into L2 ahead of the loads
+constexpr int kStepThreads = 128;
+#ifndef FSB_FP_INLINE
+#define FSB_FP_INLINE __forceinline__
+#endif
 
 struct StepArgs {
     int t_first, n_steps, selector, flags;
@@ -56,17 +46,16 @@ struct StepArgs {
 // shared-memory carve-up; sizes depend on the engine's shapes (host computes the same layout)
 struct SmemLayout {
     // doubles
-    int off_cols, off_vh, off_ratio, off_sellsum, off_nav, off_stk, off_dstake, off_dcash, off_rinj, off_rfval, off_rncap, off_scal;
+    int off_cols, off_ratio, off_sellsum, off_nav, off_dstake, off_dcash, off_rinj, off_rfval, off_rncap, off_scal;
     // ints (after the doubles)
     int off_rev, off_rfund, off_dinv, off_dfund, off_cash, off_rchoice, off_rcol, off_hcols, off_eggs, off_wl, off_wcnt,
         off_flags, off_nzf, off_pick, off_fmod, off_fsel, off_isc;
     // 16-bit words (after the ints), then bytes
-    int off_pos16, off_hor16, off_sidx, off_stl;
+    int off_pos16, off_hor16;
     int cp;     // column pitch in doubles: Mp rounded up to 128 (zero padded, so 8-lane loops need no tail)
-    int cpk;    // pitch of a staged column / probability row: max(cp, kp2)
-    int kq;     // pitch of a vh / key row: kp2
-    int kp2;    // K rounded up to a power of two >= 256 (bitonic sort length)
-    int srows;  // order rows that fit in the (cols[2..], vh) region while it is not holding columns
+    int cpk;    // pitch of a staged column / probability row: max(cp, kq)
+    int kq;     // K rounded up to a multiple of 4 (pitch of a key row in the global scratch)
+    int srows;  // order rows that fit in the staged-column region while it is not holding columns
     int wsd;    // doubles of that region per warp (member lists of the stake sequence)
     int ndoubles, nints, nshorts;
     int bytes;
@@ -75,21 +64,17 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap, int cmax, int nwarps)
 {
     SmemLayout L;
-    L.cp = (Mp + 127) & ~127;
-    int kp2 = 256;
-    while (kp2 < K) kp2 <<= 1;
-    L.kp2 = kp2;
-    L.cpk = L.cp > kp2 ? L.cp : kp2;
-    L.kq = kp2;
+    L.cp = (Mp + 127) & ~127;  // == Mp: the engine rounds Mp up to 128 itself
+    L.kq = (K + 3) & ~3;
+    const int kp = (L.kq + 127) & ~127;
+    L.cpk = L.cp > kp ? L.cp : kp;
     int d = 0;
     L.off_cols = d; d += (cmax + 2) * L.cpk;   // col 0: opening prices, col 1: current prices, 2..: staged history
-    L.off_vh = d; d += cmax * L.kq;            // must follow cols (order rows span both)
-    L.srows = (cmax * (L.cpk + L.kq)) / L.cp;
-    L.wsd = ((cmax * (L.cpk + L.kq)) / nwarps) & ~1;
+    L.srows = (cmax * L.cpk) / L.cp;
+    L.wsd = ((cmax * L.cpk) / nwarps) & ~1;
     L.off_ratio = d; d += L.cp;
     L.off_sellsum = d; d += L.cp;
-    L.off_nav = d; d += (K + 1) & ~1;
-    L.off_stk = d; d += (N + 1) & ~1;      // the stakes of the day (write-through copy of stake[])
+    L.off_nav = d; d += L.kq;
     L.off_dstake = d; d += cap;
     L.off_dcash = d; d += cap;
     L.off_rinj = d; d += cap;
@@ -121,53 +106,150 @@ __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap,
     int h = 0;
     L.off_pos16 = h; h += (N + 7) & ~7;  // padded with -1 to whole 16-byte words
     L.off_hor16 = h; h += (N + 7) & ~7;
-    L.off_sidx = h; h += cmax * kp2;
     L.nshorts = h;
-    L.off_stl = 0;
-    L.bytes = d * 8 + i * 4 + h * 2 + ((K + 15) & ~15);
+    L.bytes = 1024 /* kCtxBytes */ + d * 8 + i * 4 + h * 2 + 2 * ((K + 15) & ~15);  // Ctx + arrays + stl[K], hz[K] bytes
     return L;
 }
 
+extern __shared__ __align__(16) unsigned char fsb_smem[];  // dynamic shared memory: Ctx, then the arrays of SmemLayout
+constexpr int kCtxBytes = 1024;
+
+// The step's context: ONE instance per CTA in shared memory, filled by thread 0 per replication.
+// Phase functions receive a reference to it; thread-private ids are recomputed from threadIdx.
 struct Ctx {
-    // shared
-    double *cols, *vh, *ratio, *sellsum, *nav, *stk, *d_stake, *d_cash, *r_inj, *r_fval, *r_ncap, *scal;
-    int *rev, *rfund, *d_inv, *d_fund, *cash, *r_choice, *r_col, *hcols, *eggs, *wl, *wcnt, *flags, *nzf, *pick, *fmod, *fsel, *isc;
-    short *pos16;
-    unsigned short *hor16, *sidx;
-    unsigned char *stl;
+    // shapes / configuration (copies of DevState fields)
+    int K, M, N, Mp, T, W, cap, cmax, keep_history, cap_log, cap_trace, fast, rank256;
+    int cp, cpk, kq, srows, wsd;
+    // shared arrays: byte offsets into the dynamic shared memory (accessors below keep the address space known)
+    int o_cols, o_ratio, o_sellsum, o_nav, o_d_stake, o_d_cash, o_r_inj, o_r_fval, o_r_ncap, o_scal;
+    int o_rev, o_rfund, o_d_inv, o_d_fund, o_cash, o_r_choice, o_r_col, o_hcols, o_eggs, o_wl, o_wcnt, o_flags, o_nzf, o_pick, o_fmod, o_fsel, o_isc;
+    int o_pos16, o_hor16, o_stl, o_hz;
     unsigned long long *mbar;
     unsigned mbar_phase;
-    int cp, cpk, kq, kp2, srows, wsd;
     // replication
     double *H, *P, *beta, *vol, *impact, *volume, *market, *stake, *amount, *threshold, *nav_open, *nav_close;
     int *pos, *horizon, *live_row, *cnt;
     unsigned char *hzero, *stakeless;
-    double *scratch;
+    double *mkt_peak, *mkt_dd;
+    int *flow_hist, *err;
+    // liquidation log of the replication (functions.jl:452-456)
+    int *log_n, *log_liquidated, *log_replacedby, *log_failtime, *log_ninv, *log_nstocks;
+    double *log_size, *log_liquidity;
+    // per-CTA global scratch
+    double *scratch;           // order rows beyond the shared-memory ones
+    unsigned long long *keys;  // [cmax][kq] horizon returns of the step (sort keys or raw bits), L2 resident
+    const double *ranktab;
+    // draws
     const double *z_mkt, *z_stock, *u_review;
     const fsb_tape_rec *tape;
     long long n_tape;
-    int trace;      // slot or -1
     int tape_toff;  // dense tapes are indexed by t - 1 - tape_toff
     Rng rng;
+    double drift, marketvol, reviewprob;
+    int psize_lo, psize_hi;
+    // trace (slot < 0: not traced)
+    int trace;
+    double *tr_nav, *tr_psell, *tr_presp;
+    fsb_trace_rec *tr_recs;
+    int *tr_n;
     long long r;
-    const DevPoint *pt;
-    int tid, lane, warp, nwarps, nthreads;
     long long tmark;
+    // accessors
+    __device__ __forceinline__ double *cols_() const { return reinterpret_cast<double *>(fsb_smem + o_cols); }
+    __device__ __forceinline__ double *ratio_() const { return reinterpret_cast<double *>(fsb_smem + o_ratio); }
+    __device__ __forceinline__ double *sellsum_() const { return reinterpret_cast<double *>(fsb_smem + o_sellsum); }
+    __device__ __forceinline__ double *nav_() const { return reinterpret_cast<double *>(fsb_smem + o_nav); }
+    __device__ __forceinline__ double *d_stake_() const { return reinterpret_cast<double *>(fsb_smem + o_d_stake); }
+    __device__ __forceinline__ double *d_cash_() const { return reinterpret_cast<double *>(fsb_smem + o_d_cash); }
+    __device__ __forceinline__ double *r_inj_() const { return reinterpret_cast<double *>(fsb_smem + o_r_inj); }
+    __device__ __forceinline__ double *r_fval_() const { return reinterpret_cast<double *>(fsb_smem + o_r_fval); }
+    __device__ __forceinline__ double *r_ncap_() const { return reinterpret_cast<double *>(fsb_smem + o_r_ncap); }
+    __device__ __forceinline__ double *scal_() const { return reinterpret_cast<double *>(fsb_smem + o_scal); }
+    __device__ __forceinline__ int *rev_() const { return reinterpret_cast<int *>(fsb_smem + o_rev); }
+    __device__ __forceinline__ int *rfund_() const { return reinterpret_cast<int *>(fsb_smem + o_rfund); }
+    __device__ __forceinline__ int *d_inv_() const { return reinterpret_cast<int *>(fsb_smem + o_d_inv); }
+    __device__ __forceinline__ int *d_fund_() const { return reinterpret_cast<int *>(fsb_smem + o_d_fund); }
+    __device__ __forceinline__ int *cash_() const { return reinterpret_cast<int *>(fsb_smem + o_cash); }
+    __device__ __forceinline__ int *r_choice_() const { return reinterpret_cast<int *>(fsb_smem + o_r_choice); }
+    __device__ __forceinline__ int *r_col_() const { return reinterpret_cast<int *>(fsb_smem + o_r_col); }
+    __device__ __forceinline__ int *hcols_() const { return reinterpret_cast<int *>(fsb_smem + o_hcols); }
+    __device__ __forceinline__ int *eggs_() const { return reinterpret_cast<int *>(fsb_smem + o_eggs); }
+    __device__ __forceinline__ int *wl_() const { return reinterpret_cast<int *>(fsb_smem + o_wl); }
+    __device__ __forceinline__ int *wcnt_() const { return reinterpret_cast<int *>(fsb_smem + o_wcnt); }
+    __device__ __forceinline__ int *flags_() const { return reinterpret_cast<int *>(fsb_smem + o_flags); }
+    __device__ __forceinline__ int *nzf_() const { return reinterpret_cast<int *>(fsb_smem + o_nzf); }
+    __device__ __forceinline__ int *pick_() const { return reinterpret_cast<int *>(fsb_smem + o_pick); }
+    __device__ __forceinline__ int *fmod_() const { return reinterpret_cast<int *>(fsb_smem + o_fmod); }
+    __device__ __forceinline__ int *fsel_() const { return reinterpret_cast<int *>(fsb_smem + o_fsel); }
+    __device__ __forceinline__ int *isc_() const { return reinterpret_cast<int *>(fsb_smem + o_isc); }
+    __device__ __forceinline__ short *pos16_() const { return reinterpret_cast<short *>(fsb_smem + o_pos16); }
+    __device__ __forceinline__ unsigned short *hor16_() const { return reinterpret_cast<unsigned short *>(fsb_smem + o_hor16); }
+    __device__ __forceinline__ unsigned char *stl_() const { return fsb_smem + o_stl; }
+    __device__ __forceinline__ unsigned char *hz_() const { return fsb_smem + o_hz; }
 };
 
-// isc[] slots
-enum { I_ND = 0, I_NCASH, I_NEGGS, I_ERR, I_TMP0, I_TMP1, I_TMP2, I_NCOLS, I_IDLE };
+// Optional per-phase cycle accounting (scripts/phase_cycles.py): build with -DFSB_PHASE_TIMING.
+// Thread 0 of every CTA adds the cycles since its previous mark to g_phase_cycles[id].
+#ifdef FSB_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[32];
+#define FSB_MARK(id)                                                                   \
+    do {                                                                               \
+        if (threadIdx.x == 0) {                                                        \
+            const long long now_ = clock64();                                          \
+            atomicAdd(&g_phase_cycles[id], static_cast<unsigned long long>(now_ - c.tmark)); \
+            c.tmark = now_;                                                            \
+        }                                                                              \
+    } while (0)
+#else
+#define FSB_MARK(id) do { } while (0)
+#endif
 
-__device__ __forceinline__ double *p_open(const Ctx &c) { return c.cols; }
-__device__ __forceinline__ double *p_cur(const Ctx &c) { return c.cols + c.cpk; }
-// order row o (sale / buy values per asset): shared memory while it fits, per-CTA global scratch beyond
-__device__ __forceinline__ double *order_row(const Ctx &c, int Mp, int o)
+// isc[] slots
+enum { I_ND = 0, I_NCASH, I_NEGGS, I_ERR, I_TMP0, I_TMP1, I_TMP2, I_NCOLS, I_IDLE, I_NREV, I_DEAD };
+
+__device__ __forceinline__ Ctx &ctx() { return *reinterpret_cast<Ctx *>(fsb_smem); }
+
+#define FSB_TH                                                                               \
+    const int tid = threadIdx.x, NT = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, \
+              nwarps = blockDim.x >> 5;                                                      \
+    (void)tid; (void)NT; (void)lane; (void)warp; (void)nwarps
+
+__device__ __forceinline__ int pcol(const Ctx &c, int t)  // 1-based t -> column slot
 {
-    return (o < c.srows) ? c.cols + 2 * c.cpk + o * c.cp : c.scratch + static_cast<long long>(o - c.srows) * Mp;
+    if (c.keep_history || t <= c.W + 1) return t - 1;
+    return (c.W + 1) + ((t - 1) % (c.W + 1));
+}
+__device__ __forceinline__ int mslot(const Ctx &c, int t) { return c.keep_history ? t - 1 : (t & 1); }
+__device__ __forceinline__ double *p_open(const Ctx &c) { return c.cols_(); }
+__device__ __forceinline__ double *p_cur(const Ctx &c) { return c.cols_() + c.cpk; }
+// order row o (sale / buy values per asset): shared memory while it fits, per-CTA global scratch beyond
+__device__ __forceinline__ double *order_row(const Ctx &c, int o)
+{
+    return (o < c.srows) ? c.cols_() + 2 * c.cpk + o * c.cp : c.scratch + static_cast<long long>(o - c.srows) * c.Mp;
 }
 
-// (the two helpers below are real calls -- cold paths kept out of the instruction stream -- and take
-// plain values, so that the Ctx of the caller stays in registers)
+// ---- out-of-line building blocks (one copy each in the instruction stream) -------------------------
+__device__ __noinline__ double ddiv(double x, double y) { return x / y; }
+// x / y, skipping the division for the very common zero numerator (assets a fund does not hold): for
+// 0 < y < inf the IEEE quotient of a zero is that same signed zero
+__device__ __forceinline__ double qdiv(double x, double y)
+{
+    return (x == 0.0 && y > 0.0 && y < 1.7976931348623157e308) ? x : ddiv(x, y);
+}
+__device__ __noinline__ uint4 philox_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+    return philox4x32_10(make_uint4(c0, c1, c2, c3), k0, k1);
+}
+__device__ __forceinline__ uint4 draw_block_s(const Rng &g, uint32_t site, uint32_t a, uint32_t b, uint32_t block)
+{
+    return philox_call(block, a, site | (b << 8), g.rep, g.k0, g.k1);
+}
+__device__ __forceinline__ uint32_t draw_discrete_s(const Rng &g, uint32_t site, uint32_t a, uint32_t b, uint32_t idx, uint32_t n)
+{
+    const uint4 w = draw_block_s(g, site, a, b, idx >> 2);
+    return __umulhi(word_of(w, idx & 3), n);
+}
+
 __device__ __noinline__ bool tape_lookup_raw(const fsb_tape_rec *tape, long long n_tape, int site, int t, int a, int b, double *out)
 {
     const unsigned long long key = (static_cast<unsigned long long>(site & 0xff) << 56) |
@@ -200,67 +282,74 @@ __device__ __noinline__ void trace_emit_raw(fsb_trace_rec *recs, int *n_ptr, int
         atomicOr(err_ptr, FSB_REP_TRACE_OVERFLOW);
     }
 }
-__device__ __forceinline__ void trace_emit(const DevState &s, const Ctx &c, int t, int kind, int a, int b, double v)
+__device__ __forceinline__ void trace_emit(const Ctx &c, int t, int kind, int a, int b, double v)
 {
-    trace_emit_raw(s.tr_recs + static_cast<long long>(c.trace) * s.cap_trace, s.tr_n + c.trace, s.cap_trace, s.err + c.r, t, kind, a, b, v);
+    trace_emit_raw(c.tr_recs, c.tr_n, c.cap_trace, c.err, t, kind, a, b, v);
+}
+// trace points of a traced replication (cold): which = 0 reviewers + divestments, 1 cash-outs + prices
+// after the sale, 2 prices after the respawn, 3 opening NAVs, 4 choices
+__device__ __noinline__ void trace_phase(int t, int which, int n0, int n1)
+{
+    Ctx &c = ctx();
+    FSB_TH;
+    const long long col = static_cast<long long>(t - 1);
+    if (which == 0) {
+        if (tid == 0) {
+            for (int i = 0; i < n0; ++i) trace_emit(c, t, FSB_EV_REVIEWER, c.rev_()[i], 0, 0.0);
+            for (int o = 0; o < n1; ++o) trace_emit(c, t, FSB_EV_DIVEST, c.d_inv_()[o], c.d_fund_()[o], 0.0);
+        }
+    } else if (which == 1) {
+        if (tid == 0)
+            for (int o = 0; o < n0; ++o) trace_emit(c, t, FSB_EV_CASHOUT, c.d_inv_()[o], c.d_fund_()[o], c.d_cash_()[o]);
+        for (int m = tid; m < c.M; m += NT) c.tr_psell[m + c.M * col] = p_cur(c)[m];
+    } else if (which == 2) {
+        for (int m = tid; m < c.M; m += NT) c.tr_presp[m + c.M * col] = p_cur(c)[m];
+    } else if (which == 3) {
+        for (int k = tid; k < c.K; k += NT) c.tr_nav[k + c.K * col] = c.nav_open[k];
+    } else if (which == 4) {
+        if (tid == 0)
+            for (int i = 0; i < n0; ++i) trace_emit(c, t, FSB_EV_CHOICE, c.cash_()[i], c.r_choice_()[i], c.r_inj_()[i]);
+    }
 }
 
-// Ordered compaction of {i in [0,n): pred(i)} into out[] (ascending i).  Each warp owns a
-// contiguous chunk; contains two __syncthreads; returns the total (may exceed cap -> caller flags).
+// Ordered compaction of {i in [0,n): pred(i)} into out[] (ascending i) by ONE warp; returns the total
+// (may exceed cap -> caller flags); no block barrier inside.
 template <class Pred>
-__device__ __forceinline__ int block_compact(const Ctx &c, int n, int cap, int *out, Pred pred)
+__device__ __forceinline__ int warp_compact(int lane, int n, int cap, int *out, Pred pred)
 {
-    const int chunk = (((n + c.nwarps - 1) / c.nwarps) + 31) & ~31;
-    const int lo = c.warp * chunk;
-    const int hi = min(n, lo + chunk);
     int cnt = 0;
-    for (int b = lo; b < hi; b += 32) {
-        const int i = b + c.lane;
-        const bool p = (i < hi) && pred(i);
+    for (int b = 0; b < n; b += 32) {
+        const int i = b + lane;
+        const bool p = (i < n) && pred(i);
         const unsigned m = __ballot_sync(0xffffffffu, p);
         if (p) {
-            const int k = cnt + __popc(m & ((1u << c.lane) - 1u));
-            if (k < cap) c.wl[c.warp * cap + k] = i;
+            const int k = cnt + __popc(m & ((1u << lane) - 1u));
+            if (k < cap) out[k] = i;
         }
         cnt += __popc(m);
     }
-    if (c.lane == 0) c.wcnt[c.warp] = cnt;
-    __syncthreads();
-    int off = 0, total = 0;
-    for (int w = 0; w < c.nwarps; ++w) {
-        const int x = c.wcnt[w];
-        if (w < c.warp) off += x;
-        total += x;
-    }
-    for (int j = c.lane; j < min(cnt, cap); j += 32)
-        if (off + j < cap) out[off + j] = c.wl[c.warp * cap + j];
-    __syncthreads();
-    return total;
+    __syncwarp();
+    return cnt;
 }
 
 // counts (and, when traced, lists in ascending stock order) the price-floor hits flagged in
-// c.pick[] by the preceding marketmake phase; warp 0 only, no barrier inside
-__device__ __forceinline__ void floor_account(const DevState &s, const Ctx &c, int t, int phase)
+// c.pick_()[] by the preceding marketmake phase; warp 0 only, no barrier inside
+__device__ __noinline__ void floor_account(int t, int phase)
 {
-    if (c.warp != 0) return;
+    Ctx &c = ctx();
+    FSB_TH;
+    if (warp != 0) return;
     int nf = 0;
-    for (int b = 0; b < s.M; b += 32) {
-        const int m = b + c.lane;
-        nf += __popc(__ballot_sync(0xffffffffu, m < s.M && c.pick[m] != 0));
+    for (int b = 0; b < c.M; b += 32) {
+        const int m = b + lane;
+        nf += __popc(__ballot_sync(0xffffffffu, m < c.M && c.pick_()[m] != 0));
     }
-    if (c.lane == 0 && nf > 0) {
+    if (lane == 0 && nf > 0) {
         c.cnt[CNT_FLOOR] += nf;
         if (c.trace >= 0)
-            for (int m = 0; m < s.M; ++m)
-                if (c.pick[m]) trace_emit(s, c, t, FSB_EV_FLOOR, m, phase, 0.0);
+            for (int m = 0; m < c.M; ++m)
+                if (c.pick_()[m]) trace_emit(c, t, FSB_EV_FLOOR, m, phase, 0.0);
     }
-}
-
-// x / y, skipping the division routine's slow path for the very common zero numerator (assets a fund
-// does not hold): for 0 < y < inf the IEEE quotient of a zero is that same signed zero
-__device__ __forceinline__ double qdiv(double x, double y)
-{
-    return (x == 0.0 && y > 0.0 && y < 1.7976931348623157e308) ? x : x / y;
 }
 
 // order-preserving map Float64 -> uint64 under Julia's isless (-0.0 < +0.0, every NaN last and equal)
@@ -284,15 +373,21 @@ __device__ __forceinline__ bool better(double a, int ia, double b, int ib)
     return ia < ib;
 }
 
-__device__ __forceinline__ int select_best(const double *rho, int K, int lane)
+// horizon returns of one column live in the global scratch as raw double bits (selectors other than the rank rule)
+__device__ __forceinline__ double rho_at(const unsigned long long *col, int k)
+{
+    return __longlong_as_double(static_cast<long long>(__ldcg(col + k)));
+}
+
+__device__ __forceinline__ int select_best(const unsigned long long *rho, int K, int lane)
 {
     double bv = 0.0;
     int bi = -1;
     for (int k = lane; k < K; k += 32) {
-        const double r = rho[k];
+        const double r = rho_at(rho, k);
         if (bi < 0 || better(r, k, bv, bi)) { bv = r; bi = k; }
     }
-#pragma unroll
+#pragma unroll 1
     for (int sft = 16; sft >= 1; sft >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, bv, sft);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, sft);
@@ -303,19 +398,21 @@ __device__ __forceinline__ int select_best(const double *rho, int K, int lane)
 
 // One warp chooses a fund for reinvestor `inv` by "best", "goodenough" or "random"
 // (functions.jl:344-353, 381-395, 412-415); rho = horizonreturns of the reinvestor's column.
-__device__ __forceinline__ int select_fund_warp(const DevState &s, const Ctx &c, int t, int inv, const double *rho, int selector, int *err)
+__device__ __noinline__ int select_fund_warp(int t, int inv, const unsigned long long *rho, int selector)
 {
-    const int K = s.K;
+    Ctx &c = ctx();
+    FSB_TH;
+    const int K = c.K;
     double forced;
     if (c.tape && tape_lookup(c, FSB_TAPE_CHOICE_IDX, t, inv, 0, &forced)) return static_cast<int>(forced);
-    if (selector == FSB_SEL_BEST) return select_best(rho, K, c.lane);
+    if (selector == FSB_SEL_BEST) return select_best(rho, K, lane);
     double u;
     uint32_t word;
     if (c.tape) {
-        if (!tape_lookup(c, FSB_TAPE_CHOICE_U, t, inv, 0, &u)) { *err |= FSB_REP_TAPE_MISSING; return 0; }
+        if (!tape_lookup(c, FSB_TAPE_CHOICE_U, t, inv, 0, &u)) { if (lane == 0) atomicOr(&c.isc_()[I_ERR], FSB_REP_TAPE_MISSING); return 0; }
         word = static_cast<uint32_t>(u * 4294967296.0);
     } else {
-        const uint4 w = draw_block(c.rng, SITE_CHOICE, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(inv));
+        const uint4 w = draw_block_s(c.rng, SITE_CHOICE, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(inv));
         word = w.z;
     }
     if (selector == FSB_SEL_RANDOM) return static_cast<int>(__umulhi(word, static_cast<uint32_t>(K)));
@@ -323,15 +420,15 @@ __device__ __forceinline__ int select_fund_warp(const DevState &s, const Ctx &c,
     const double thr = c.threshold[inv];
     int nc = 0;
     for (int b = 0; b < K; b += 32) {
-        const int k = b + c.lane;
-        nc += __popc(__ballot_sync(0xffffffffu, k < K && rho[k] > thr));
+        const int k = b + lane;
+        nc += __popc(__ballot_sync(0xffffffffu, k < K && rho_at(rho, k < K ? k : 0) > thr));
     }
-    if (nc == 0) return select_best(rho, K, c.lane);
+    if (nc == 0) return select_best(rho, K, lane);
     const int pick = static_cast<int>(__umulhi(word, static_cast<uint32_t>(nc)));
     int seen = 0, choice = 0;
     for (int b = 0; b < K; b += 32) {
-        const int k = b + c.lane;
-        const unsigned m = __ballot_sync(0xffffffffu, k < K && rho[k] > thr);
+        const int k = b + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, k < K && rho_at(rho, k < K ? k : 0) > thr);
         const int here = __popc(m);
         if (pick < seen + here) {
             unsigned mm = m;
@@ -347,34 +444,33 @@ __device__ __forceinline__ int select_fund_warp(const DevState &s, const Ctx &c,
 // One THREAD samples the rank-proportional choice (functions.jl:400-410, Q14) for reinvestor `inv`:
 // pk[k] = rank_k / (K(K+1)/2) is already in shared memory; Distributions v0.20 sampler:
 // cp = 0, i = 0; while cp < u && i < K: cp += p[++i].
-__device__ __forceinline__ int select_fund_prob(const DevState &s, const Ctx &c, int t, int inv, const double *pk, int *err)
+__device__ __forceinline__ int select_fund_prob(Ctx &c, int t, int inv, const double *pk)
 {
     double forced;
     if (c.tape && tape_lookup(c, FSB_TAPE_CHOICE_IDX, t, inv, 0, &forced)) return static_cast<int>(forced);
     double u;
     if (c.tape) {
-        if (!tape_lookup(c, FSB_TAPE_CHOICE_U, t, inv, 0, &u)) { *err |= FSB_REP_TAPE_MISSING; return 0; }
+        if (!tape_lookup(c, FSB_TAPE_CHOICE_U, t, inv, 0, &u)) { atomicOr(&c.isc_()[I_ERR], FSB_REP_TAPE_MISSING); return 0; }
     } else {
-        const uint4 w = draw_block(c.rng, SITE_CHOICE, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(inv));
+        const uint4 w = draw_block_s(c.rng, SITE_CHOICE, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(inv));
         u = u52(w.x, w.y);
     }
     double cp = 0.0;
     int i = 0;
-    const int K = s.K;
-    while (i + 8 <= K) {  // 8 probabilities per trip (the adds stay sequential: same cp sequence)
-        double pv[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) pv[q] = pk[i + q];
-        bool stop = false;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (!stop) {
-                if (cp < u) { cp = cp + pv[q]; ++i; }
-                else stop = true;
-            }
-        }
-        if (stop) return (i > 0) ? i - 1 : 0;
+    const int K = c.K;
+#pragma unroll 1
+    while (i + 4 <= K) {  // 4 probabilities per trip (the adds stay sequential: same cp sequence)
+        const double p0 = pk[i], p1 = pk[i + 1], p2 = pk[i + 2], p3 = pk[i + 3];
+        if (!(cp < u)) break;
+        cp = cp + p0; ++i;
+        if (!(cp < u)) break;
+        cp = cp + p1; ++i;
+        if (!(cp < u)) break;
+        cp = cp + p2; ++i;
+        if (!(cp < u)) break;
+        cp = cp + p3; ++i;
     }
+#pragma unroll 1
     while (cp < u && i < K) {
         cp = cp + pk[i];
         ++i;
@@ -382,44 +478,29 @@ __device__ __forceinline__ int select_fund_prob(const DevState &s, const Ctx &c,
     return (i > 0) ? i - 1 : 0;
 }
 
-// Bitonic sort of n = 2^q (key, idx) pairs in shared memory by ONE warp, ascending in (key, idx).
-__device__ __forceinline__ void warp_bitonic(unsigned long long *keys, unsigned short *idx, int n, int lane)
+// Rank of K <= 256 keys by ONE warp, in registers: 8 packed words per lane, word = key with its low
+// 8 bits replaced by the fund index, bitonic network over 256 words (21 in-lane + 15 shuffle stages; the
+// stage loops stay rolled for code size, the 8 words are indexed statically so they stay in registers).
+// Exact unless two DIFFERENT keys agree in their upper 56 bits and the index order contradicts them;
+// that is repaired afterwards on neighbours.  Writes prob[k] = ranktab[rank_k - 1] = rank_k / normaliser
+// (Q14), rank = 1-based position in the stable ascending order.
+__device__ FSB_FP_INLINE void warp_rank256(const unsigned long long *keys, int K, double *prob, const double *ranktab)
 {
-    for (int k2 = 2; k2 <= n; k2 <<= 1) {
-        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-            for (int i = lane; i < (n >> 1); i += 32) {
-                const int a = ((i & ~(j2 - 1)) << 1) | (i & (j2 - 1));
-                const int b = a | j2;
-                const bool up = ((a & k2) == 0);
-                const unsigned long long ka = keys[a], kb = keys[b];
-                const unsigned short ia = idx[a], ib = idx[b];
-                const bool gt = (ka > kb) || (ka == kb && ia > ib);
-                if (gt == up) {
-                    keys[a] = kb; keys[b] = ka;
-                    idx[a] = ib; idx[b] = ia;
-                }
-            }
-            __syncwarp();
+    const int lane = threadIdx.x & 31;
+    unsigned long long v[8];
+    {
+        const ulonglong2 *k2p = reinterpret_cast<const ulonglong2 *>(keys) + lane * 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = lane * 8 + 2 * r;
+            ulonglong2 kk = make_ulonglong2(~0ULL, ~0ULL);
+            if (e < K) kk = __ldcg(k2p + r);  // key rows are padded to a multiple of 4 entries
+            v[2 * r] = (((e < K) ? kk.x : ~0ULL) & ~0xffULL) | static_cast<unsigned long long>(e);
+            v[2 * r + 1] = (((e + 1 < K) ? kk.y : ~0ULL) & ~0xffULL) | static_cast<unsigned long long>(e + 1);
         }
     }
-}
-
-// Rank of K <= 256 keys by ONE warp, in registers: 8 packed words per lane, word = key with its low
-// 8 bits replaced by the fund index, bitonic network over 256 words (21 in-lane + 15 shuffle stages).
-// Exact unless two DIFFERENT keys agree in their upper 56 bits and the index order contradicts them;
-// that is detected afterwards on neighbours (returns false: caller re-sorts exactly in shared memory).
-// On success writes prob[k] = rank_k / normaliser (Q14), rank = 1-based position in the stable order.
-__device__ __forceinline__ bool warp_rank256(const unsigned long long *keys, int K, double *prob, double normaliser, int lane)
-{
-    unsigned long long v[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int e = lane * 8 + r;
-        const unsigned long long kk = (e < K) ? keys[e] : ~0ULL;
-        v[r] = (kk & ~0xffULL) | static_cast<unsigned long long>(e);
-    }
     // stages (k2, j2): partner = e ^ j2, ascending iff (e & k2) == 0, e = 8 * lane + r.  j2 >= 8 crosses
-    // lanes (shuffle), j2 in {4, 2, 1} stays in the lane's registers.  Outer loops stay rolled (code size).
+    // lanes (shuffle), j2 in {4, 2, 1} stays in the lane's registers.
 #pragma unroll 1
     for (int k2 = 2; k2 <= 256; k2 <<= 1) {
 #pragma unroll 1
@@ -441,10 +522,10 @@ __device__ __forceinline__ bool warp_rank256(const unsigned long long *keys, int
                 for (int r = 0; r < 8; ++r) {
                     if ((r & j2) == 0) {
                         const bool up = (((lane * 8 + r) & k2) == 0);
-                        const unsigned long long a = v[r], b = v[r | j2];
-                        const bool sw = (a > b) == up;
-                        v[r] = sw ? b : a;
-                        v[r | j2] = sw ? a : b;
+                        const unsigned long long x = v[r], y = v[r | j2];
+                        const bool sw = (x > y) == up;
+                        v[r] = sw ? y : x;
+                        v[r | j2] = sw ? x : y;
                     }
                 }
             }
@@ -452,12 +533,13 @@ __device__ __forceinline__ bool warp_rank256(const unsigned long long *keys, int
     }
     // words that agree in their upper 56 bits were ordered by index; order them by their full keys
     // (stable odd-even transposition sweeps over neighbours; such runs are short and rare)
-    auto wrong = [&](unsigned long long a, unsigned long long b) {
-        if ((a ^ b) >= 256ULL) return false;
-        const int ia = static_cast<int>(a & 0xff), ib = static_cast<int>(b & 0xff);
-        return ia < K && ib < K && keys[ia] > keys[ib];
+    auto wrong = [&](unsigned long long x, unsigned long long y) {
+        if ((x ^ y) >= 256ULL) return false;
+        const int ia = static_cast<int>(x & 0xff), ib = static_cast<int>(y & 0xff);
+        return ia < K && ib < K && __ldcg(keys + ia) > __ldcg(keys + ib);
     };
-    for (int sweep = 0;; ++sweep) {
+#pragma unroll 1
+    for (int sweep = 0; sweep < 300; ++sweep) {  // (a stable sort of <= 256 words needs < 256 sweeps)
         bool moved = false;
 #pragma unroll
         for (int r = 0; r < 8; r += 2) {
@@ -474,240 +556,292 @@ __device__ __forceinline__ bool warp_rank256(const unsigned long long *keys, int
         if (sw_hi) { v[7] = nxt; moved = true; }
         if (sw_lo) { v[0] = prv; moved = true; }
         if (!__any_sync(0xffffffffu, moved)) break;
-        if (sweep >= 300) return false;  // (cannot happen: a stable sort of <= 256 words needs < 256 sweeps)
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int idx = static_cast<int>(v[r] & 0xff);
-        if (idx < K) prob[idx] = static_cast<double>(lane * 8 + r + 1) / normaliser;
+        if (idx < K) prob[idx] = __ldg(ranktab + lane * 8 + r);
     }
-    return true;
+}
+
+// Rank by counting, any K (the general path): rank_k = 1 + #{j : key_j < key_k or (key_j == key_k and j < k)}
+__device__ __noinline__ void warp_rank_count(const unsigned long long *keys, int K, double *prob, const double *ranktab)
+{
+    const int lane = threadIdx.x & 31;
+    for (int k = lane; k < K; k += 32) {
+        const unsigned long long kk = __ldcg(keys + k);
+        int rank = 0;
+        for (int q = 0; q < K; ++q) {
+            const unsigned long long kj = __ldcg(keys + q);
+            rank += (kj < kk || (kj == kk && q < k)) ? 1 : 0;
+        }
+        prob[k] = __ldg(ranktab + rank);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// the full pass: every holdings row against NC shared-memory columns starting at column `cb`.
-// 8 lanes per row, 4 rows per warp and round; lane j owns double2 words j, j+8, ... (the canonical
-// chains); the loop runs over the zero-padded pitch cp so that every lane does the same trip count
-// (fma(0, 0, acc) == acc exactly).  Holdings are loaded four words ahead of their use (register
-// double buffer) and rows are L2-prefetched two rounds ahead.  Results: column 0 -> nav_open (unless
-// the row was modified before this pass: its opening NAV was taken in the review pass), column 1 ->
-// nav / nav_close, column q >= 2 -> horizon return (nav - vh) / vh (:375-379), stored as the value
-// or, for the rank rule, as its order-preserving 64-bit key.
-// FAST: cp == cpk == 256 at compile time (column offsets become immediates).
+// reduction of N partial sums over the 8 lanes of a group, transposing: after the butterfly steps
+// 4, 2, 1 every lane keeps only the sums it owns.  Each sum is formed as (own + partner's) at every
+// level, i.e. exactly the values of tree8() (IEEE addition commutes), with about a third of the shuffles.
+// Ownership afterwards (b2, b1, b0 = bits of the lane's position j in its group):
+//   N = 4 : v[0] = sum 2*b2 + b1                      (lane pairs hold the same sum)
+//   N = 8 : v[0] = sum 4*b2 + 2*b1 + b0 = j
+//   N = 12: v[0] = sum 6*b2 + 3*b1 + b0, v[1] = sum 6*b2 + 3*b1 + 2   (v[1] shared by a lane pair)
+//   N = 16: v[q] = sum 8*b2 + 4*b1 + 2*b0 + q, q = 0, 1
 // ------------------------------------------------------------------------------------------------
-template <int NC, bool FAST>
-__device__ __forceinline__ void full_pass(const DevState &s, const Ctx &c, const int cb, const int nreal, const bool want_keys)
+template <int N, int n>
+__device__ __forceinline__ void halve(double (&v)[N], const bool b, const int mask)
 {
-    // Each 8-lane group owns TWO rows per round (k and k + 4: 8 consecutive rows per warp), so that one
-    // 128-bit shared-memory load of a column word feeds four FMAs (the pass is bound by the shared-memory
-    // pipe otherwise: a 128-bit LDS costs 4 wavefronts however many lanes share its address).
-    const int K = s.K, Mp = s.Mp, half = Mp >> 1;
-    const int j = c.lane & 7, g = c.lane >> 3;
-    const int rpr = c.nwarps * 8;
-    const int cstride = (FAST ? 256 : c.cpk) >> 1;
-    const int nb = FAST ? 8 : (c.cp >> 5);  // batches of 2 words per lane and row (cp is a multiple of 128 doubles: nb % 4 == 0)
-    const double2 *colp = reinterpret_cast<const double2 *>(c.cols + cb * (FAST ? 256 : c.cpk)) + j;
-    auto rowptr = [&](int k) {
-        return reinterpret_cast<const double2 *>(c.H + static_cast<long long>(k < K ? k : 0) * Mp) + j;
+    constexpr int h = n >> 1;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+        const double lo = v[i], hi = v[i + h];
+        const double send = b ? lo : hi, keep = b ? hi : lo;
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+    if (n & 1) {  // odd count: the last sum is reduced in place by both partners and moves to slot h
+        const double x = v[n - 1];
+        v[h] = x + __shfl_xor_sync(0xffffffffu, x, mask);
+    }
+}
+template <int N>
+__device__ __forceinline__ void reduce8_transposed(double (&v)[N], int j)
+{
+    static_assert(N == 4 || N == 8 || N == 12 || N == 16, "unsupported tile");
+    const bool b2 = (j & 4) != 0, b1 = (j & 2) != 0, b0 = (j & 1) != 0;
+    halve<N, N>(v, b2, 4);
+    halve<N, N / 2>(v, b1, 2);
+    halve<N, N / 4>(v, b0, 1);   // N/4 = 1 (N=4), 2 (8), 3 (12), 4 (16)
+}
+template <int N>
+__device__ __forceinline__ int owned_sum(int j, int q)  // index of the sum in v[q] after reduce8_transposed
+{
+    const int b2 = (j >> 2) & 1, b1 = (j >> 1) & 1, b0 = j & 1;
+    if (N == 4) return 2 * b2 + b1;
+    if (N == 8) return j;
+    if (N == 12) return 6 * b2 + 3 * b1 + (q == 0 ? b0 : 2);
+    return 8 * b2 + 4 * b1 + 2 * b0 + q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the full pass: every holdings row against the shared-memory columns cb .. cb + 4*NCG - 1.
+// A round of a warp = 4 consecutive rows.  Lane (g, j): g = lane / 8 owns the columns cb + g + 4*cc,
+// j = lane % 8 owns the double2 words j, j+8, ... of a row (the canonical chains).  All four groups load
+// the same holdings words (one 128-byte request per row and step, served once), every group a different
+// column word: 8 FMAs per 128-bit shared-memory load.  The loop runs over the zero-padded pitch cp
+// (fma(0, 0, acc) == acc exactly).  Holdings are loaded four steps ahead of their use (register ring,
+// loop body = 4 steps so that the ring is indexed statically) and rounds are L2-prefetched kPfAhead
+// rounds ahead.
+// OPEN: only column 0 (a day without divestments): every group owns its own round of 4 rows instead.
+// Results: column 0 -> nav_open (unless the row was modified before this pass: its opening NAV was
+// taken in the review pass), column 1 -> nav / nav_close, column q >= 2 -> horizon return
+// (nav - vh) / vh (:375-379), stored as its order-preserving 64-bit key (rank rule) or as raw bits.
+// ------------------------------------------------------------------------------------------------
+template <int NCG, bool OPEN, bool FAST>
+__device__ FSB_FP_INLINE void full_pass(const int cb, const int nreal, const int want_keys)
+{
+    Ctx &c = ctx();
+    constexpr int R = 4;
+    FSB_TH;
+    const int K = c.K;
+    const int half = FAST ? 128 : (c.Mp >> 1);     // double2 words per row (Mp is a multiple of 128: no tail, no masks)
+    const int cstride = FAST ? 128 : (c.cpk >> 1);  // double2 words per shared-memory column
+    const int nsteps = FAST ? 16 : (c.Mp >> 4);     // word steps per row: a multiple of 8
+    const int j = lane & 7, g = lane >> 3;
+    const int nrounds = (K + R - 1) / R;  // rounds of 4 rows (rows K.. of the last one are zero padding)
+    const double2 *colp = reinterpret_cast<const double2 *>(c.cols_()) + (OPEN ? 0 : (cb + g)) * cstride + j;
+    const double2 *H2 = reinterpret_cast<const double2 *>(c.H) + j;
+    // the unit a warp pulls per trip: OPEN: 4 rounds (one per group), else 1 round
+    constexpr int upw = OPEN ? 4 : 1;
+    const int ntrips = (nrounds + upw - 1) / upw;
+    auto round_of = [&](int trip) { return OPEN ? 4 * trip + g : trip; };
+    auto rowptr = [&](int trip) {
+        int rd = round_of(trip);
+        if (rd >= nrounds) rd = nrounds - 1;  // (idle group of the last OPEN trip re-reads the last round)
+        return H2 + static_cast<long long>(rd) * R * half;
     };
-    auto ldb = [&](const double2 *ra, const double2 *rb, int b, double2(&h)[4]) {
+    int trip = warp;
+    if (trip >= ntrips) return;
+    double2 hb[4][R];
+    auto load = [&](double2(&dst)[R], const double2 *rp, int w) {  // w = first word of the step
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int e2 = 16 * b + 8 * i;
-            const bool in = (e2 + j < half);
-            h[i] = in ? ra[e2] : make_double2(0.0, 0.0);
-            h[2 + i] = in ? rb[e2] : make_double2(0.0, 0.0);
-        }
+        for (int r = 0; r < R; ++r) dst[r] = __ldcg(rp + r * half + w);
     };
-    auto comp = [&](const double2 *cp_, const double2(&h)[4], double(&acc)[2 * NC]) {
+    const double2 *cur = rowptr(trip);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-#pragma unroll
-            for (int q = 0; q < NC; ++q) {
-                const double2 p = cp_[q * cstride + 8 * i];
-                acc[q] = fma(h[i].x, p.x, acc[q]);
-                acc[q] = fma(h[i].y, p.y, acc[q]);
-                acc[NC + q] = fma(h[2 + i].x, p.x, acc[NC + q]);
-                acc[NC + q] = fma(h[2 + i].y, p.y, acc[NC + q]);
+    for (int st = 0; st < 4; ++st) load(hb[st], cur, 8 * st);
+    const double *const keep_nav = c.nav_();
+    const long long rowbytes = static_cast<long long>(c.Mp) * 8;
+#pragma unroll 1
+    for (; trip < ntrips; trip += nwarps) {
+        {   // L2 prefetch of the round(s) this warp reads kPfAhead trips from now
+            const int tp = trip + kPfAhead * nwarps;
+            if (lane == 0 && tp < ntrips) {
+                const int r0 = upw * tp * R;
+                const int nr = min(upw * R, ((K + 3) & ~3) - r0);
+                l2_prefetch_bulk(reinterpret_cast<const char *>(c.H) + r0 * rowbytes, static_cast<unsigned>(nr * rowbytes));
             }
         }
-    };
-    int kb = c.warp * 8;
-    if (kb >= K) return;
-    const double2 *ra = rowptr(kb + g), *rb = rowptr(kb + 4 + g);
-    double2 h0[4], h1[4];
-    ldb(ra, rb, 0, h0);
+        const int tn = (trip + nwarps < ntrips) ? trip + nwarps : trip;
+        const double2 *nxt = rowptr(tn);
+        double acc[R * NCG];
+#pragma unroll
+        for (int q = 0; q < R * NCG; ++q) acc[q] = 0.0;
+        const double2 *cp_i = colp;
 #pragma unroll 1
-    for (; kb < K; kb += rpr) {
-        if (c.lane == 0) {
-            const int kpf = kb + 2 * rpr;
-            if (FSB_PF_MODE == 1 && kpf < K) l2_prefetch_bulk(c.H + static_cast<long long>(kpf) * Mp, static_cast<unsigned>(min(8, K - kpf) * Mp * 8));
-        }
-        const int kn = (kb + rpr < K) ? kb + rpr : kb;
-        const double2 *rna = rowptr(kn + g), *rnb = rowptr(kn + 4 + g);
-        double acc[2 * NC];
+        for (int i0 = 0; i0 < nsteps; i0 += 4) {
+            // the ring is refilled 4 steps ahead: from this row block, or from the next trip's on the last iteration
+            const double2 *lp = (i0 + 4 < nsteps) ? cur + 8 * (i0 + 4) : nxt;
 #pragma unroll
-        for (int q = 0; q < 2 * NC; ++q) acc[q] = 0.0;
-#pragma unroll 1
-        for (int b = 0; b < nb; b += 2) {
-            ldb(ra, rb, b + 1, h1);
-            comp(colp + 16 * b, h0, acc);
-            if (b + 2 < nb) ldb(ra, rb, b + 2, h0); else ldb(rna, rnb, 0, h0);
-            comp(colp + 16 * b + 16, h1, acc);
-        }
-        ra = rna; rb = rnb;
-        // ---- epilogue: lane j of a group owns result columns j and j + 8 of both rows ---------------
+            for (int q = 0; q < 4; ++q) {
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int k = kb + 4 * rr + g;
-            const bool on = k < K;
-            double m0 = 0.0, m1 = 0.0, navk = 0.0;
+                for (int cc = 0; cc < NCG; ++cc) {
+                    const double2 p = cp_i[4 * cc * cstride + 8 * q];
 #pragma unroll
-            for (int q = 0; q < NC; ++q) {
-                const double v = tree8(acc[rr * NC + q]);
-                if (q == 1) navk = v;
-                if (j == (q & 7)) { if (q < 8) m0 = v; else m1 = v; }
+                    for (int r = 0; r < R; ++r) {
+                        acc[r + R * cc] = fma(hb[q][r].x, p.x, acc[r + R * cc]);
+                        acc[r + R * cc] = fma(hb[q][r].y, p.y, acc[r + R * cc]);
+                    }
+                }
+                load(hb[q], lp, 8 * q);
             }
-            if (cb != 0) navk = c.nav[on ? k : 0];
+            cp_i += 32;
+        }
+        cur = nxt;
+        // ---- epilogue ----------------------------------------------------------------------------
+        reduce8_transposed<R * NCG>(acc, j);
+        constexpr int NF = (R * NCG > 8) ? 2 : 1;
+        const int rd = round_of(trip);
+        int own[NF];
 #pragma unroll
-            for (int part = 0; part < (NC > 8 ? 2 : 1); ++part) {
-                const int q = j + 8 * part;
-                const double v = part ? m1 : m0;
-                const int col = cb + q;
-                if (on && q < nreal) {
+        for (int q = 0; q < NF; ++q) own[q] = owned_sum<R * NCG>(j, q);
+        if (OPEN) {
+            const int k = rd * R + own[0];
+            if (rd < nrounds && k < K && (j & 1) == 0) { c.nav_open[k] = acc[0]; c.nav_close[k] = acc[0]; }
+            continue;
+        }
+        // column 1 first: the day's NAV is the numerator of every horizon return of the row
+        if (cb == 0) {
+#pragma unroll
+            for (int q = 0; q < NF; ++q) {
+                const int col = g + 4 * (own[q] >> 2), k = rd * R + (own[q] & 3);
+                const bool mine = (R * NCG == 4 || (R * NCG == 12 && q == 1)) ? ((j & 1) == 0) : true;
+                if (mine && k < K) {
                     if (col == 0) {
-                        if (!((c.fmod[k >> 5] >> (k & 31)) & 1)) c.nav_open[k] = v;
+                        if (!((c.fmod_()[k >> 5] >> (k & 31)) & 1)) c.nav_open[k] = acc[q];
                     } else if (col == 1) {
-                        c.nav[k] = v;
-                        c.nav_close[k] = v;
-                    } else {
-                        const double rho = (navk - v) / v;
-                        if (want_keys) reinterpret_cast<unsigned long long *>(c.vh)[(col - 2) * c.kq + k] = sort_key(rho);
-                        else c.vh[(col - 2) * c.kq + k] = rho;
+                        c.nav_()[k] = acc[q];
+                        c.nav_close[k] = acc[q];
                     }
                 }
             }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < NF; ++q) {
+            const int col = cb + g + 4 * (own[q] >> 2), k = rd * R + (own[q] & 3);
+            const bool mine = (R * NCG == 4 || (R * NCG == 12 && q == 1)) ? ((j & 1) == 0) : true;
+            if (col >= 2 && col - cb < nreal && k < K) {   // (all lanes divide; only the owner stores)
+                const double navk = keep_nav[k], v = acc[q];
+                const double rho = ddiv(navk - v, v);
+                const unsigned long long word = want_keys ? sort_key(rho) : static_cast<unsigned long long>(__double_as_longlong(rho));
+                if (mine) __stcg(c.keys + static_cast<long long>(col - 2) * c.kq + k, word);
+            }
         }
     }
 }
 
-// nc columns are processed by the next even instantiation (one spare column of finite stale data is
-// multiplied and dropped: cols[] always holds cmax + 2 columns)
-template <bool FAST>
-__device__ __forceinline__ void full_pass_dispatch(const DevState &s, const Ctx &c, int cb, int nc, bool want_keys)
+// nc columns starting at cb are processed by the instantiation with ceil(nc / 4) columns per group
+// (spare columns of finite stale data are multiplied and dropped: cols[] always holds cmax + 2 columns).
+// c.fast: Mp == 256 and K <= 256 (the default shape): strides and trip counts are compile-time constants.
+__device__ __forceinline__ void full_pass_dispatch(Ctx &c, int cb, int nc, int want_keys)
 {
-    switch ((nc + 1) >> 1) {
-    case 1: full_pass<2, FAST>(s, c, cb, nc, want_keys); break;
-    case 2: full_pass<4, FAST>(s, c, cb, nc, want_keys); break;
-    case 3: full_pass<6, FAST>(s, c, cb, nc, want_keys); break;
-    case 4: full_pass<8, FAST>(s, c, cb, nc, want_keys); break;
-    case 5: full_pass<10, FAST>(s, c, cb, nc, want_keys); break;
-    default: full_pass<12, FAST>(s, c, cb, nc, want_keys); break;
-    }
-}
-
-// the day's NAV when nothing was divested (:464 false): nav_open = nav_close = H * p_open
-__device__ __forceinline__ void open_pass(const DevState &s, const Ctx &c)
-{
-    const int K = s.K, Mp = s.Mp, half = Mp >> 1, hp = c.cp >> 1;
-    const int j = c.lane & 7, g = c.lane >> 3;
-    const int rpr = c.nwarps * 4;
-    const double2 *colp = reinterpret_cast<const double2 *>(c.cols);
-    for (int kb = c.warp * 4; kb < K; kb += rpr) {
-        if (c.lane == 0) {
-            const int kpf = kb + 2 * rpr;
-            if (FSB_PF_MODE == 1 && kpf < K) l2_prefetch_bulk(c.H + static_cast<long long>(kpf) * Mp, static_cast<unsigned>(min(4, K - kpf) * Mp * 8));
-        }
-        const int k = kb + g;
-        const bool on = k < K;
-        const double2 *row = reinterpret_cast<const double2 *>(c.H + static_cast<long long>(on ? k : kb) * Mp);
-        double acc = 0.0;
-#pragma unroll 8
-        for (int e2 = j; e2 < hp; e2 += 8) {
-            const double2 h = (e2 < half) ? row[e2] : make_double2(0.0, 0.0);
-            const double2 p = colp[e2];
-            acc = fma(h.x, p.x, acc);
-            acc = fma(h.y, p.y, acc);
-        }
-        const double v = tree8(acc);
-        if (on && j == 0) { c.nav_open[k] = v; c.nav_close[k] = v; }
+    const int ncg = (nc + 3) >> 2;
+    if (c.fast) {
+        if (ncg <= 1) full_pass<1, false, true>(cb, nc, want_keys);
+        else if (ncg == 2) full_pass<2, false, true>(cb, nc, want_keys);
+        else if (ncg == 3) full_pass<3, false, true>(cb, nc, want_keys);
+        else full_pass<4, false, true>(cb, nc, want_keys);
+    } else {
+        if (ncg <= 1) full_pass<1, false, false>(cb, nc, want_keys);
+        else if (ncg == 2) full_pass<2, false, false>(cb, nc, want_keys);
+        else if (ncg == 3) full_pass<3, false, false>(cb, nc, want_keys);
+        else full_pass<4, false, false>(cb, nc, want_keys);
     }
 }
 
 // reads entry i of the per-warp ordered lists produced by the reviewer draw
-__device__ __forceinline__ int chunk_list_get(const Ctx &c, int cap, int i)
+__device__ __forceinline__ int chunk_list_get(const Ctx &c, int nwarps, int i)
 {
     int w = 0, off = 0;
-    for (; w < c.nwarps - 1; ++w) {
-        const int x = c.wcnt[w];
+    for (; w < nwarps - 1; ++w) {
+        const int x = c.wcnt_()[w];
         if (i < off + x) break;
         off += x;
     }
-    return c.wl[w * cap + (i - off)];
+    return c.wl_()[w * c.cap + (i - off)];
 }
 
 // ------------------------------------------------------------------------------------------------
-// one time step of one replication
+// T0: marketmove! (:13-17), stockmove! (:29-34), investor maps, drawreviewers (:147-151); ends with B1
 // ------------------------------------------------------------------------------------------------
-template <bool FAST>
-__device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int t, int selector, int flags)
+__device__ FSB_FP_INLINE void phase_shocks(const int t)
 {
-    const int K = s.K, M = s.M, N = s.N, Mp = s.Mp, cap = s.cap_ev;
-    const int half = Mp >> 1, hp = c.cp >> 1;
-    const DevPoint &pt = *c.pt;
-    const int tid = c.tid, NT = c.nthreads, lane = c.lane;
-    const int j8 = lane & 7, g4 = lane >> 3;
-    const bool traced = (c.trace >= 0);
-    double *Pt = c.P + static_cast<long long>(pcol(s, t)) * Mp;
-    const double *Pprev = c.P + static_cast<long long>(pcol(s, t - 1)) * Mp;
+    Ctx &c = ctx();
+    FSB_TH;
+    const int K = c.K, M = c.M, N = c.N, Mp = c.Mp, cap = c.cap, hp = c.cp >> 1;
+    const double *Pprev = c.P + static_cast<long long>(pcol(c, t - 1)) * Mp;
     double *const po = p_open(c), *const pc = p_cur(c);
-
-    // ---- L2 prefetch of the first two rounds of holdings rows (consumed by the full pass) ------
+    // L2 prefetch of what the step certainly reads: the first rounds of holdings rows (consumed by the
+    // full pass) and the stakes (gathered by the stake sequence and the dilution)
     if (lane == 0) {
-        const int rpr = c.nwarps * 8;
-        for (int q = 0; q < 2; ++q) {
-            const int kpf = c.warp * 8 + q * rpr;
-            if (FSB_PF_MODE == 1 && kpf < K) l2_prefetch_bulk(c.H + static_cast<long long>(kpf) * Mp, static_cast<unsigned>(min(8, K - kpf) * Mp * 8));
+        const int kq = (K + 3) & ~3;
+        for (int q = 0; q < kPfAhead; ++q) {
+            const int r0 = 4 * (warp + q * nwarps);
+            if (r0 < kq) l2_prefetch_bulk(c.H + static_cast<long long>(r0) * Mp, static_cast<unsigned>(min(4, kq - r0) * Mp * 8));
         }
+        if (warp == 0 && (N & 1) == 0) l2_prefetch_bulk(c.stake, static_cast<unsigned>(N * 8));
     }
-
-    if (FSB_PF_MODE == 2)
-        for (int k = tid; k < K; k += NT) l2_prefetch_bulk(c.H + static_cast<long long>(k) * Mp, static_cast<unsigned>(Mp * 8));
-
-    // ---- marketmove! (:13-17): every thread evaluates the same draw (no barrier) -----------------
+    // marketmove!: every thread evaluates the same draw (no barrier)
     double mret;
     {
-        const double z = c.z_mkt ? c.z_mkt[t - 1 - c.tape_toff] : draw_normal(c.rng, SITE_MKT, static_cast<uint32_t>(t), 0, 0);
-        const double mprev = c.market[mslot(s, t - 1)];
-        const double g = (1.0 + pt.drift) + pt.marketvol * z;
+        double z;
+        if (c.z_mkt) z = c.z_mkt[t - 1 - c.tape_toff];
+        else {
+            const uint4 w = draw_block_s(c.rng, SITE_MKT, static_cast<uint32_t>(t), 0, 0);
+            z = det_norminv(u52(w.x, w.y));
+        }
+        const double mprev = c.market[mslot(c, t - 1)];
+        const double g = (1.0 + c.drift) + c.marketvol * z;
         const double mnew = mprev * g;
-        mret = (mnew - mprev) / mprev;
+        mret = ddiv(mnew - mprev, mprev);
         if (tid == 0) {
-            c.market[mslot(s, t)] = mnew;
-            double peak = s.mkt_peak[c.r];
-            if (mnew > peak) { peak = mnew; s.mkt_peak[c.r] = peak; }
-            const double dd = (peak - mnew) / peak;
-            if (dd > s.mkt_dd[c.r]) s.mkt_dd[c.r] = dd;
+            c.market[mslot(c, t)] = mnew;
+            double peak = *c.mkt_peak;
+            if (mnew > peak) { peak = mnew; *c.mkt_peak = peak; }
+            const double dd = ddiv(peak - mnew, peak);
+            if (dd > *c.mkt_dd) *c.mkt_dd = dd;
         }
     }
-    // ---- stockmove! (:29-34), two assets per thread (one Philox block = two uniforms) ------------
+    // stockmove!, two assets per thread (one Philox block = two uniforms)
+#pragma unroll 1
     for (int m2 = tid; m2 < hp; m2 += NT) {
         double2 v = make_double2(0.0, 0.0);
         const int m = 2 * m2;
         if (m < M) {
+            const double2 prev = reinterpret_cast<const double2 *>(Pprev)[m2];
+            const double2 be = reinterpret_cast<const double2 *>(c.beta)[m2];
+            const double2 vo = reinterpret_cast<const double2 *>(c.vol)[m2];
             double z0, z1 = 0.0;
             if (c.z_stock) {
                 const double *zs = c.z_stock + static_cast<long long>(M) * (t - 1 - c.tape_toff);
                 z0 = zs[m];
                 if (m + 1 < M) z1 = zs[m + 1];
             } else {
-                const uint4 w = draw_block(c.rng, SITE_STOCK, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(m2));
+                const uint4 w = draw_block_s(c.rng, SITE_STOCK, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(m2));
                 z0 = det_norminv(u52(w.x, w.y));
                 z1 = det_norminv(u52(w.z, w.w));
             }
-            const double2 prev = reinterpret_cast<const double2 *>(Pprev)[m2];
-            const double2 be = reinterpret_cast<const double2 *>(c.beta)[m2];
-            const double2 vo = reinterpret_cast<const double2 *>(c.vol)[m2];
             v.x = (1.0 + mret * be.x) * prev.x + (vo.x * z0) * prev.x;
             if (m + 1 < M) v.y = (1.0 + mret * be.y) * prev.y + (vo.y * z1) * prev.y;
         }
@@ -715,31 +849,31 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
         reinterpret_cast<double2 *>(pc)[m2] = v;
     }
     FSB_MARK(19);
-    // ---- investor -> fund map, horizons and the stake-less flags into shared memory ---------------
-    if (tid < 16) c.isc[tid] = 0;
+    // investor -> fund map, horizons and the fund flags into shared memory
+    if (tid < 16) c.isc_()[tid] = 0;
     {
         int idle = 0;  // investors already in cash when the day starts (none in a run from initialise)
+#pragma unroll 2
         for (int n = tid; n < ((N + 7) & ~7); n += NT) {
             const int f = (n < N) ? c.pos[n] : -1;
-            c.pos16[n] = static_cast<short>(f);
-            c.hor16[n] = static_cast<unsigned short>((n < N) ? c.horizon[n] : 0);
+            c.pos16_()[n] = static_cast<short>(f);
+            c.hor16_()[n] = static_cast<unsigned short>((n < N) ? c.horizon[n] : 0);
             idle += (f == K);
         }
         idle = __reduce_add_sync(0xffffffffu, idle);
-        if (lane == 0) c.wcnt[c.nwarps + c.warp] = idle;
+        if (lane == 0) c.wcnt_()[nwarps + warp] = idle;
     }
-    for (int n = tid; n < N; n += NT) c.stk[n] = c.stake[n];
-    for (int k = tid; k < K; k += NT) c.stl[k] = c.stakeless[k];
-    for (int q = tid; q < (K + 31) / 32; q += NT) { c.fmod[q] = 0; c.fsel[q] = 0; }
-    for (int q = tid; q < cap; q += NT) c.nzf[q] = 0;
-
+    for (int k = tid; k < K; k += NT) { c.stl_()[k] = c.stakeless[k]; c.hz_()[k] = c.hzero[k]; }
+    for (int q = tid; q < (K + 31) / 32; q += NT) { c.fmod_()[q] = 0; c.fsel_()[q] = 0; }
+    for (int q = tid; q < cap; q += NT) c.nzf_()[q] = 0;
     FSB_MARK(20);
-    // ---- drawreviewers (:147-151): ascending ids, per-warp chunks of the investor range ----------
+    // drawreviewers: ascending ids, per-warp chunks of the investor range
     {
-        const double rp = pt.reviewprob;
-        const int chunk = (((N + c.nwarps - 1) / c.nwarps) + 63) & ~63;
-        const int lo = c.warp * chunk, hi = min(N, lo + chunk);
+        const double rp = c.reviewprob;
+        const int chunk = (((N + nwarps - 1) / nwarps) + 63) & ~63;
+        const int lo = warp * chunk, hi = min(N, lo + chunk);
         int cnt = 0;
+#pragma unroll 1
         for (int b = lo; b < hi; b += 64) {
             const int n0 = b + 2 * lane;
             double u0 = 2.0, u1 = 2.0;
@@ -749,7 +883,7 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
                     u0 = ur[n0];
                     if (n0 + 1 < hi) u1 = ur[n0 + 1];
                 } else {
-                    const uint4 w = draw_block(c.rng, SITE_REVIEW, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(n0 >> 1));
+                    const uint4 w = draw_block_s(c.rng, SITE_REVIEW, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(n0 >> 1));
                     u0 = u52(w.x, w.y);
                     if (n0 + 1 < hi) u1 = u52(w.z, w.w);
                 }
@@ -758,49 +892,57 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
             const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
             const unsigned lt = (1u << lane) - 1u;
             int k0 = cnt + __popc(m0 & lt) + __popc(m1 & lt);
-            if (f0) { if (k0 < cap) c.wl[c.warp * cap + k0] = n0; ++k0; }
-            if (f1 && k0 < cap) c.wl[c.warp * cap + k0] = n0 + 1;
+            if (f0) { if (k0 < cap) c.wl_()[warp * cap + k0] = n0; ++k0; }
+            if (f1 && k0 < cap) c.wl_()[warp * cap + k0] = n0 + 1;
             cnt += __popc(m0) + __popc(m1);
         }
-        if (lane == 0) c.wcnt[c.warp] = cnt;
+        if (lane == 0) c.wcnt_()[warp] = cnt;
     }
     __syncthreads();  // B1: prices, maps and reviewer chunks visible
     FSB_MARK(1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// T1: perfreview (:157-176): (V[f,t] - V[f,t-h]) / V[f,h] < threshold  (Q1, Q2).
+// Review pass: 8 lanes per reviewer, 4 reviewers per warp; the reviewed fund's row against the opening
+// prices and the history columns t-h and h.  Returns the number of divestments (< 0: event overflow).
+// ------------------------------------------------------------------------------------------------
+__device__ FSB_FP_INLINE int phase_review(const int t)
+{
+    Ctx &c = ctx();
+    FSB_TH;
+    const int K = c.K, Mp = c.Mp, cap = c.cap, half = Mp >> 1;
+    const int j8 = lane & 7, g4 = lane >> 3;
     int nrev = 0, idle_cash = 0;
     {
         bool ovf = false;
-        for (int w = 0; w < c.nwarps; ++w) {
-            const int x = c.wcnt[w];
+        for (int w = 0; w < nwarps; ++w) {
+            const int x = c.wcnt_()[w];
             ovf = ovf || (x > cap);
             nrev += x;
-            idle_cash += c.wcnt[c.nwarps + w];
+            idle_cash += c.wcnt_()[nwarps + w];
         }
-        if (ovf || nrev > cap) {  // uniform across the block
-            if (tid == 0) atomicOr(&s.err[c.r], FSB_REP_EVENT_OVERFLOW);
-            return;
-        }
+        if (ovf || nrev > cap) return -1;  // uniform across the block
     }
-
-    // ---- perfreview (:157-176): (V[f,t] - V[f,t-h]) / V[f,h] < threshold  (Q1, Q2) --------------
-    // review pass: 8 lanes per reviewer, 4 reviewers per warp; the reviewed fund's row against
-    // the opening prices and the history columns t-h and h
-    for (int ib = c.warp * 4; ib < nrev; ib += c.nwarps * 4) {
+    const double *po = p_open(c);
+#pragma unroll 1
+    for (int ib = warp * 4; ib < nrev; ib += nwarps * 4) {
         const int i = ib + g4;
         const bool on = i < nrev;
-        const int n = on ? chunk_list_get(c, cap, i) : 0;
-        const int f = c.pos16[n];
+        const int n = on ? chunk_list_get(c, nwarps, i) : 0;
+        const int f = c.pos16_()[n];
         bool valid = on && f < K;
         double thr = 0.0, amt = 0.0;
         if (valid) {  // (loaded together with the row and the columns: one memory latency)
             thr = c.threshold[n];
             amt = c.amount[n];
         }
-        const int h = c.hor16[n];
+        const int h = c.hor16_()[n];
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
         if (valid) {
             const double2 *row = reinterpret_cast<const double2 *>(c.H + static_cast<long long>(f) * Mp);
-            const double2 *c1 = reinterpret_cast<const double2 *>(c.P + static_cast<long long>(pcol(s, t - h)) * Mp);
-            const double2 *c2 = reinterpret_cast<const double2 *>(c.P + static_cast<long long>(pcol(s, h)) * Mp);
+            const double2 *c1 = reinterpret_cast<const double2 *>(c.P + static_cast<long long>(pcol(c, t - h)) * Mp);
+            const double2 *c2 = reinterpret_cast<const double2 *>(c.P + static_cast<long long>(pcol(c, h)) * Mp);
             const double2 *c0 = reinterpret_cast<const double2 *>(po);
 #pragma unroll 4
             for (int e2 = j8; e2 < half; e2 += 8) {
@@ -812,16 +954,13 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
         }
         a0 = tree8(a0); a1 = tree8(a1); a2 = tree8(a2);
         valid = valid && (amt > 0.0);
+        int flag = 0;
+        if (valid) flag = (ddiv(a0 - a1, a2) < thr) ? 1 : 0;
         if (on && j8 == 0) {
-            int flag = 0;
-            if (valid) {
-                const double valchange = (a0 - a1) / a2;
-                flag = (valchange < thr) ? 1 : 0;
-                c.nav_open[f] = a0;
-            }
-            c.rev[i] = n;
-            c.rfund[i] = f;
-            c.flags[i] = flag;
+            if (valid) c.nav_open[f] = a0;
+            c.rev_()[i] = n;
+            c.rfund_()[i] = f;
+            c.flags_()[i] = flag;
         }
     }
     __syncthreads();  // B2
@@ -830,14 +969,14 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
     int nd = 0;
     for (int b = 0; b < nrev; b += 32) {
         const int i = b + lane;
-        const bool p = (i < nrev) && c.flags[i];
+        const bool p = (i < nrev) && c.flags_()[i];
         const unsigned m = __ballot_sync(0xffffffffu, p);
         if (p) {
             const int k = nd + __popc(m & ((1u << lane) - 1u));
-            const int f = c.rfund[i];
-            c.d_inv[k] = c.rev[i];
-            c.d_fund[k] = f;
-            if (c.warp == 0) atomicOr(reinterpret_cast<unsigned *>(&c.fmod[f >> 5]), 1u << (f & 31));
+            const int f = c.rfund_()[i];
+            c.d_inv_()[k] = c.rev_()[i];
+            c.d_fund_()[k] = f;
+            if (warp == 0) atomicOr(reinterpret_cast<unsigned *>(&c.fmod_()[f >> 5]), 1u << (f & 31));
         }
         nd += __popc(m);
     }
@@ -846,94 +985,107 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
         c.cnt[CNT_REVIEWS] += nrev;
         c.cnt[CNT_DIVEST] += nd;
         c.cnt[CNT_STEPS] += 1;
-        if (traced) {
-            for (int i = 0; i < nrev; ++i) trace_emit(s, c, t, FSB_EV_REVIEWER, c.rev[i], 0, 0.0);
-            for (int o = 0; o < nd; ++o) trace_emit(s, c, t, FSB_EV_DIVEST, c.d_inv[o], c.d_fund[o], 0.0);
-        }
+        c.isc_()[I_NREV] = nrev;
+        c.isc_()[I_IDLE] = idle_cash;
     }
     FSB_MARK(16);
-    if (nd == 0) {  // :464 -- nothing else happens this step
-        open_pass(s, c);
-        for (int m2 = tid; m2 < half; m2 += NT) reinterpret_cast<double2 *>(Pt)[m2] = reinterpret_cast<const double2 *>(pc)[m2];
-        if (tid == 0) s.flow_hist[c.r * kFlowBins] += 1;
-        __syncthreads();
-        FSB_MARK(3);
-        if (traced)
-            for (int k = tid; k < K; k += NT)
-                s.tr_nav[static_cast<long long>(c.trace) * K * s.T + k + static_cast<long long>(K) * (t - 1)] = c.nav_open[k];
-        return;
-    }
+    return nd;
+}
 
-    // ---- liquidate! (:183-201), part 1: the stake sequence (sequential within a fund) ---------
-    // one warp per distinct fund; the fund's members (ascending investor id) are gathered into a
-    // per-warp list (16-byte scans of the shared investor->fund map), summed in that order and
-    // renormalised from the list
-    if (c.warp == 1 % c.nwarps) {  // history columns of the leavers' horizons: wanted in L2 by the full pass
+// ------------------------------------------------------------------------------------------------
+// T2: liquidate! (:183-201), trackvolume! (:467), marketmake! (:205-211), executeorder!(Sell)
+// (:213-224), disburse! cash (:243-252).  Returns 1 when a fund's stakes sum to zero (:471).
+// ------------------------------------------------------------------------------------------------
+__device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
+{
+    Ctx &c = ctx();
+    FSB_TH;
+    const int K = c.K, M = c.M, N = c.N, Mp = c.Mp;
+    const int j8 = lane & 7, g4 = lane >> 3;
+    double *const pc = p_cur(c);
+    // part 1: the stake sequence (sequential within a fund).  One warp per distinct fund; the fund's
+    // members (ascending investor id) are gathered into a per-warp list (16-byte scans of the shared
+    // investor->fund map) with their stakes, the fund's divestments are applied in order on the list and
+    // the stakes written back once
+    if (warp == 1 % nwarps) {  // history columns of the leavers' horizons: wanted in L2 by the column staging
         for (int o = lane; o < nd; o += 32)
-            l2_prefetch_bulk(c.P + static_cast<long long>(pcol(s, t - c.hor16[c.d_inv[o]])) * Mp, static_cast<unsigned>(Mp * 8));
+            l2_prefetch_bulk(c.P + static_cast<long long>(pcol(c, t - c.hor16_()[c.d_inv_()[o]])) * Mp, static_cast<unsigned>(Mp * 8));
     }
     FSB_MARK(17);
     {
         const int capm = (c.wsd * 2) / 3;
-        double *mv = c.cols + 2 * c.cpk + c.warp * c.wsd;
+        double *mv = c.cols_() + 2 * c.cpk + warp * c.wsd;
         int *mn = reinterpret_cast<int *>(mv + capm);
-        for (int o = c.warp; o < nd; o += c.nwarps) {
-            const int f = c.d_fund[o];
+#pragma unroll 1
+        for (int o = warp; o < nd; o += nwarps) {
+            const int f = c.d_fund_()[o];
             bool leader = true;
-            for (int q = 0; q < o; ++q) leader = leader && (c.d_fund[q] != f);
+            for (int q = 0; q < o; ++q) leader = leader && (c.d_fund_()[q] != f);
             if (!leader) continue;
-            double tot = 0.0;
-            for (int o2 = o; o2 < nd; ++o2) {
-                if (c.d_fund[o2] != f) continue;
-                const int inv = c.d_inv[o2];
-                const double sk = c.stk[inv];
-                __syncwarp();
-                if (lane == 0) { c.d_stake[o2] = sk; c.stk[inv] = 0.0; c.stake[inv] = 0.0; }
-                __syncwarp();
-                int cntm = 0;
-                for (int b = 0; b < N; b += 256) {
-                    const int n0 = b + 8 * lane;
-                    unsigned mask = 0;
-                    if (n0 < N) {
-                        const int4 w = *reinterpret_cast<const int4 *>(c.pos16 + n0);
-                        const int ws[4] = { w.x, w.y, w.z, w.w };
+            // members of the fund, ascending id (the leavers still count: their position moves at the cash-out)
+            int cntm = 0;
+#pragma unroll 1
+            for (int b = 0; b < N; b += 256) {
+                const int n0 = b + 8 * lane;
+                unsigned mask = 0;
+                if (n0 < N) {
+                    const int4 w = *reinterpret_cast<const int4 *>(c.pos16_() + n0);
+                    const int ws[4] = { w.x, w.y, w.z, w.w };
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            mask |= (static_cast<short>(ws[q] & 0xffff) == f) ? (1u << (2 * q)) : 0u;
-                            mask |= (static_cast<short>(ws[q] >> 16) == f) ? (2u << (2 * q)) : 0u;
-                        }
+                    for (int q = 0; q < 4; ++q) {
+                        mask |= (static_cast<short>(ws[q] & 0xffff) == f) ? (1u << (2 * q)) : 0u;
+                        mask |= (static_cast<short>(ws[q] >> 16) == f) ? (2u << (2 * q)) : 0u;
                     }
-                    const int cntl = __popc(mask);
-                    int incl = cntl;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int x = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += x;
-                    }
-                    int w = cntm + incl - cntl;
-                    while (mask) {
-                        const int q = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        if (w < capm) { mn[w] = n0 + q; mv[w] = c.stk[n0 + q]; }
-                        ++w;
-                    }
-                    cntm += __shfl_sync(0xffffffffu, incl, 31);
                 }
-                __syncwarp();
-                // sum(stakes[fund,:]): members dealt round-robin to the 32 lanes, butterfly 16,8,4,2,1
-                tot = 0.0;
-                if (cntm <= capm) {
+                const int cntl = __popc(mask);
+                int incl = cntl;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int x = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += x;
+                }
+                int w = cntm + incl - cntl;
+                while (mask) {
+                    const int q = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (w < capm) { mn[w] = n0 + q; mv[w] = c.stake[n0 + q]; }
+                    ++w;
+                }
+                cntm += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            __syncwarp();
+            double tot = 0.0;
+            if (cntm <= capm) {
+#pragma unroll 1
+                for (int o2 = o; o2 < nd; ++o2) {
+                    if (c.d_fund_()[o2] != f) continue;
+                    const int inv = c.d_inv_()[o2];
+                    for (int q = lane; q < cntm; q += 32)
+                        if (mn[q] == inv) { c.d_stake_()[o2] = mv[q]; mv[q] = 0.0; }
+                    __syncwarp();
+                    // sum(stakes[fund,:]): members dealt round-robin to the 32 lanes, butterfly 16,8,4,2,1
+                    tot = 0.0;
                     for (int q = lane; q < cntm; q += 32) tot = tot + mv[q];
 #pragma unroll
                     for (int sft = 16; sft >= 1; sft >>= 1) tot = tot + __shfl_xor_sync(0xffffffffu, tot, sft);
                     if (tot > 0.0)
-                        for (int q = lane; q < cntm; q += 32) { const double sv = qdiv(mv[q], tot); c.stk[mn[q]] = sv; c.stake[mn[q]] = sv; }
-                } else {  // list does not fit: scan twice; member i of the fund goes to lane i % 32
+                        for (int q = lane; q < cntm; q += 32) mv[q] = qdiv(mv[q], tot);
+                    __syncwarp();
+                }
+                for (int q = lane; q < cntm; q += 32) c.stake[mn[q]] = mv[q];
+            } else {  // list does not fit: work on the global stakes; member i of the fund goes to lane i % 32
+#pragma unroll 1
+                for (int o2 = o; o2 < nd; ++o2) {
+                    if (c.d_fund_()[o2] != f) continue;
+                    const int inv = c.d_inv_()[o2];
+                    if (lane == 0) { c.d_stake_()[o2] = c.stake[inv]; c.stake[inv] = 0.0; }
+                    __syncwarp();
                     int seen = 0;
+                    tot = 0.0;
                     for (int b = 0; b < N; b += 32) {
                         const int n = b + lane;
-                        const bool mem = (n < N) && (c.pos16[n] == f);
-                        const double v = mem ? c.stk[n] : 0.0;
+                        const bool mem = (n < N) && (c.pos16_()[n] == f);
+                        const double v = mem ? c.stake[n] : 0.0;
                         unsigned m = __ballot_sync(0xffffffffu, mem);
                         while (m) {
                             const int q = __ffs(m) - 1;
@@ -947,14 +1099,14 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
                     for (int sft = 16; sft >= 1; sft >>= 1) tot = tot + __shfl_xor_sync(0xffffffffu, tot, sft);
                     if (tot > 0.0) {
                         for (int n = lane; n < N; n += 32)
-                            if (c.pos16[n] == f) { const double sv = qdiv(c.stk[n], tot); c.stk[n] = sv; c.stake[n] = sv; }
+                            if (c.pos16_()[n] == f) c.stake[n] = qdiv(c.stake[n], tot);
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             if (lane == 0) {
                 const unsigned char sl = (tot == 0.0) ? 1 : 0;
-                c.stl[f] = sl;
+                c.stl_()[f] = sl;
                 c.stakeless[f] = sl;
             }
         }
@@ -962,18 +1114,20 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
     FSB_MARK(18);
     __syncthreads();  // B4
     FSB_MARK(4);
-
-    // ---- liquidate! part 2 + trackvolume! (:467) + marketmake! (:205-211), one asset per thread ----
+    // part 2: sale orders, net supply, impact; one asset per thread and trip
+#pragma unroll 1
     for (int m = tid; m < M; m += NT) {
         const double p = pc[m];
+        const double imp = c.impact[m];
         double net = 0.0;
+#pragma unroll 1
         for (int o0 = 0; o0 < nd; o0 += 4) {
             // rows of up to 4 orders are loaded together unless two of them sell the same fund
             // (then the later one must see the earlier one's scaled holdings)
             const int n4 = min(4, nd - o0);
             int fq[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) fq[q] = (q < n4) ? c.d_fund[o0 + q] : -1 - q;
+            for (int q = 0; q < 4; ++q) fq[q] = (q < n4) ? c.d_fund_()[o0 + q] : -1 - q;
             const bool dup = (fq[1] == fq[0]) || (fq[2] == fq[0]) || (fq[2] == fq[1]) || (fq[3] == fq[0]) || (fq[3] == fq[1]) || (fq[3] == fq[2]);
             double hq[4];
 #pragma unroll
@@ -983,270 +1137,297 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
             for (int q = 0; q < 4; ++q) {
                 if (q < n4) {
                     const int o = o0 + q;
-                    const double sk = c.d_stake[o];
+                    const double sk = c.d_stake_()[o];
                     double *hpn = c.H + static_cast<long long>(fq[q]) * Mp + m;
                     const double h = dup ? *hpn : hq[q];
                     const double v = (-sk) * (h * p);
-                    order_row(c, Mp, o)[m] = v;
+                    order_row(c, o)[m] = v;
                     net = net + v;
                     const double hn = h * (1.0 - sk);
                     *hpn = hn;
-                    if (hn != 0.0) c.nzf[o] = 1;
+                    if (hn != 0.0) c.nzf_()[o] = 1;
                 }
             }
         }
-        c.sellsum[m] = net;
-        double v = (1.0 + net * c.impact[m]) * p;
+        c.sellsum_()[m] = net;
+        double v = (1.0 + net * imp) * p;
         int fl = 0;
         if (v < kPriceFloor) { v = kPriceFloor; fl = 1; }
         if (c.volume) c.volume[static_cast<long long>(t - 1) * Mp + m] -= net;
-        c.pick[m] = fl;
+        c.pick_()[m] = fl;
         pc[m] = v;
-        c.ratio[m] = v / p;  // priceratio, :217
+        c.ratio_()[m] = ddiv(v, p);  // priceratio, :217
     }
     __syncthreads();  // B5
     FSB_MARK(5);
-    // ---- executeorder!(Sell) cash-outs (:218-222) and disburse! (:243-252), 8 lanes per order ----
-    for (int ob = c.warp * 4; ob < nd; ob += c.nwarps * 4) {
+    // cash-outs (:218-222) and disburse! (:243-252), 8 lanes per order
+#pragma unroll 1
+    for (int ob = warp * 4; ob < nd; ob += nwarps * 4) {
         const int o = ob + g4;
         const bool on = o < nd;
-        const double cash = -sumprod8(order_row(c, Mp, on ? o : ob), c.ratio, M, j8, on);
+        const double cash = -sumprod8(order_row(c, on ? o : ob), c.ratio_(), M, j8, on);
         if (on && j8 == 0) {
-            const int inv = c.d_inv[o];
-            c.d_cash[o] = cash;
+            const int inv = c.d_inv_()[o];
+            c.d_cash_()[o] = cash;
             c.amount[inv] = cash;  // Q8: assigned, not accumulated
             c.pos[inv] = K;
-            c.pos16[inv] = static_cast<short>(K);
+            c.pos16_()[inv] = static_cast<short>(K);
         }
     }
-    if (c.warp == c.nwarps - 1) {
+    if (warp == nwarps - 1) {
         // redemption-flow histogram: total money sold this step, log2 bins
-        const double flow = -sum8(c.sellsum, M, j8);
+        const double flow = -sum8(c.sellsum_(), M, j8);
         if (lane == 0) {
             int bin = 0;
             if (flow >= 1.0) {
                 const int e = static_cast<int>((__double_as_longlong(flow) >> 52) & 0x7ff) - 1023;
                 bin = min(kFlowBins - 1, e + 1);
             }
-            s.flow_hist[c.r * kFlowBins + bin] += 1;
+            c.flow_hist[bin] += 1;
         }
         for (int o = lane; o < nd; o += 32) {  // the last order of a fund decides whether its row is all zero
-            const int f = c.d_fund[o];
+            const int f = c.d_fund_()[o];
             bool last = true;
-            for (int q = o + 1; q < nd; ++q) last = last && (c.d_fund[q] != f);
-            if (last) c.hzero[f] = c.nzf[o] ? 0 : 1;
+            for (int q = o + 1; q < nd; ++q) last = last && (c.d_fund_()[q] != f);
+            if (last) { const unsigned char z = c.nzf_()[o] ? 0 : 1; c.hz_()[f] = z; c.hzero[f] = z; }
         }
     }
-    floor_account(s, c, t, 0);
-    // ---- respawn trigger (:471): any fund whose stakes sum to zero ----------------------------
+    floor_account(t, 0);
+    // respawn trigger (:471): any fund whose stakes sum to zero
     int dead_local = 0;
-    for (int k = tid; k < K; k += NT) dead_local |= c.stl[k];
+    for (int k = tid; k < K; k += NT) dead_local |= c.stl_()[k];
     const int any_dead = __syncthreads_or(dead_local);  // B6
     FSB_MARK(6);
-    if (traced && tid == 0)
-        for (int o = 0; o < nd; ++o) trace_emit(s, c, t, FSB_EV_CASHOUT, c.d_inv[o], c.d_fund[o], c.d_cash[o]);
-    if (traced)
-        for (int m = tid; m < M; m += NT)
-            s.tr_psell[static_cast<long long>(c.trace) * M * s.T + m + static_cast<long long>(M) * (t - 1)] = pc[m];
+    return any_dead;
+}
 
-    int any_egg = 0;
-    if (any_dead) {  // Q5: the trigger is the stake sums, the candidates are the all-zero rows
+// ------------------------------------------------------------------------------------------------
+// T3: respawn! (:275-321) + executeorder!(Buy) (:229-239) + disburse! shares (:256-263); cold (0.23 per
+// step).  Q5: the trigger is the stake sums, the candidates are the all-zero rows.  Returns 0, or != 0
+// when the replication must stop (error flags already raised).
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ int phase_respawn(const int t, const int nd, const int flags)
+{
+    Ctx &c = ctx();
+    FSB_TH;
+    const int K = c.K, M = c.M, N = c.N, Mp = c.Mp, cap = c.cap;
+    const int j8 = lane & 7;
+    const bool traced = (c.trace >= 0);
+    double *const po = p_open(c), *const pc = p_cur(c);
+    {
         int eg = 0;
-        for (int k = tid; k < K; k += NT) eg |= c.hzero[k];
-        any_egg = __syncthreads_or(eg);
+        for (int k = tid; k < K; k += NT) eg |= c.hz_()[k];
+        if (!__syncthreads_or(eg)) return 0;
     }
-    if (any_egg) {
-        // ---- respawn! (:275-321) ----------------------------------------------------------------
-        const int neggs = block_compact(c, K, cap, c.eggs, [&](int k) { return c.hzero[k] != 0; });
-        const int ncash = block_compact(c, N, cap, c.cash, [&](int n) { return c.pos16[n] == K && c.amount[n] > 0.0; });
-        if (neggs > cap || ncash > cap || neggs > ncash) {
-            if (tid == 0) atomicOr(&s.err[c.r], (neggs > ncash && neggs <= cap && ncash <= cap) ? FSB_REP_Q6_NO_ANCHOR : FSB_REP_EVENT_OVERFLOW);
-            return;
+    const int idle_cash = c.isc_()[I_IDLE];
+    if (warp == 0) {
+        const int ne = warp_compact(lane, K, cap, c.eggs_(), [&](int k) { return c.hz_()[k] != 0; });
+        int ncs;
+        if (idle_cash == 0) {  // the cash holders are today's leavers with a positive cash-out (ascending ids)
+            ncs = warp_compact(lane, nd, cap, c.cash_(), [&](int o) { return c.d_cash_()[o] > 0.0; });
+            for (int q = lane; q < min(ncs, cap); q += 32) c.cash_()[q] = c.d_inv_()[c.cash_()[q]];
+        } else {
+            ncs = warp_compact(lane, N, cap, c.cash_(), [&](int n) { return c.pos16_()[n] == K && c.amount[n] > 0.0; });
         }
-        for (int i = 0; i < neggs; ++i) {
-            if (tid == 0) {
-                int jj = i, e = 0;
-                if (c.tape) {
-                    double v;
-                    if (!tape_lookup(c, FSB_TAPE_ANCHOR, t, i, 0, &v)) e |= FSB_REP_TAPE_MISSING;
-                    else {
-                        for (jj = i; jj < ncash; ++jj) if (c.cash[jj] == static_cast<int>(v)) break;
-                        if (jj == ncash) { e |= FSB_REP_TAPE_INVALID; jj = i; }
-                    }
-                } else {
-                    jj = i + static_cast<int>(draw_discrete(c.rng, SITE_SHUFFLE, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(i), static_cast<uint32_t>(ncash - i)));
+        if (lane == 0) { c.isc_()[I_NEGGS] = ne; c.isc_()[I_NCASH] = ncs; }
+    }
+    __syncthreads();
+    const int neggs = c.isc_()[I_NEGGS], ncash = c.isc_()[I_NCASH];
+    if (neggs > cap || ncash > cap || neggs > ncash) {
+        if (tid == 0) atomicOr(c.err, (neggs > ncash && neggs <= cap && ncash <= cap) ? FSB_REP_Q6_NO_ANCHOR : FSB_REP_EVENT_OVERFLOW);
+        return 1;
+    }
+#pragma unroll 1
+    for (int i = 0; i < neggs; ++i) {
+        if (tid == 0) {
+            int jj = i, e = 0;
+            if (c.tape) {
+                double v;
+                if (!tape_lookup(c, FSB_TAPE_ANCHOR, t, i, 0, &v)) e |= FSB_REP_TAPE_MISSING;
+                else {
+                    for (jj = i; jj < ncash; ++jj) if (c.cash_()[jj] == static_cast<int>(v)) break;
+                    if (jj == ncash) { e |= FSB_REP_TAPE_INVALID; jj = i; }
                 }
-                const int tmp = c.cash[i]; c.cash[i] = c.cash[jj]; c.cash[jj] = tmp;
-                const int inv = c.cash[i], egg = c.eggs[i];
-                const double capital = c.amount[inv];
-                c.pos[inv] = egg;      // :288-289 (amount keeps the capital)
-                c.pos16[inv] = static_cast<short>(egg);
-                c.stake[inv] = 1.0;    // :296
-                c.stk[inv] = 1.0;
-                c.stl[egg] = 0;
-                c.stakeless[egg] = 0;
-                int nk = 0;
-                if (c.tape) {
-                    double v;
-                    if (!tape_lookup(c, FSB_TAPE_RPSIZE, t, i, 0, &v)) e |= FSB_REP_TAPE_MISSING; else nk = static_cast<int>(v);
-                } else {
-                    nk = pt.psize_lo + static_cast<int>(draw_discrete(c.rng, SITE_RPSIZE, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(i), static_cast<uint32_t>(pt.psize_hi - pt.psize_lo + 1)));
-                }
-                c.scal[1] = capital;
-                c.isc[I_TMP0] = nk;
-                c.isc[I_TMP1] = egg;
-                c.isc[I_TMP2] = inv;
-                if (e) c.isc[I_ERR] |= e;
-                if (traced) {
-                    trace_emit(s, c, t, FSB_EV_SPAWN, egg, inv, capital);
-                    trace_emit(s, c, t, FSB_EV_SPAWN_N, egg, nk, 0.0);
+            } else {
+                jj = i + static_cast<int>(draw_discrete_s(c.rng, SITE_SHUFFLE, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(i), static_cast<uint32_t>(ncash - i)));
+            }
+            const int tmp = c.cash_()[i]; c.cash_()[i] = c.cash_()[jj]; c.cash_()[jj] = tmp;
+            const int inv = c.cash_()[i], egg = c.eggs_()[i];
+            const double capital = c.amount[inv];
+            c.pos[inv] = egg;      // :288-289 (amount keeps the capital)
+            c.pos16_()[inv] = static_cast<short>(egg);
+            c.stake[inv] = 1.0;    // :296
+            c.stl_()[egg] = 0;
+            c.stakeless[egg] = 0;
+            int nk = 0;
+            if (c.tape) {
+                double v;
+                if (!tape_lookup(c, FSB_TAPE_RPSIZE, t, i, 0, &v)) e |= FSB_REP_TAPE_MISSING; else nk = static_cast<int>(v);
+            } else {
+                nk = c.psize_lo + static_cast<int>(draw_discrete_s(c.rng, SITE_RPSIZE, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(i), static_cast<uint32_t>(c.psize_hi - c.psize_lo + 1)));
+            }
+            c.scal_()[1] = capital;
+            c.isc_()[I_TMP0] = nk;
+            c.isc_()[I_TMP1] = egg;
+            c.isc_()[I_TMP2] = inv;
+            if (e) c.isc_()[I_ERR] |= e;
+            if (traced) {
+                trace_emit(c, t, FSB_EV_SPAWN, egg, inv, capital);
+                trace_emit(c, t, FSB_EV_SPAWN_N, egg, nk, 0.0);
+            }
+        }
+        for (int m = tid; m < c.cp; m += NT) c.pick_()[m] = 0;
+        __syncthreads();
+        const int nk = c.isc_()[I_TMP0], egg = c.isc_()[I_TMP1];
+        const double capital = c.scal_()[1];
+        // the egg's opening NAV, if the review pass has not taken it (row is about to change)
+        if (warp == 1 % nwarps) {
+            const bool need = !((c.fmod_()[egg >> 5] >> (egg & 31)) & 1);
+            const double v = dot8(c.H + static_cast<long long>(egg) * Mp, po, M, j8, need);
+            if (need && lane == 0) {
+                c.nav_open[egg] = v;
+                c.fmod_()[egg >> 5] |= 1u << (egg & 31);
+            }
+        }
+        // fundholdinit! picks (:123-129): all increments to one stock are the same value, so
+        // counting picks per stock and adding that value `count` times is the same sequence
+        for (int jj = tid; jj < nk; jj += NT) {
+            int sidx = 0;
+            if (c.tape) {
+                double v;
+                if (!tape_lookup(c, FSB_TAPE_RPPICK, t, i, jj, &v)) atomicOr(&c.isc_()[I_ERR], FSB_REP_TAPE_MISSING);
+                else sidx = static_cast<int>(v);
+            } else {
+                sidx = static_cast<int>(draw_discrete_s(c.rng, SITE_RPPICK, static_cast<uint32_t>(t), static_cast<uint32_t>(i), static_cast<uint32_t>(jj), static_cast<uint32_t>(M)));
+            }
+            atomicAdd(&c.pick_()[sidx], 1);
+        }
+        if (traced && tid == 0) {
+            for (int jj = 0; jj < nk; ++jj) {
+                double v = 0.0;
+                if (c.tape) tape_lookup(c, FSB_TAPE_RPPICK, t, i, jj, &v);
+                else v = static_cast<double>(draw_discrete_s(c.rng, SITE_RPPICK, static_cast<uint32_t>(t), static_cast<uint32_t>(i), static_cast<uint32_t>(jj), static_cast<uint32_t>(M)));
+                trace_emit(c, t, FSB_EV_PICK, egg, static_cast<int>(v), 0.0);
+            }
+        }
+        __syncthreads();
+        double *bo = order_row(c, i);
+        for (int m = tid; m < Mp; m += NT) {
+            double val = 0.0;
+            if (m < M) {
+                const double p = pc[m];
+                const double x = ddiv(ddiv(capital, static_cast<double>(nk)), p);
+                double u = c.H[static_cast<long long>(egg) * Mp + m];
+                const int cn = c.pick_()[m];
+                for (int q = 0; q < cn; ++q) u = u + x;
+                val = u * p;  // buy order in money, at the pre-impact price (Q15)
+            }
+            bo[m] = val;
+        }
+        __syncthreads();
+        if (warp == 0) {  // log chain + new row (:298-318)
+            const double fundsize = sum8(bo, M, j8);
+            int nst = 0;
+            double acc = 0.0;
+            for (int e = 2 * j8; e < M; e += 16) {
+                const double v0 = bo[e];
+                nst += (v0 > 0.0);
+                acc = acc + qdiv(v0, fundsize) * c.impact[e];
+                if (e + 1 < M) {
+                    const double v1 = bo[e + 1];
+                    nst += (v1 > 0.0);
+                    acc = acc + qdiv(v1, fundsize) * c.impact[e + 1];
                 }
             }
-            for (int m = tid; m < c.cp; m += NT) c.pick[m] = 0;
-            __syncthreads();
-            const int nk = c.isc[I_TMP0], egg = c.isc[I_TMP1];
-            const double capital = c.scal[1];
-            // the egg's opening NAV, if the review pass has not taken it (row is about to change)
-            if (c.warp == 1 % c.nwarps) {
-                const bool need = !((c.fmod[egg >> 5] >> (egg & 31)) & 1);
-                const double v = dot8(c.H + static_cast<long long>(egg) * Mp, po, M, j8, need);
-                if (need && lane == 0) {
-                    c.nav_open[egg] = v;
-                    c.fmod[egg >> 5] |= 1u << (egg & 31);
-                }
-            }
-            // fundholdinit! picks (:123-129): all increments to one stock are the same value, so
-            // counting picks per stock and adding that value `count` times is the same sequence
-            for (int jj = tid; jj < nk; jj += NT) {
-                int sidx = 0;
-                if (c.tape) {
-                    double v;
-                    if (!tape_lookup(c, FSB_TAPE_RPPICK, t, i, jj, &v)) atomicOr(&c.isc[I_ERR], FSB_REP_TAPE_MISSING);
-                    else sidx = static_cast<int>(v);
-                } else {
-                    sidx = static_cast<int>(draw_discrete(c.rng, SITE_RPPICK, static_cast<uint32_t>(t), static_cast<uint32_t>(i), static_cast<uint32_t>(jj), static_cast<uint32_t>(M)));
-                }
-                atomicAdd(&c.pick[sidx], 1);
-            }
-            if (traced && tid == 0 && !c.tape)
-                for (int jj = 0; jj < nk; ++jj)
-                    trace_emit(s, c, t, FSB_EV_PICK, egg, static_cast<int>(draw_discrete(c.rng, SITE_RPPICK, static_cast<uint32_t>(t), static_cast<uint32_t>(i), static_cast<uint32_t>(jj), static_cast<uint32_t>(M))), 0.0);
-            if (traced && tid == 0 && c.tape)
-                for (int jj = 0; jj < nk; ++jj) { double v = 0.0; tape_lookup(c, FSB_TAPE_RPPICK, t, i, jj, &v); trace_emit(s, c, t, FSB_EV_PICK, egg, static_cast<int>(v), 0.0); }
-            __syncthreads();
-            double *bo = order_row(c, Mp, i);
-            for (int m = tid; m < Mp; m += NT) {
-                double val = 0.0;
-                if (m < M) {
-                    const double p = pc[m];
-                    const double x = (capital / static_cast<double>(nk)) / p;
-                    double u = c.H[static_cast<long long>(egg) * Mp + m];
-                    const int cn = c.pick[m];
-                    for (int q = 0; q < cn; ++q) u = u + x;
-                    val = u * p;  // buy order in money, at the pre-impact price (Q15)
-                }
-                bo[m] = val;
-            }
-            __syncthreads();
-            if (c.warp == 0) {  // log chain + new row (:298-318)
-                const double fundsize = sum8(bo, M, j8);
-                int nst = 0;
-                double acc = 0.0;
-                for (int e = 2 * j8; e < M; e += 16) {
-                    const double v0 = bo[e];
-                    nst += (v0 > 0.0);
-                    acc = acc + qdiv(v0, fundsize) * c.impact[e];
-                    if (e + 1 < M) {
-                        const double v1 = bo[e + 1];
-                        nst += (v1 > 0.0);
-                        acc = acc + qdiv(v1, fundsize) * c.impact[e + 1];
-                    }
-                }
-                const double liq = tree8(acc);
+            const double liq = tree8(acc);
 #pragma unroll
-                for (int sft = 4; sft >= 1; sft >>= 1) nst += __shfl_xor_sync(0xffffffffu, nst, sft);
-                if (lane == 0) {
-                    const int rows = s.log_n[c.r];
-                    if (rows >= s.cap_log) {
-                        c.isc[I_ERR] |= FSB_REP_LOG_OVERFLOW;
-                    } else {
-                        const long long lb = c.r * s.cap_log;
-                        const int old = c.live_row[egg];
-                        s.log_liquidated[lb + old] = 1;
-                        s.log_replacedby[lb + old] = rows + 1;  // 1-based row id, as in Julia
-                        s.log_failtime[lb + old] = t;
-                        s.log_liquidated[lb + rows] = 0;
-                        s.log_replacedby[lb + rows] = 0;
-                        s.log_size[lb + rows] = fundsize;
-                        s.log_liquidity[lb + rows] = liq;
-                        s.log_failtime[lb + rows] = 0;
-                        s.log_ninv[lb + rows] = 1;
-                        s.log_nstocks[lb + rows] = nst;
-                        c.live_row[egg] = rows;
-                        s.log_n[c.r] = rows + 1;
-                        c.cnt[CNT_RESPAWN] += 1;
-                    }
+            for (int sft = 4; sft >= 1; sft >>= 1) nst += __shfl_xor_sync(0xffffffffu, nst, sft);
+            if (lane == 0) {
+                const int rows = *c.log_n;
+                if (rows >= c.cap_log) {
+                    c.isc_()[I_ERR] |= FSB_REP_LOG_OVERFLOW;
+                } else {
+                    const int old = c.live_row[egg];
+                    c.log_liquidated[old] = 1;
+                    c.log_replacedby[old] = rows + 1;  // 1-based row id, as in Julia
+                    c.log_failtime[old] = t;
+                    c.log_liquidated[rows] = 0;
+                    c.log_replacedby[rows] = 0;
+                    c.log_size[rows] = fundsize;
+                    c.log_liquidity[rows] = liq;
+                    c.log_failtime[rows] = 0;
+                    c.log_ninv[rows] = 1;
+                    c.log_nstocks[rows] = nst;
+                    c.live_row[egg] = rows;
+                    *c.log_n = rows + 1;
+                    c.cnt[CNT_RESPAWN] += 1;
                 }
             }
-            __syncthreads();
         }
-        if (c.isc[I_ERR]) {
-            if (tid == 0) atomicOr(&s.err[c.r], c.isc[I_ERR]);
-            return;
-        }
-        // executeorder!(Buy) (:229-239) for the respawn orders + disburse! shares (:256-263)
-        for (int o = tid; o < cap; o += NT) c.nzf[o] = 0;
-        __syncthreads();
-        for (int m = tid; m < M; m += NT) {
-            double net = 0.0;
-            for (int i = 0; i < neggs; ++i) net = net + order_row(c, Mp, i)[m];
-            if (c.volume && !(flags & FSB_RUN_NO_VOLUME_QUIRK)) c.volume[static_cast<long long>(t - 1) * Mp + m] -= c.sellsum[m];  // :474 (Q3)
-            const double ni = net * c.impact[m];
-            double v = (1.0 + ni) * pc[m];
-            int fl = 0;
-            if (v < kPriceFloor) { v = kPriceFloor; fl = 1; }
-            c.pick[m] = fl;
-            pc[m] = v;
-            for (int i = 0; i < neggs; ++i) {
-                double *hpn = c.H + static_cast<long long>(c.eggs[i]) * Mp + m;
-                const double hn = *hpn + qdiv(order_row(c, Mp, i)[m], v);
-                *hpn = hn;
-                if (hn != 0.0) c.nzf[i] = 1;
-            }
-        }
-        __syncthreads();
-        if (tid == 0)
-            for (int i = 0; i < neggs; ++i) c.hzero[c.eggs[i]] = c.nzf[i] ? 0 : 1;
-        floor_account(s, c, t, 1);
         __syncthreads();
     }
-    if (traced)
-        for (int m = tid; m < M; m += NT)
-            s.tr_presp[static_cast<long long>(c.trace) * M * s.T + m + static_cast<long long>(M) * (t - 1)] = pc[m];
+    if (c.isc_()[I_ERR]) {
+        if (tid == 0) atomicOr(c.err, c.isc_()[I_ERR]);
+        return 1;
+    }
+    // executeorder!(Buy) for the respawn orders + disburse! shares
+    for (int o = tid; o < cap; o += NT) c.nzf_()[o] = 0;
+    __syncthreads();
+    for (int m = tid; m < M; m += NT) {
+        double net = 0.0;
+        for (int i = 0; i < neggs; ++i) net = net + order_row(c, i)[m];
+        if (c.volume && !(flags & FSB_RUN_NO_VOLUME_QUIRK)) c.volume[static_cast<long long>(t - 1) * Mp + m] -= c.sellsum_()[m];  // :474 (Q3)
+        const double ni = net * c.impact[m];
+        double v = (1.0 + ni) * pc[m];
+        int fl = 0;
+        if (v < kPriceFloor) { v = kPriceFloor; fl = 1; }
+        c.pick_()[m] = fl;
+        pc[m] = v;
+        for (int i = 0; i < neggs; ++i) {
+            double *hpn = c.H + static_cast<long long>(c.eggs_()[i]) * Mp + m;
+            const double hn = *hpn + qdiv(order_row(c, i)[m], v);
+            *hpn = hn;
+            if (hn != 0.0) c.nzf_()[i] = 1;
+        }
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int i = 0; i < neggs; ++i) { const unsigned char z = c.nzf_()[i] ? 0 : 1; c.hz_()[c.eggs_()[i]] = z; c.hzero[c.eggs_()[i]] = z; }
+    floor_account(t, 1);
+    __syncthreads();
+    return 0;
+}
 
-    FSB_MARK(7);
-    // ---- cash holders (:481, :339) and their distinct horizons, by warp 0 ----------------------
-    if (c.warp == 0) {
+// ------------------------------------------------------------------------------------------------
+// T4: cash holders (:481, :339) and their distinct horizons, by warp 0; ends with B7.
+// Returns the number of cash holders (< 0: event overflow).
+// ------------------------------------------------------------------------------------------------
+__device__ FSB_FP_INLINE int phase_cashlist(const int nd)
+{
+    Ctx &c = ctx();
+    FSB_TH;
+    const int K = c.K, N = c.N, cap = c.cap;
+    if (warp == 0) {
         int cnt = 0;
-        if (idle_cash == 0) {
+        if (c.isc_()[I_IDLE] == 0) {
             // nobody was in cash when the day started: the cash holders are today's leavers (ascending
             // ids already) that got a positive cash-out and were not used as respawn anchors
             for (int b = 0; b < nd; b += 32) {
                 const int o = b + lane;
-                const bool p = (o < nd) && (c.pos16[c.d_inv[o]] == K) && (c.d_cash[o] > 0.0);
+                const bool p = (o < nd) && (c.pos16_()[c.d_inv_()[o]] == K) && (c.d_cash_()[o] > 0.0);
                 const unsigned m = __ballot_sync(0xffffffffu, p);
-                if (p) c.cash[cnt + __popc(m & ((1u << lane) - 1u))] = c.d_inv[o];
+                if (p) c.cash_()[cnt + __popc(m & ((1u << lane) - 1u))] = c.d_inv_()[o];
                 cnt += __popc(m);
             }
         } else {
             for (int b = 0; b < N; b += 32) {
                 const int n = b + lane;
-                bool p = (n < N) && (c.pos16[n] == K);
+                bool p = (n < N) && (c.pos16_()[n] == K);
                 if (p) p = c.amount[n] > 0.0;
                 const unsigned m = __ballot_sync(0xffffffffu, p);
                 if (p) {
                     const int k = cnt + __popc(m & ((1u << lane) - 1u));
-                    if (k < cap) c.cash[k] = n;
+                    if (k < cap) c.cash_()[k] = n;
                 }
                 cnt += __popc(m);
             }
@@ -1256,258 +1437,316 @@ __device__ __forceinline__ void step_replication(const DevState &s, Ctx &c, int 
             int ncols = 0;
             const int nn = min(cnt, cap);
             for (int i = 0; i < nn; ++i) {
-                const int h = c.hor16[c.cash[i]];
+                const int h = c.hor16_()[c.cash_()[i]];
                 int q = 0;
-                for (; q < ncols; ++q) if (c.hcols[q] == h) break;
-                if (q == ncols) c.hcols[ncols++] = h;
-                c.r_col[i] = q;
+                for (; q < ncols; ++q) if (c.hcols_()[q] == h) break;
+                if (q == ncols) c.hcols_()[ncols++] = h;
+                c.r_col_()[i] = q;
             }
-            c.isc[I_NCASH] = cnt;
-            c.isc[I_NCOLS] = ncols;
+            c.isc_()[I_NCASH] = cnt;
+            c.isc_()[I_NCOLS] = ncols;
         }
     }
     __syncthreads();  // B7
     FSB_MARK(8);
-    const int ncash = c.isc[I_NCASH];
-    if (ncash > cap) {
-        if (tid == 0) atomicOr(&s.err[c.r], FSB_REP_EVENT_OVERFLOW);
-        return;
-    }
-    const int ncols = c.isc[I_NCOLS];
-    const int cmax = s.cmax;
-    const double normaliser = static_cast<double>(static_cast<long long>(K) * (K + 1) / 2);
+    const int ncash = c.isc_()[I_NCASH];
+    return (ncash > cap) ? -1 : ncash;
+}
 
-    // ---- fundrevalue!(1:K) at :460 and :479 + horizon returns of reinvest! (:335-379) ------------
-    for (int c0 = 0; c0 == 0 || c0 < ncols; c0 += cmax) {
-        const int nc = min(cmax, ncols - c0);
-        // stage the history columns t-h of this chunk: bulk asynchronous copies by one thread
-        if (nc > 0) {
-            if (tid == 0) {
-                fence_proxy_async();
-                mbar_expect_tx(c.mbar, static_cast<unsigned>(nc * Mp * 8));
-                for (int q = 0; q < nc; ++q)
-                    bulk_g2s(c.cols + (2 + q) * c.cpk, c.P + static_cast<long long>(pcol(s, t - c.hcols[c0 + q])) * Mp,
-                             static_cast<unsigned>(Mp * 8), c.mbar);
-            }
-            const int padw = c.cp - Mp;
-            for (int q = tid; q < nc * padw; q += NT) c.cols[(2 + q / padw) * c.cpk + Mp + (q % padw)] = 0.0;
-            mbar_wait(c.mbar, c.mbar_phase);
-            c.mbar_phase ^= 1u;
-        }
-        __syncthreads();  // B8 (pads; also orders the previous chunk's readers before this chunk's results)
-        FSB_MARK(9);
-        const bool prob = (selector == FSB_SEL_PROBABILISTIC);
-        full_pass_dispatch<FAST>(s, c, c0 == 0 ? 0 : 2, c0 == 0 ? 2 + nc : nc, prob);
-        __syncthreads();  // B9: vh[] holds the horizon returns (or their sort keys) of this chunk
-        FSB_MARK(10);
-        if (nc > 0) {
-            if (prob) {
-                // rank rule: p_k = rank_k / (K(K+1)/2) per column, into the (now free) staged column
-                for (int jc = c.warp; jc < nc; jc += c.nwarps) {
-                    unsigned long long *keys = reinterpret_cast<unsigned long long *>(c.vh) + jc * c.kq;
-                    double *prob_k = c.cols + (2 + jc) * c.cpk;
-                    bool done = false;
-                    if (c.kp2 == 256) done = warp_rank256(keys, K, prob_k, normaliser, lane);
-                    if (!done) {  // K > 256, or a 56-bit tie the packed sort cannot order: exact sort in shared memory
-                        unsigned short *idx = c.sidx + jc * c.kp2;
-                        for (int i = lane; i < c.kp2; i += 32) {
-                            if (i >= K) keys[i] = ~0ULL;
-                            idx[i] = static_cast<unsigned short>(i);
-                        }
-                        __syncwarp();
-                        warp_bitonic(keys, idx, c.kp2, lane);
-                        for (int i = lane; i < K; i += 32) prob_k[idx[i]] = static_cast<double>(i + 1) / normaliser;
-                    }
-                    __syncwarp();
-                    FSB_MARK(23);
-                    // the same warp samples the choice of every cash holder whose horizon is this column
-                    for (int i = lane; i < ncash; i += 32) {
-                        if (c.r_col[i] != c0 + jc) continue;
-                        int e = 0;
-                        const int choice = select_fund_prob(s, c, t, c.cash[i], prob_k, &e);
-                        c.r_choice[i] = choice;
-                        if (e) atomicOr(&c.isc[I_ERR], e);
-                    }
-                }
-                FSB_MARK(11);
-            } else {
-                for (int i = c.warp; i < ncash; i += c.nwarps) {
-                    const int col = c.r_col[i];
-                    if (col < c0 || col >= c0 + nc) continue;
-                    int e = 0;
-                    const int choice = select_fund_warp(s, c, t, c.cash[i], c.vh + (col - c0) * c.kq, selector, &e);
-                    if (lane == 0) {
-                        c.r_choice[i] = choice;
-                        if (e) atomicOr(&c.isc[I_ERR], e);
-                    }
-                }
-            }
-            __syncthreads();
-            FSB_MARK(12);
-        }
-    }
-    if (traced)
-        for (int k = tid; k < K; k += NT)
-            s.tr_nav[static_cast<long long>(c.trace) * K * s.T + k + static_cast<long long>(K) * (t - 1)] = c.nav_open[k];
-    if (c.isc[I_ERR]) {
-        if (tid == 0) atomicOr(&s.err[c.r], c.isc[I_ERR]);
-        return;
-    }
-    if (ncash > 0) {
-        for (int i = tid; i < ncash; i += NT) {
-            const int ch = c.r_choice[i];
-            const double inj = c.amount[c.cash[i]];
-            const double fv = c.nav[ch];  // == holdings[choice,:]' * stockvals[:,t], :360
-            c.r_inj[i] = inj;
-            c.r_fval[i] = fv;
-            c.r_ncap[i] = fv + inj;
-            c.stl[ch] = 1;  // cleared below by every member whose diluted stake is non-zero
-            atomicOr(reinterpret_cast<unsigned *>(&c.fsel[ch >> 5]), 1u << (ch & 31));
-        }
-        for (int o = tid; o < cap; o += NT) c.nzf[o] = 0;
-        __syncthreads();  // B13
-        FSB_MARK(13);
+// stage the history columns t-h of a chunk: bulk asynchronous copies (TMA unit) issued by one thread; ends with B8
+__device__ FSB_FP_INLINE void phase_stage_columns(const int t, const int c0, const int nc)
+{
+    Ctx &c = ctx();
+    FSB_TH;
+    const int Mp = c.Mp;
+    if (nc > 0) {
+        const unsigned phase = c.mbar_phase;
         if (tid == 0) {
-            c.cnt[CNT_REINVEST] += ncash;
-            if (traced)
-                for (int i = 0; i < ncash; ++i) trace_emit(s, c, t, FSB_EV_CHOICE, c.cash[i], c.r_choice[i], c.r_inj[i]);
+            fence_proxy_async();
+            mbar_expect_tx(c.mbar, static_cast<unsigned>(nc * Mp * 8));
+            for (int q = 0; q < nc; ++q)
+                bulk_g2s(c.cols_() + (2 + q) * c.cpk, c.P + static_cast<long long>(pcol(c, t - c.hcols_()[c0 + q])) * Mp,
+                         static_cast<unsigned>(Mp * 8), c.mbar);
         }
-        // stakes (:363-366), sequential over reinvestors per investor (Q7), parallel over investors
-        for (int n = tid; n < N; n += NT) {
-            int mypos = c.pos16[n];
-            // only cash holders and members of a chosen fund can be touched
-            if (mypos != K && !((c.fsel[mypos >> 5] >> (mypos & 31)) & 1)) continue;
-            bool touched = false;
-            for (int i = 0; i < ncash; ++i) {
-                const int ch = c.r_choice[i];
-                if (c.cash[i] == n) { mypos = ch; touched = true; }
-                else if (mypos == ch) touched = true;
-            }
-            if (!touched) continue;
-            mypos = c.pos16[n];
-            double st = c.stk[n];
-            for (int i = 0; i < ncash; ++i) {
-                const int ch = c.r_choice[i];
-                if (c.cash[i] == n) {
-                    mypos = ch;
-                    st = c.r_inj[i] / c.r_ncap[i];
-                } else if (mypos == ch) {
-                    st = qdiv(st * c.r_fval[i], c.r_ncap[i]);
-                }
-            }
-            c.pos[n] = mypos;
-            c.pos16[n] = static_cast<short>(mypos);
-            c.stake[n] = st;
-            c.stk[n] = st;
-            if (st != 0.0 && mypos < K) c.stl[mypos] = 0;
-        }
-        FSB_MARK(24);
-        // buy orders (:367-368), net demand, impact, shares (:229-239), holdings (:259); one asset per thread
-        for (int m = tid; m < M; m += NT) {
-            const double p = pc[m];
-            double net = 0.0;
-            for (int i0 = 0; i0 < ncash; i0 += 4) {  // holdings do not change in this loop: 4 rows in flight
-                const int n4 = min(4, ncash - i0);
-                double hq[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) hq[q] = c.H[static_cast<long long>(c.r_choice[q < n4 ? i0 + q : i0]) * Mp + m];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (q < n4) {
-                        const int i = i0 + q;
-                        const double v = qdiv(hq[q] * p, c.r_fval[i]) * c.r_inj[i];
-                        order_row(c, Mp, i)[m] = v;
-                        net = net + v;
-                    }
-                }
-            }
-            if (c.volume && !(flags & FSB_RUN_NO_VOLUME_QUIRK)) c.volume[static_cast<long long>(t - 1) * Mp + m] -= c.sellsum[m];  // :484 (Q3)
-            double v = (1.0 + net * c.impact[m]) * p;
-            int fl = 0;
-            if (v < kPriceFloor) { v = kPriceFloor; fl = 1; }
-            c.pick[m] = fl;
-            pc[m] = v;
-            for (int i0 = 0; i0 < ncash; i0 += 4) {
-                const int n4 = min(4, ncash - i0);
-                int fq[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) fq[q] = (q < n4) ? c.r_choice[i0 + q] : -1 - q;
-                const bool dup = (fq[1] == fq[0]) || (fq[2] == fq[0]) || (fq[2] == fq[1]) || (fq[3] == fq[0]) || (fq[3] == fq[1]) || (fq[3] == fq[2]);
-                double hq[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) hq[q] = c.H[static_cast<long long>(fq[q] >= 0 ? fq[q] : fq[0]) * Mp + m];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (q < n4) {
-                        const int i = i0 + q;
-                        double *hpn = c.H + static_cast<long long>(fq[q]) * Mp + m;
-                        const double hn = (dup ? *hpn : hq[q]) + qdiv(order_row(c, Mp, i)[m], v);
-                        *hpn = hn;
-                        if (hn != 0.0) c.nzf[i] = 1;
-                    }
-                }
-            }
-        }
-        FSB_MARK(25);
-        __syncthreads();  // B14
-        FSB_MARK(14);
-        // funds that received shares are revalued at the final prices (disburse! -> fundrevalue!)
-        for (int ib = c.warp * 4; ib < ncash; ib += c.nwarps * 4) {
-            const int i = ib + g4;
-            bool on = i < ncash;
-            const int f = c.r_choice[on ? i : ib];
-            if (on)
-                for (int q = i + 1; q < ncash; ++q) on = on && (c.r_choice[q] != f);
-            const double v = dot8(c.H + static_cast<long long>(f) * Mp, pc, M, j8, on);
-            if (on && j8 == 0) c.nav_close[f] = v;
-        }
-        for (int i = tid; i < ncash; i += NT) {
-            const int f = c.r_choice[i];
-            bool last = true;
-            for (int q = i + 1; q < ncash; ++q) last = last && (c.r_choice[q] != f);
-            if (last) {
-                c.hzero[f] = c.nzf[i] ? 0 : 1;
-                c.stakeless[f] = c.stl[f];
-            }
-        }
-        floor_account(s, c, t, 2);
+        mbar_wait(c.mbar, phase);
     }
+    __syncthreads();  // B8 (pads; also orders the previous chunk's readers before this chunk's results)
+    if (nc > 0 && tid == 0) c.mbar_phase ^= 1u;  // (every thread has read the phase before the barrier)
+    FSB_MARK(9);
+}
+
+// T6: fund choice of the cash holders whose horizon is in the chunk [c0, c0 + nc) (:344-353, 381-415)
+__device__ FSB_FP_INLINE void phase_choice(const int t, const int c0, const int nc, const int ncash, const int selector)
+{
+    Ctx &c = ctx();
+    FSB_TH;
+    const int K = c.K;
+    if (selector == FSB_SEL_PROBABILISTIC) {
+        // rank rule: p_k = rank_k / (K(K+1)/2) per column, into the (now free) staged column
+#pragma unroll 1
+        for (int jc = warp; jc < nc; jc += nwarps) {
+            const unsigned long long *keys = c.keys + static_cast<long long>(jc) * c.kq;
+            double *prob_k = c.cols_() + (2 + jc) * c.cpk;
+            if (c.rank256) warp_rank256(keys, K, prob_k, c.ranktab);
+            else warp_rank_count(keys, K, prob_k, c.ranktab);
+            __syncwarp();
+            FSB_MARK(23);
+            // the same warp samples the choice of every cash holder whose horizon is this column
+            for (int i = lane; i < ncash; i += 32) {
+                if (c.r_col_()[i] != c0 + jc) continue;
+                c.r_choice_()[i] = select_fund_prob(c, t, c.cash_()[i], prob_k);
+            }
+        }
+        FSB_MARK(11);
+    } else {
+#pragma unroll 1
+        for (int i = warp; i < ncash; i += nwarps) {
+            const int col = c.r_col_()[i];
+            if (col < c0 || col >= c0 + nc) continue;
+            const int choice = select_fund_warp(t, c.cash_()[i], c.keys + static_cast<long long>(col - c0) * c.kq, selector);
+            if (lane == 0) c.r_choice_()[i] = choice;
+        }
+    }
+    __syncthreads();
+    FSB_MARK(12);
+}
+
+// ------------------------------------------------------------------------------------------------
+// T7-T9: reinvest! (:335-373): stake dilution (Q7), buy orders, executeorder!(Buy), disburse! shares
+// ------------------------------------------------------------------------------------------------
+__device__ FSB_FP_INLINE void phase_reinvest(const int t, const int ncash, const int flags)
+{
+    Ctx &c = ctx();
+    FSB_TH;
+    const int K = c.K, M = c.M, N = c.N, Mp = c.Mp, cap = c.cap;
+    const int j8 = lane & 7, g4 = lane >> 3;
+    double *const pc = p_cur(c);
+    for (int i = tid; i < ncash; i += NT) {
+        const int ch = c.r_choice_()[i];
+        const double inj = c.amount[c.cash_()[i]];
+        const double fv = c.nav_()[ch];  // == holdings[choice,:]' * stockvals[:,t], :360
+        c.r_inj_()[i] = inj;
+        c.r_fval_()[i] = fv;
+        c.r_ncap_()[i] = fv + inj;
+        c.stl_()[ch] = 1;  // cleared below by every member whose diluted stake is non-zero
+        atomicOr(reinterpret_cast<unsigned *>(&c.fsel_()[ch >> 5]), 1u << (ch & 31));
+    }
+    for (int o = tid; o < cap; o += NT) c.nzf_()[o] = 0;
+    __syncthreads();  // B13
+    FSB_MARK(13);
+    if (tid == 0) c.cnt[CNT_REINVEST] += ncash;
+    if (c.trace >= 0) trace_phase(t, 4, ncash, 0);
+    // stakes (:363-366), sequential over reinvestors per investor (Q7), parallel over investors
+#pragma unroll 1
+    for (int n = tid; n < N; n += NT) {
+        int mypos = c.pos16_()[n];
+        // only cash holders and members of a chosen fund can be touched
+        if (mypos != K && !((c.fsel_()[mypos >> 5] >> (mypos & 31)) & 1)) continue;
+        bool touched = false;
+        for (int i = 0; i < ncash; ++i) {
+            const int ch = c.r_choice_()[i];
+            if (c.cash_()[i] == n) { mypos = ch; touched = true; }
+            else if (mypos == ch) touched = true;
+        }
+        if (!touched) continue;
+        mypos = c.pos16_()[n];
+        double st = c.stake[n];
+        for (int i = 0; i < ncash; ++i) {
+            const int ch = c.r_choice_()[i];
+            if (c.cash_()[i] == n) {
+                mypos = ch;
+                st = ddiv(c.r_inj_()[i], c.r_ncap_()[i]);
+            } else if (mypos == ch) {
+                st = qdiv(st * c.r_fval_()[i], c.r_ncap_()[i]);
+            }
+        }
+        c.pos[n] = mypos;
+        c.pos16_()[n] = static_cast<short>(mypos);
+        c.stake[n] = st;
+        if (st != 0.0 && mypos < K) c.stl_()[mypos] = 0;
+    }
+    FSB_MARK(24);
+    // buy orders (:367-368), net demand, impact, shares (:229-239), holdings (:259); one asset per thread
+#pragma unroll 1
+    for (int m = tid; m < M; m += NT) {
+        const double p = pc[m];
+        const double imp = c.impact[m];
+        double net = 0.0;
+#pragma unroll 1
+        for (int i0 = 0; i0 < ncash; i0 += 4) {  // holdings do not change in this loop: 4 rows in flight
+            const int n4 = min(4, ncash - i0);
+            double hq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hq[q] = c.H[static_cast<long long>(c.r_choice_()[q < n4 ? i0 + q : i0]) * Mp + m];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < n4) {
+                    const int i = i0 + q;
+                    const double v = qdiv(hq[q] * p, c.r_fval_()[i]) * c.r_inj_()[i];
+                    order_row(c, i)[m] = v;
+                    net = net + v;
+                }
+            }
+        }
+        if (c.volume && !(flags & FSB_RUN_NO_VOLUME_QUIRK)) c.volume[static_cast<long long>(t - 1) * Mp + m] -= c.sellsum_()[m];  // :484 (Q3)
+        double v = (1.0 + net * imp) * p;
+        int fl = 0;
+        if (v < kPriceFloor) { v = kPriceFloor; fl = 1; }
+        c.pick_()[m] = fl;
+        pc[m] = v;
+#pragma unroll 1
+        for (int i0 = 0; i0 < ncash; i0 += 4) {
+            const int n4 = min(4, ncash - i0);
+            int fq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) fq[q] = (q < n4) ? c.r_choice_()[i0 + q] : -1 - q;
+            const bool dup = (fq[1] == fq[0]) || (fq[2] == fq[0]) || (fq[2] == fq[1]) || (fq[3] == fq[0]) || (fq[3] == fq[1]) || (fq[3] == fq[2]);
+            double hq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hq[q] = c.H[static_cast<long long>(fq[q] >= 0 ? fq[q] : fq[0]) * Mp + m];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < n4) {
+                    const int i = i0 + q;
+                    double *hpn = c.H + static_cast<long long>(fq[q]) * Mp + m;
+                    const double hn = (dup ? *hpn : hq[q]) + qdiv(order_row(c, i)[m], v);
+                    *hpn = hn;
+                    if (hn != 0.0) c.nzf_()[i] = 1;
+                }
+            }
+        }
+    }
+    FSB_MARK(25);
+    __syncthreads();  // B14
+    FSB_MARK(14);
+    // funds that received shares are revalued at the final prices (disburse! -> fundrevalue!)
+#pragma unroll 1
+    for (int ib = warp * 4; ib < ncash; ib += nwarps * 4) {
+        const int i = ib + g4;
+        bool on = i < ncash;
+        const int f = c.r_choice_()[on ? i : ib];
+        if (on)
+            for (int q = i + 1; q < ncash; ++q) on = on && (c.r_choice_()[q] != f);
+        const double v = dot8(c.H + static_cast<long long>(f) * Mp, pc, M, j8, on);
+        if (on && j8 == 0) c.nav_close[f] = v;
+    }
+    for (int i = tid; i < ncash; i += NT) {
+        const int f = c.r_choice_()[i];
+        bool last = true;
+        for (int q = i + 1; q < ncash; ++q) last = last && (c.r_choice_()[q] != f);
+        if (last) {
+            c.hzero[f] = c.nzf_()[i] ? 0 : 1;
+            c.stakeless[f] = c.stl_()[f];
+        }
+    }
+    floor_account(t, 2);
+}
+
+// the day's closing prices into the history; ends the step
+__device__ FSB_FP_INLINE void phase_store_prices(const int t)
+{
+    Ctx &c = ctx();
+    FSB_TH;
+    const int half = c.Mp >> 1;
+    double *Pt = c.P + static_cast<long long>(pcol(c, t)) * c.Mp;
+    const double *pc = p_cur(c);
     for (int m2 = tid; m2 < half; m2 += NT) reinterpret_cast<double2 *>(Pt)[m2] = reinterpret_cast<const double2 *>(pc)[m2];
     __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// one time step of one replication
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void step_replication(Ctx &c, const int t, const int selector, const int flags)
+{
+    const bool traced = (c.trace >= 0);
+    phase_shocks(t);
+    const int nd = phase_review(t);
+    if (nd < 0) {
+        if (threadIdx.x == 0) atomicOr(c.err, FSB_REP_EVENT_OVERFLOW);
+        return;
+    }
+    if (traced) trace_phase(t, 0, c.isc_()[I_NREV], nd);  // (only thread 0 reads I_NREV, which it wrote itself)
+    if (nd == 0) {  // :464 -- nothing else happens this step: nav_open = nav_close = H * p_open
+        if (c.fast) full_pass<1, true, true>(0, 1, 0);
+        else full_pass<1, true, false>(0, 1, 0);
+        if (threadIdx.x == 0) c.flow_hist[0] += 1;
+        phase_store_prices(t);
+        FSB_MARK(3);
+        if (traced) trace_phase(t, 3, 0, 0);
+        return;
+    }
+    const int any_dead = phase_liquidate(t, nd);
+    if (traced) trace_phase(t, 1, nd, 0);
+    if (any_dead && phase_respawn(t, nd, flags)) return;
+    if (traced) trace_phase(t, 2, 0, 0);
+    FSB_MARK(7);
+    const int ncash = phase_cashlist(nd);
+    if (ncash < 0) {
+        if (threadIdx.x == 0) atomicOr(c.err, FSB_REP_EVENT_OVERFLOW);
+        return;
+    }
+    const int ncols = c.isc_()[I_NCOLS];
+    const int cmax = c.cmax;
+    const int want_keys = (selector == FSB_SEL_PROBABILISTIC) ? 1 : 0;
+    // fundrevalue!(1:K) at :460 and :479 + horizon returns of reinvest! (:335-379)
+    // first chunk: the two price columns + up to cmax horizons; later chunks: up to cmax - 2 horizons
+#pragma unroll 1
+    for (int c0 = 0; c0 == 0 || c0 < ncols; c0 += (c0 == 0 ? cmax : cmax - 2)) {
+        const int nc = min(c0 == 0 ? cmax : cmax - 2, ncols - c0);
+        phase_stage_columns(t, c0, nc);
+        full_pass_dispatch(c, c0 == 0 ? 0 : 2, c0 == 0 ? 2 + nc : nc, want_keys);
+        __syncthreads();  // B9: keys[] holds the horizon returns (or their sort keys) of this chunk
+        FSB_MARK(10);
+        if (nc > 0) phase_choice(t, c0, nc, ncash, selector);
+    }
+    if (traced) trace_phase(t, 3, 0, 0);
+    if (c.isc_()[I_ERR]) {
+        if (threadIdx.x == 0) atomicOr(c.err, c.isc_()[I_ERR]);
+        return;
+    }
+    if (ncash > 0) phase_reinvest(t, ncash, flags);
+    phase_store_prices(t);
     FSB_MARK(15);
 }
 
 // ------------------------------------------------------------------------------------------------
 // kernel: persistent CTAs pull replications from a work counter
 // ------------------------------------------------------------------------------------------------
-template <bool FAST>
-__global__ void __launch_bounds__(256, 2) fsb_step_kernel(const DevState s, const StepArgs a, const int launch_parity)
+__global__ void __launch_bounds__(kStepThreads, 4) fsb_step_kernel(const DevState s, const StepArgs a, const int launch_parity)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(sizeof(Ctx) <= kCtxBytes, "Ctx outgrew its shared-memory slot");
+    Ctx &c = ctx();
     __shared__ long long r_sh;
     __shared__ __align__(8) unsigned long long mbar_sh;
     const int nwarps = blockDim.x >> 5;
     const SmemLayout L = make_layout(s.K, s.Mp, s.N, s.cap_ev, s.cmax, nwarps);
-    double *sd = reinterpret_cast<double *>(smem_raw);
-    int *si = reinterpret_cast<int *>(sd + L.ndoubles);
-    unsigned short *sh = reinterpret_cast<unsigned short *>(si + L.nints);
-    Ctx c;
-    c.cols = sd + L.off_cols; c.vh = sd + L.off_vh; c.ratio = sd + L.off_ratio; c.sellsum = sd + L.off_sellsum;
-    c.nav = sd + L.off_nav; c.stk = sd + L.off_stk; c.d_stake = sd + L.off_dstake; c.d_cash = sd + L.off_dcash;
-    c.r_inj = sd + L.off_rinj; c.r_fval = sd + L.off_rfval; c.r_ncap = sd + L.off_rncap; c.scal = sd + L.off_scal;
-    c.rev = si + L.off_rev; c.rfund = si + L.off_rfund; c.d_inv = si + L.off_dinv; c.d_fund = si + L.off_dfund;
-    c.cash = si + L.off_cash; c.r_choice = si + L.off_rchoice; c.r_col = si + L.off_rcol; c.hcols = si + L.off_hcols;
-    c.eggs = si + L.off_eggs; c.wl = si + L.off_wl; c.wcnt = si + L.off_wcnt; c.flags = si + L.off_flags;
-    c.nzf = si + L.off_nzf; c.pick = si + L.off_pick; c.fmod = si + L.off_fmod; c.fsel = si + L.off_fsel; c.isc = si + L.off_isc;
-    c.pos16 = reinterpret_cast<short *>(sh + L.off_pos16); c.hor16 = sh + L.off_hor16; c.sidx = sh + L.off_sidx;
-    c.stl = reinterpret_cast<unsigned char *>(sh + L.nshorts);
-    c.cp = L.cp; c.cpk = L.cpk; c.kq = L.kq; c.kp2 = L.kp2; c.srows = L.srows; c.wsd = L.wsd;
-    c.mbar = &mbar_sh; c.mbar_phase = 0;
-    c.tmark = clock64();
-    c.tid = threadIdx.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5; c.nwarps = nwarps; c.nthreads = blockDim.x;
-    c.scratch = s.scratch + static_cast<long long>(blockIdx.x) * s.cap_ev * s.Mp;
-    c.rng.k0 = static_cast<uint32_t>(s.seed); c.rng.k1 = static_cast<uint32_t>(s.seed >> 32);
-    if (threadIdx.x == 0) mbar_init(&mbar_sh, 1);
+    double *sd = reinterpret_cast<double *>(fsb_smem + kCtxBytes);
+    if (threadIdx.x == 0) {
+        c.K = s.K; c.M = s.M; c.N = s.N; c.Mp = s.Mp; c.T = s.T; c.W = s.W; c.cap = s.cap_ev; c.cmax = s.cmax;
+        c.keep_history = s.keep_history; c.cap_log = s.cap_log; c.cap_trace = s.cap_trace;
+        c.cp = L.cp; c.cpk = L.cpk; c.kq = L.kq; c.srows = L.srows; c.wsd = L.wsd;
+        c.rank256 = (s.K <= 256) ? 1 : 0;  // the in-register rank sort holds 256 keys
+        c.fast = (s.K <= 256 && s.Mp == 256) ? 1 : 0;
+        const int bd = kCtxBytes, bi = bd + 8 * L.ndoubles, bs = bi + 4 * L.nints;  // byte offsets of the double / int / 16-bit regions
+        c.o_cols = bd + 8 * L.off_cols; c.o_ratio = bd + 8 * L.off_ratio; c.o_sellsum = bd + 8 * L.off_sellsum;
+        c.o_nav = bd + 8 * L.off_nav; c.o_d_stake = bd + 8 * L.off_dstake; c.o_d_cash = bd + 8 * L.off_dcash;
+        c.o_r_inj = bd + 8 * L.off_rinj; c.o_r_fval = bd + 8 * L.off_rfval; c.o_r_ncap = bd + 8 * L.off_rncap; c.o_scal = bd + 8 * L.off_scal;
+        c.o_rev = bi + 4 * L.off_rev; c.o_rfund = bi + 4 * L.off_rfund; c.o_d_inv = bi + 4 * L.off_dinv; c.o_d_fund = bi + 4 * L.off_dfund;
+        c.o_cash = bi + 4 * L.off_cash; c.o_r_choice = bi + 4 * L.off_rchoice; c.o_r_col = bi + 4 * L.off_rcol; c.o_hcols = bi + 4 * L.off_hcols;
+        c.o_eggs = bi + 4 * L.off_eggs; c.o_wl = bi + 4 * L.off_wl; c.o_wcnt = bi + 4 * L.off_wcnt; c.o_flags = bi + 4 * L.off_flags;
+        c.o_nzf = bi + 4 * L.off_nzf; c.o_pick = bi + 4 * L.off_pick; c.o_fmod = bi + 4 * L.off_fmod; c.o_fsel = bi + 4 * L.off_fsel; c.o_isc = bi + 4 * L.off_isc;
+        c.o_pos16 = bs + 2 * L.off_pos16; c.o_hor16 = bs + 2 * L.off_hor16;
+        c.o_stl = bs + 2 * L.nshorts;
+        c.o_hz = c.o_stl + ((s.K + 15) & ~15);
+        c.mbar = &mbar_sh; c.mbar_phase = 0;
+        c.tmark = clock64();
+        c.scratch = s.scratch + static_cast<long long>(blockIdx.x) * s.cap_ev * s.Mp;
+        c.keys = s.keys + static_cast<long long>(blockIdx.x) * s.cmax * L.kq;
+        c.ranktab = s.ranktab;
+        c.rng.k0 = static_cast<uint32_t>(s.seed); c.rng.k1 = static_cast<uint32_t>(s.seed >> 32);
+        mbar_init(&mbar_sh, 1);
+    }
     for (int q = threadIdx.x; q < L.ndoubles; q += blockDim.x) sd[q] = 0.0;  // zero pads once
     __syncthreads();
 
@@ -1516,37 +1755,54 @@ __global__ void __launch_bounds__(256, 2) fsb_step_kernel(const DevState s, cons
         if (threadIdx.x == 0) r_sh = atomicAdd(&s.queue[launch_parity], 1);
         __syncthreads();
         const long long r = r_sh;
-        __syncthreads();
         if (r >= s.R) break;
-        if (s.err[r] & ~FSB_REP_TRACE_OVERFLOW) continue;  // frozen replication (uniform)
-        const long long g = s.rep_offset + r;
-        c.r = r;
-        c.rng.rep = static_cast<uint32_t>(g);
-        c.pt = s.points + (s.reps_per_point > 0 ? static_cast<int>(g / s.reps_per_point) : 0);
-        c.H = s.H + r * s.h_stride;
-        c.P = s.P + r * s.p_stride;
-        c.beta = s.beta + r * s.Mp; c.vol = s.vol + r * s.Mp; c.impact = s.impact + r * s.Mp;
-        c.volume = s.volume ? s.volume + r * static_cast<long long>(s.T) * s.Mp : nullptr;
-        c.market = s.market + r * s.mkt_len;
-        c.pos = s.pos + r * s.N; c.horizon = s.horizon + r * s.N;
-        c.stake = s.stake + r * s.N; c.amount = s.amount + r * s.N; c.threshold = s.threshold + r * s.N;
-        c.nav_open = s.nav_open + r * s.K; c.nav_close = s.nav_close + r * s.K;
-        c.hzero = s.hzero + r * s.K; c.stakeless = s.stakeless + r * s.K; c.live_row = s.live_row + r * s.K;
-        c.cnt = s.cnt + r * kCnt;
-        c.z_mkt = s.any_tape ? s.z_mkt[r] : nullptr;
-        c.z_stock = s.any_tape ? s.z_stock[r] : nullptr;
-        c.u_review = s.any_tape ? s.u_review[r] : nullptr;
-        c.tape = s.any_tape ? s.ev_tape[r] : nullptr;
-        c.n_tape = s.any_tape ? s.ev_n[r] : 0;
-        c.tape_toff = 0;
-        if (s.step_tape) {  // this step's shocks for the whole batch, fed from host buffers
-            c.z_mkt = s.st_zmkt + r; c.z_stock = s.st_zstock + r * s.M; c.u_review = s.st_urev + r * s.N;
-            c.tape_toff = a.t_first - 1;
+        const int frozen = s.err[r] & ~FSB_REP_TRACE_OVERFLOW;
+        if (threadIdx.x == 0 && !frozen) {
+            const long long g = s.rep_offset + r;
+            const DevPoint &pt = s.points[s.reps_per_point > 0 ? static_cast<int>(g / s.reps_per_point) : 0];
+            c.r = r;
+            c.rng.rep = static_cast<uint32_t>(g);
+            c.drift = pt.drift; c.marketvol = pt.marketvol; c.reviewprob = pt.reviewprob;
+            c.psize_lo = pt.psize_lo; c.psize_hi = pt.psize_hi;
+            c.H = s.H + r * s.h_stride;
+            c.P = s.P + r * s.p_stride;
+            c.beta = s.beta + r * s.Mp; c.vol = s.vol + r * s.Mp; c.impact = s.impact + r * s.Mp;
+            c.volume = s.volume ? s.volume + r * static_cast<long long>(s.T) * s.Mp : nullptr;
+            c.market = s.market + r * s.mkt_len;
+            c.pos = s.pos + r * s.N; c.horizon = s.horizon + r * s.N;
+            c.stake = s.stake + r * s.N; c.amount = s.amount + r * s.N; c.threshold = s.threshold + r * s.N;
+            c.nav_open = s.nav_open + r * s.K; c.nav_close = s.nav_close + r * s.K;
+            c.hzero = s.hzero + r * s.K; c.stakeless = s.stakeless + r * s.K; c.live_row = s.live_row + r * s.K;
+            c.cnt = s.cnt + r * kCnt;
+            c.mkt_peak = s.mkt_peak + r; c.mkt_dd = s.mkt_dd + r;
+            c.flow_hist = s.flow_hist + r * kFlowBins; c.err = s.err + r;
+            const long long lb = r * s.cap_log;
+            c.log_n = s.log_n + r;
+            c.log_liquidated = s.log_liquidated + lb; c.log_replacedby = s.log_replacedby + lb;
+            c.log_failtime = s.log_failtime + lb; c.log_ninv = s.log_ninv + lb; c.log_nstocks = s.log_nstocks + lb;
+            c.log_size = s.log_size + lb; c.log_liquidity = s.log_liquidity + lb;
+            c.z_mkt = s.any_tape ? s.z_mkt[r] : nullptr;
+            c.z_stock = s.any_tape ? s.z_stock[r] : nullptr;
+            c.u_review = s.any_tape ? s.u_review[r] : nullptr;
+            c.tape = s.any_tape ? s.ev_tape[r] : nullptr;
+            c.n_tape = s.any_tape ? s.ev_n[r] : 0;
+            c.tape_toff = 0;
+            if (s.step_tape) {  // this step's shocks for the whole batch, fed from host buffers
+                c.z_mkt = s.st_zmkt + r; c.z_stock = s.st_zstock + r * s.M; c.u_review = s.st_urev + r * s.N;
+                c.tape_toff = a.t_first - 1;
+            }
+            c.trace = s.trace_slot ? s.trace_slot[r] : -1;
+            if (c.trace >= 0) {
+                const long long sl = c.trace;
+                c.tr_nav = s.tr_nav + sl * s.K * s.T; c.tr_psell = s.tr_psell + sl * s.M * s.T; c.tr_presp = s.tr_presp + sl * s.M * s.T;
+                c.tr_recs = s.tr_recs + sl * s.cap_trace; c.tr_n = s.tr_n + sl;
+            }
         }
-        c.trace = s.trace_slot ? s.trace_slot[r] : -1;
+        __syncthreads();  // context visible; also keeps r_sh stable until every thread has read it
+        if (frozen) continue;  // frozen replication (uniform)
         for (int q = 0; q < a.n_steps; ++q) {
             FSB_MARK(0);
-            step_replication<FAST>(s, c, a.t_first + q, a.selector, a.flags);
+            step_replication(c, a.t_first + q, a.selector, a.flags);
             __syncthreads();
             if (s.err[r] & ~FSB_REP_TRACE_OVERFLOW) break;  // written by this CTA's thread 0 before the sync
         }

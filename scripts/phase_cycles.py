@@ -10,15 +10,14 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from __graft_entry__ import load_package  # noqa: E402
 
-NAMES = {0: "queue/idle between steps", 1: "P0 shocks+maps+reviewer draw (to B1)", 2: "review pass (to B2)",
-         3: "no-divestment day: open pass + end", 4: "compaction + stake sequence (to B4)", 5: "sale orders + impact (to B5)",
-         6: "cash-outs + flow hist (to B6)", 7: "respawn block", 8: "cash list + horizons (to B7)",
-         9: "column staging wait (to B8)", 10: "full pass (to B9)", 11: "rank sort (to its barrier)",
-         12: "fund choice (to its barrier)", 13: "injections (to B13)", 14: "stakes + buy orders + impact (to B14)",
-         15: "final revalue + price store (to end)", 16: "  (4a) compaction + counters, warp 0",
-         17: "  (4b) column prefetch issue", 18: "  (4c) stake sequence, warp 0", 4: "  (4d) wait at B4",
-         19: "  (1a) prefetch + market + stock move", 20: "  (1b) maps + stakes to shared", 1: "  (1c) reviewer draw + wait at B1",
-         23: "  (11a) rank sort of warp 0 columns", 11: "  (11b) choice scans of warp 0", 24: "  (14a) stakes loop", 25: "  (14b) buy orders + impact", 14: "  (14c) wait at B14"}
+NAMES = {0: "queue/idle between steps", 19: "T0a prefetch + market + stock move", 20: "T0b maps + flags to shared",
+         1: "T0c reviewer draw + wait at B1", 2: "T1 review pass (to B2)", 16: "T1b compaction + counters",
+         3: "no-divestment day: open pass + end", 17: "T2a column prefetch issue", 18: "T2b stake sequence (own warp)",
+         4: "T2c wait at B4", 5: "T2d sale orders + impact (to B5)", 6: "T2e cash-outs + flow hist (to B6)",
+         7: "T3 respawn block", 8: "T4 cash list + horizons (to B7)", 9: "T4b column staging wait (to B8)",
+         10: "T5 full pass (to B9)", 23: "T6a rank sort of own columns", 11: "T6b choice scans",
+         12: "T6c wait for the other warps' choices", 13: "T7a injections (to B13)", 24: "T7b stakes loop",
+         25: "T8 buy orders + impact", 14: "T8b wait at B14", 15: "T9 final revalue + price store (to end)"}
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=8)
