@@ -89,7 +89,7 @@ struct fsb_engine {
     int64_t device_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int grid = 0, block = 256, smem_bytes = 0, init_smem = 0;
+    int grid[3] = {0, 0, 0}, block = 256, smem_bytes[3] = {0, 0, 0}, init_smem = 0;
     int launch_parity = 0;
     bool fast = false;
     bool log_built = false, state_set = false;
@@ -204,34 +204,48 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     d.cap_trace = cfg->trace_capacity > 0 ? cfg->trace_capacity : 1 << 20;
     e->block = cfg->block_threads > 0 ? ((cfg->block_threads + 31) / 32) * 32 : kStepThreads;
     if (e->block > kStepThreads) e->block = kStepThreads;
-    // shared memory: the largest horizon-column chunk (2, 6, 10 or 14 columns) that leaves room for the
-    // wanted number of CTAs per SM
-    int smem_max = 0, smem_sm = 0;
+    if (d.K >= 32768) { delete e; return fail(FSB_ERR_BAD_PARAMS, "bigk must be < 32768 (16-bit fund ids in shared memory)"); }
+    // shared memory of the three kernels of a step.  events-1 / events-2: the two price columns + a few
+    // order / probability rows (more rows spill to a global scratch); pass: the largest horizon-column
+    // chunk (2, 6, 10 or 14 columns) that leaves room for the wanted number of CTAs per SM
+    int smem_max = 0, smem_sm = 0, sms = 0;
     CU(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     CU(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
-    if (d.K >= 32768) { delete e; return fail(FSB_ERR_BAD_PARAMS, "bigk must be < 32768 (16-bit fund ids in shared memory)"); }
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    const int nw = e->block / 32;
     int want_ctas = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : 4;
     if (const char *ev = getenv("FSB_CTAS_PER_SM")) want_ctas = std::max(1, atoi(ev));
     const int budget = std::min(smem_max, smem_sm / want_ctas - 1024);
     d.cmax = kMaxCols;
+    d.pf_ahead = kPfAheadDefault;
+    if (const char *ev = getenv("FSB_PF_AHEAD")) d.pf_ahead = std::max(0, atoi(ev));
     if (const char *ev = getenv("FSB_CMAX")) d.cmax = std::min(kMaxCols, std::max(2, ((atoi(ev) + 2) / 4) * 4 - 2));
-    SmemLayout L = make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax, e->block / 32);
-    while (L.bytes + 64 > budget && d.cmax > 2) {
-        d.cmax -= 4;
-        L = make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax, e->block / 32);
-    }
-    if (L.bytes + 64 > smem_max) { delete e; return fail(FSB_ERR_BAD_PARAMS, "shapes need %d bytes of shared memory per CTA (> %d)", L.bytes, smem_max); }
-    e->smem_bytes = L.bytes;
+    while (make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax + 2, nw).bytes + 64 > budget && d.cmax > 2) d.cmax -= 4;
+    d.slots_a = 2 + 6;
+    d.slots_c = 2 + std::max(nw, 6);
+    if (const char *ev = getenv("FSB_EVENT_ROWS")) { d.slots_a = 2 + std::max(1, atoi(ev)); d.slots_c = 2 + std::max(nw, atoi(ev)); }
+    while (make_layout(d.K, d.Mp, d.N, d.cap_ev, d.slots_a, nw).bytes + 64 > smem_max && d.slots_a > 3) --d.slots_a;
+    while (make_layout(d.K, d.Mp, d.N, d.cap_ev, d.slots_c, nw).bytes + 64 > smem_max && d.slots_c > 2 + nw) --d.slots_c;
+    d.kc = std::min(d.W, std::max(32, 2 * kMaxCols));
+    d.hi_stride = hand_ints(d.K, d.cap_ev);
     e->init_smem = (d.W + 2 + d.K) * 8;
-    e->fast = (d.K <= 256);
-    CU(cudaFuncSetAttribute(fsb_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_bytes));
     if (e->init_smem > 48 * 1024) CU(cudaFuncSetAttribute(fsb_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->init_smem));
-    int sms = 0, occ = 0;
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fsb_step_kernel, e->block, e->smem_bytes));
-    if (occ < 1) { delete e; return fail(FSB_ERR_CUDA, "step kernel cannot be resident (smem %d)", e->smem_bytes); }
-    if (cfg->blocks_per_sm > 0) occ = std::min(occ, cfg->blocks_per_sm);
-    e->grid = static_cast<int>(std::min<long long>(d.R, static_cast<long long>(sms) * occ));
+    {
+        const int slots[3] = {d.slots_a, d.cmax + 2, d.slots_c};
+        const void *kern[3] = {(const void *)fsb_events1_kernel, (const void *)fsb_pass_kernel, (const void *)fsb_events2_kernel};
+        for (int k = 0; k < 3; ++k) {
+            const SmemLayout L = make_layout(d.K, d.Mp, d.N, d.cap_ev, slots[k], nw);
+            if (L.bytes + 64 > smem_max) { delete e; return fail(FSB_ERR_BAD_PARAMS, "shapes need %d bytes of shared memory per CTA (> %d)", L.bytes, smem_max); }
+            e->smem_bytes[k] = L.bytes;
+            CU(cudaFuncSetAttribute(kern[k], cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
+            int occ = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern[k], e->block, L.bytes));
+            if (occ < 1) { delete e; return fail(FSB_ERR_CUDA, "step kernel %d cannot be resident (smem %d)", k, L.bytes); }
+            if (cfg->blocks_per_sm > 0) occ = std::min(occ, cfg->blocks_per_sm);
+            e->grid[k] = static_cast<int>(std::min<long long>(d.R, static_cast<long long>(sms) * occ));
+        }
+    }
+    e->fast = (d.K <= 256);
 
     // points + tables
     std::vector<double> tables;
@@ -270,9 +284,12 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     A(err, R); A(cnt, R * kCnt);
     A(mkt_peak, R); A(mkt_dd, R);
     A(flow_hist, R * kFlowBins);
-    A(scratch, static_cast<size_t>(e->grid) * d.cap_ev * d.Mp);
-    A(keys, static_cast<size_t>(e->grid) * d.cmax * ((d.K + 3) & ~3));
-    A(queue, 2);
+    A(scratch, static_cast<size_t>(std::max(e->grid[0], std::max(e->grid[1], e->grid[2]))) * d.cap_ev * d.Mp);
+    A(keys, R * d.kc * ((d.K + 3) & ~3));
+    A(hand_i, R * d.hi_stride);
+    A(hand_p, R * d.Mp);
+    if (d.keep_history) A(hand_s, R * d.Mp);
+    A(queue, 6);
 #undef A
     {
         DevPoint *pd = nullptr; double *td = nullptr, *rt = nullptr;
@@ -553,13 +570,15 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
         ++e->last_launches;
     }
     if (t_last >= t_first) {
-        CU(cudaMemsetAsync(d.queue, 0, 2 * sizeof(int), e->stream));
-        const int spl = std::max(1, e->cfg.steps_per_launch);
-        for (int64_t t = t_first; t <= t_last; t += spl) {
-            StepArgs a{static_cast<int>(t), static_cast<int>(std::min<int64_t>(spl, t_last - t + 1)), selector, flags};
-            fsb_step_kernel<<<e->grid, e->block, e->smem_bytes, e->stream>>>(d, a, e->launch_parity);
+        CU(cudaMemsetAsync(d.queue, 0, 6 * sizeof(int), e->stream));
+        // one simulated day = three kernels on the engine's stream: events-1, holdings pass, events-2
+        for (int64_t t = t_first; t <= t_last; ++t) {
+            StepArgs a{static_cast<int>(t), 1, selector, flags};
+            fsb_events1_kernel<<<e->grid[0], e->block, e->smem_bytes[0], e->stream>>>(d, a, e->launch_parity);
+            fsb_pass_kernel<<<e->grid[1], e->block, e->smem_bytes[1], e->stream>>>(d, a, e->launch_parity);
+            fsb_events2_kernel<<<e->grid[2], e->block, e->smem_bytes[2], e->stream>>>(d, a, e->launch_parity);
             e->launch_parity ^= 1;
-            ++e->last_launches;
+            e->last_launches += 3;
         }
         CU(cudaGetLastError());
         e->t_done = t_last;

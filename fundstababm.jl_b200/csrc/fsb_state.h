@@ -25,6 +25,10 @@ struct DevState {
     int mkt_len;    // T (keep_history) or 2
     int keep_history;
     int cap_ev, cap_log, cap_trace, cmax;
+    int pf_ahead;   // holdings rounds prefetched into L2 ahead of the full pass's loads
+    int kc;         // key columns (distinct reinvestor horizons) a replication can have per step
+    int hi_stride;  // ints per replication in hand_i
+    int slots_a, slots_c;  // shared-memory column slots of the events-1 / events-2 kernels
     int n_points;
     long long R, rep_offset, reps_per_point;
     long long h_stride;  // doubles per replication in H
@@ -69,9 +73,13 @@ struct DevState {
     int *tr_n;                             // [slots]
     // per-CTA scratch + work queue
     double *scratch;  // [grid][cap_ev][Mp] order rows beyond the shared-memory ones
-    unsigned long long *keys;  // [grid][cmax][K4] horizon returns of the step being processed (per CTA, L2 resident)
+    unsigned long long *keys;  // [R][kc][K4] horizon returns of the step being processed (pass kernel -> events-2 kernel)
+    // handoff between the three kernels of a step (fsb_step.cuh)
+    int *hand_i;               // [R][hi_stride]
+    double *hand_p;            // [R][Mp] opening prices of the day
+    double *hand_s;            // [R][Mp] net sale per asset of the day (keep_history only, else null)
     const double *ranktab;     // [K] (i + 1) / (K (K + 1) / 2): rank probabilities of the rank rule (Q14)
-    int *queue;       // [2] dynamic work counters (double buffered across launches)
+    int *queue;       // [3][2] dynamic work counters per kernel kind (double buffered across launches)
     const DevPoint *points;
     const double *tables;
 };

@@ -33,7 +33,7 @@ namespace fsb {
 
 constexpr double kPriceFloor = 0.000000001;  // functions.jl:208-209 (Q10)
 constexpr int kMaxCols = 14;                 // horizon columns per full pass (4 groups x 4 columns, minus the 2 price columns)
-constexpr int kPfAhead = 2;                  // holdings rounds prefetched into L2 ahead of the loads
+constexpr int kPfAheadDefault = 2;           // holdings rounds prefetched into L2 ahead of the loads (DevState::pf_ahead)
 constexpr int kStepThreads = 128;
 #ifndef FSB_FP_INLINE
 #define FSB_FP_INLINE __forceinline__
@@ -61,7 +61,9 @@ struct SmemLayout {
     int bytes;
 };
 
-__host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap, int cmax, int nwarps)
+// nslots: column slots of `cols` (slot 0: opening prices, 1: current prices, 2..: staged history columns /
+// order rows / probability rows, depending on the kernel)
+__host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap, int nslots, int nwarps)
 {
     SmemLayout L;
     L.cp = (Mp + 127) & ~127;  // == Mp: the engine rounds Mp up to 128 itself
@@ -69,9 +71,9 @@ __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap,
     const int kp = (L.kq + 127) & ~127;
     L.cpk = L.cp > kp ? L.cp : kp;
     int d = 0;
-    L.off_cols = d; d += (cmax + 2) * L.cpk;   // col 0: opening prices, col 1: current prices, 2..: staged history
-    L.srows = (cmax * L.cpk) / L.cp;
-    L.wsd = ((cmax * L.cpk) / nwarps) & ~1;
+    L.off_cols = d; d += nslots * L.cpk;
+    L.srows = ((nslots - 2) * L.cpk) / L.cp;
+    L.wsd = (((nslots - 2) * L.cpk) / nwarps) & ~1;
     L.off_ratio = d; d += L.cp;
     L.off_sellsum = d; d += L.cp;
     L.off_nav = d; d += L.kq;
@@ -118,7 +120,7 @@ constexpr int kCtxBytes = 1024;
 // Phase functions receive a reference to it; thread-private ids are recomputed from threadIdx.
 struct Ctx {
     // shapes / configuration (copies of DevState fields)
-    int K, M, N, Mp, T, W, cap, cmax, keep_history, cap_log, cap_trace, fast, rank256;
+    int K, M, N, Mp, T, W, cap, cmax, keep_history, cap_log, cap_trace, fast, rank256, pf_ahead, kc;
     int cp, cpk, kq, srows, wsd;
     // shared arrays: byte offsets into the dynamic shared memory (accessors below keep the address space known)
     int o_cols, o_ratio, o_sellsum, o_nav, o_d_stake, o_d_cash, o_r_inj, o_r_fval, o_r_ncap, o_scal;
@@ -207,6 +209,44 @@ __device__ unsigned long long g_phase_cycles[32];
 // isc[] slots
 enum { I_ND = 0, I_NCASH, I_NEGGS, I_ERR, I_TMP0, I_TMP1, I_TMP2, I_NCOLS, I_IDLE, I_NREV, I_DEAD };
 
+// Global pointers of the replication a CTA is working on, rebuilt from the kernel parameters in every
+// inlined phase: pointers derived from kernel parameters are KNOWN to be global memory, so loads through
+// them neither alias the shared-memory stores in between (they can be hoisted and overlapped) nor need
+// generic addressing.  (The copies in Ctx serve the out-of-line cold paths.)
+struct Rep {
+    double *H, *P, *beta, *vol, *impact, *volume, *market, *stake, *amount, *threshold, *nav_open, *nav_close;
+    int *pos, *horizon, *cnt;
+    unsigned char *hzero, *stakeless;
+    double *mkt_peak, *mkt_dd;
+    int *flow_hist;
+    double *scratch;
+    unsigned long long *keys;
+    int *hand_i;
+    double *hand_p, *hand_s;
+};
+__device__ __forceinline__ Rep rep_ptrs(const DevState &s, const long long r, const int kq)
+{
+    Rep g;
+    g.H = s.H + r * s.h_stride;
+    g.P = s.P + r * s.p_stride;
+    g.beta = s.beta + r * s.Mp; g.vol = s.vol + r * s.Mp; g.impact = s.impact + r * s.Mp;
+    g.volume = s.volume ? s.volume + r * static_cast<long long>(s.T) * s.Mp : nullptr;
+    g.market = s.market + r * s.mkt_len;
+    g.pos = s.pos + r * s.N; g.horizon = s.horizon + r * s.N;
+    g.stake = s.stake + r * s.N; g.amount = s.amount + r * s.N; g.threshold = s.threshold + r * s.N;
+    g.nav_open = s.nav_open + r * s.K; g.nav_close = s.nav_close + r * s.K;
+    g.hzero = s.hzero + r * s.K; g.stakeless = s.stakeless + r * s.K;
+    g.cnt = s.cnt + r * kCnt;
+    g.mkt_peak = s.mkt_peak + r; g.mkt_dd = s.mkt_dd + r;
+    g.flow_hist = s.flow_hist + r * kFlowBins;
+    g.scratch = s.scratch + static_cast<long long>(blockIdx.x) * s.cap_ev * s.Mp;
+    g.keys = s.keys + r * (static_cast<long long>(s.kc) * kq);
+    g.hand_i = s.hand_i + r * s.hi_stride;
+    g.hand_p = s.hand_p + r * s.Mp;
+    g.hand_s = s.hand_s ? s.hand_s + r * s.Mp : nullptr;
+    return g;
+}
+
 __device__ __forceinline__ Ctx &ctx() { return *reinterpret_cast<Ctx *>(fsb_smem); }
 
 #define FSB_TH                                                                               \
@@ -223,9 +263,9 @@ __device__ __forceinline__ int mslot(const Ctx &c, int t) { return c.keep_histor
 __device__ __forceinline__ double *p_open(const Ctx &c) { return c.cols_(); }
 __device__ __forceinline__ double *p_cur(const Ctx &c) { return c.cols_() + c.cpk; }
 // order row o (sale / buy values per asset): shared memory while it fits, per-CTA global scratch beyond
-__device__ __forceinline__ double *order_row(const Ctx &c, int o)
+__device__ __forceinline__ double *order_row(const Ctx &c, double *scratch, int o)
 {
-    return (o < c.srows) ? c.cols_() + 2 * c.cpk + o * c.cp : c.scratch + static_cast<long long>(o - c.srows) * c.Mp;
+    return (o < c.srows) ? c.cols_() + 2 * c.cpk + o * c.cp : scratch + static_cast<long long>(o - c.srows) * c.Mp;
 }
 
 // ---- out-of-line building blocks (one copy each in the instruction stream) -------------------------
@@ -630,7 +670,7 @@ __device__ __forceinline__ int owned_sum(int j, int q)  // index of the sum in v
 // the same holdings words (one 128-byte request per row and step, served once), every group a different
 // column word: 8 FMAs per 128-bit shared-memory load.  The loop runs over the zero-padded pitch cp
 // (fma(0, 0, acc) == acc exactly).  Holdings are loaded four steps ahead of their use (register ring,
-// loop body = 4 steps so that the ring is indexed statically) and rounds are L2-prefetched kPfAhead
+// loop body = 4 steps so that the ring is indexed statically) and rounds are L2-prefetched pf_ahead
 // rounds ahead.
 // OPEN: only column 0 (a day without divestments): every group owns its own round of 4 rows instead.
 // Results: column 0 -> nav_open (unless the row was modified before this pass: its opening NAV was
@@ -638,9 +678,10 @@ __device__ __forceinline__ int owned_sum(int j, int q)  // index of the sum in v
 // (nav - vh) / vh (:375-379), stored as its order-preserving 64-bit key (rank rule) or as raw bits.
 // ------------------------------------------------------------------------------------------------
 template <int NCG, bool OPEN, bool FAST>
-__device__ FSB_FP_INLINE void full_pass(const int cb, const int nreal, const int want_keys)
+__device__ FSB_FP_INLINE void full_pass(const DevState &s, const int cb, const int nreal, const int want_keys, const int kcol0)
 {
     Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq);
     constexpr int R = 4;
     FSB_TH;
     const int K = c.K;
@@ -650,7 +691,7 @@ __device__ FSB_FP_INLINE void full_pass(const int cb, const int nreal, const int
     const int j = lane & 7, g = lane >> 3;
     const int nrounds = (K + R - 1) / R;  // rounds of 4 rows (rows K.. of the last one are zero padding)
     const double2 *colp = reinterpret_cast<const double2 *>(c.cols_()) + (OPEN ? 0 : (cb + g)) * cstride + j;
-    const double2 *H2 = reinterpret_cast<const double2 *>(c.H) + j;
+    const double2 *H2 = reinterpret_cast<const double2 *>(G.H) + j;
     // the unit a warp pulls per trip: OPEN: 4 rounds (one per group), else 1 round
     constexpr int upw = OPEN ? 4 : 1;
     const int ntrips = (nrounds + upw - 1) / upw;
@@ -658,6 +699,9 @@ __device__ FSB_FP_INLINE void full_pass(const int cb, const int nreal, const int
     auto rowptr = [&](int trip) {
         int rd = round_of(trip);
         if (rd >= nrounds) rd = nrounds - 1;  // (idle group of the last OPEN trip re-reads the last round)
+#ifdef FSB_EXPERIMENTS
+        if (c.pf_ahead == 99) rd = 0;  // timing experiment: L2-hot holdings (results are wrong)
+#endif
         return H2 + static_cast<long long>(rd) * R * half;
     };
     int trip = warp;
@@ -674,12 +718,29 @@ __device__ FSB_FP_INLINE void full_pass(const int cb, const int nreal, const int
     const long long rowbytes = static_cast<long long>(c.Mp) * 8;
 #pragma unroll 1
     for (; trip < ntrips; trip += nwarps) {
-        {   // L2 prefetch of the round(s) this warp reads kPfAhead trips from now
-            const int tp = trip + kPfAhead * nwarps;
-            if (lane == 0 && tp < ntrips) {
+        {   // L2 prefetch of the round(s) this warp reads pf_ahead trips from now
+            const int pfd = c.pf_ahead % 100, pfm = c.pf_ahead / 100;
+            const int tp = trip + pfd * nwarps;
+            if (pfd > 0 && tp < ntrips) {
                 const int r0 = upw * tp * R;
                 const int nr = min(upw * R, ((K + 3) & ~3) - r0);
-                l2_prefetch_bulk(reinterpret_cast<const char *>(c.H) + r0 * rowbytes, static_cast<unsigned>(nr * rowbytes));
+                const char *src = reinterpret_cast<const char *>(G.H) + r0 * rowbytes;
+                if (pfm == 0) {
+                    if (lane == 0) l2_prefetch_bulk(src, static_cast<unsigned>(nr * rowbytes));
+                } else if (pfm == 1) {  // one 128-byte line per lane and instruction
+                    for (long long off = lane * 128LL; off < nr * rowbytes; off += 32 * 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off));
+                } else if (pfm == 2) {  // touch loads: real loads whose result is never used (one sector per line)
+                    for (long long off = lane * 128LL; off < nr * rowbytes; off += 32 * 128) {
+                        unsigned dummy;
+                        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(dummy) : "l"(src + off));
+                    }
+                } else {                // touch loads covering every 32-byte sector
+                    for (long long off = lane * 32LL; off < nr * rowbytes; off += 32 * 32) {
+                        unsigned dummy;
+                        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(dummy) : "l"(src + off));
+                    }
+                }
             }
         }
         const int tn = (trip + nwarps < ntrips) ? trip + nwarps : trip;
@@ -717,7 +778,7 @@ __device__ FSB_FP_INLINE void full_pass(const int cb, const int nreal, const int
         for (int q = 0; q < NF; ++q) own[q] = owned_sum<R * NCG>(j, q);
         if (OPEN) {
             const int k = rd * R + own[0];
-            if (rd < nrounds && k < K && (j & 1) == 0) { c.nav_open[k] = acc[0]; c.nav_close[k] = acc[0]; }
+            if (rd < nrounds && k < K && (j & 1) == 0) { G.nav_open[k] = acc[0]; G.nav_close[k] = acc[0]; }
             continue;
         }
         // column 1 first: the day's NAV is the numerator of every horizon return of the row
@@ -728,10 +789,10 @@ __device__ FSB_FP_INLINE void full_pass(const int cb, const int nreal, const int
                 const bool mine = (R * NCG == 4 || (R * NCG == 12 && q == 1)) ? ((j & 1) == 0) : true;
                 if (mine && k < K) {
                     if (col == 0) {
-                        if (!((c.fmod_()[k >> 5] >> (k & 31)) & 1)) c.nav_open[k] = acc[q];
+                        if (!((c.fmod_()[k >> 5] >> (k & 31)) & 1)) G.nav_open[k] = acc[q];
                     } else if (col == 1) {
                         c.nav_()[k] = acc[q];
-                        c.nav_close[k] = acc[q];
+                        G.nav_close[k] = acc[q];
                     }
                 }
             }
@@ -745,7 +806,7 @@ __device__ FSB_FP_INLINE void full_pass(const int cb, const int nreal, const int
                 const double navk = keep_nav[k], v = acc[q];
                 const double rho = ddiv(navk - v, v);
                 const unsigned long long word = want_keys ? sort_key(rho) : static_cast<unsigned long long>(__double_as_longlong(rho));
-                if (mine) __stcg(c.keys + static_cast<long long>(col - 2) * c.kq + k, word);
+                if (mine) __stcg(G.keys + static_cast<long long>(kcol0 + col - 2) * c.kq + k, word);
             }
         }
     }
@@ -754,19 +815,19 @@ __device__ FSB_FP_INLINE void full_pass(const int cb, const int nreal, const int
 // nc columns starting at cb are processed by the instantiation with ceil(nc / 4) columns per group
 // (spare columns of finite stale data are multiplied and dropped: cols[] always holds cmax + 2 columns).
 // c.fast: Mp == 256 and K <= 256 (the default shape): strides and trip counts are compile-time constants.
-__device__ __forceinline__ void full_pass_dispatch(Ctx &c, int cb, int nc, int want_keys)
+__device__ __forceinline__ void full_pass_dispatch(const DevState &s, Ctx &c, int cb, int nc, int want_keys, int kcol0)
 {
     const int ncg = (nc + 3) >> 2;
     if (c.fast) {
-        if (ncg <= 1) full_pass<1, false, true>(cb, nc, want_keys);
-        else if (ncg == 2) full_pass<2, false, true>(cb, nc, want_keys);
-        else if (ncg == 3) full_pass<3, false, true>(cb, nc, want_keys);
-        else full_pass<4, false, true>(cb, nc, want_keys);
+        if (ncg <= 1) full_pass<1, false, true>(s, cb, nc, want_keys, kcol0);
+        else if (ncg == 2) full_pass<2, false, true>(s, cb, nc, want_keys, kcol0);
+        else if (ncg == 3) full_pass<3, false, true>(s, cb, nc, want_keys, kcol0);
+        else full_pass<4, false, true>(s, cb, nc, want_keys, kcol0);
     } else {
-        if (ncg <= 1) full_pass<1, false, false>(cb, nc, want_keys);
-        else if (ncg == 2) full_pass<2, false, false>(cb, nc, want_keys);
-        else if (ncg == 3) full_pass<3, false, false>(cb, nc, want_keys);
-        else full_pass<4, false, false>(cb, nc, want_keys);
+        if (ncg <= 1) full_pass<1, false, false>(s, cb, nc, want_keys, kcol0);
+        else if (ncg == 2) full_pass<2, false, false>(s, cb, nc, want_keys, kcol0);
+        else if (ncg == 3) full_pass<3, false, false>(s, cb, nc, want_keys, kcol0);
+        else full_pass<4, false, false>(s, cb, nc, want_keys, kcol0);
     }
 }
 
@@ -785,23 +846,16 @@ __device__ __forceinline__ int chunk_list_get(const Ctx &c, int nwarps, int i)
 // ------------------------------------------------------------------------------------------------
 // T0: marketmove! (:13-17), stockmove! (:29-34), investor maps, drawreviewers (:147-151); ends with B1
 // ------------------------------------------------------------------------------------------------
-__device__ FSB_FP_INLINE void phase_shocks(const int t)
+__device__ FSB_FP_INLINE void phase_shocks(const DevState &s, const int t)
 {
     Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq);
     FSB_TH;
     const int K = c.K, M = c.M, N = c.N, Mp = c.Mp, cap = c.cap, hp = c.cp >> 1;
-    const double *Pprev = c.P + static_cast<long long>(pcol(c, t - 1)) * Mp;
+    const double *Pprev = G.P + static_cast<long long>(pcol(c, t - 1)) * Mp;
     double *const po = p_open(c), *const pc = p_cur(c);
-    // L2 prefetch of what the step certainly reads: the first rounds of holdings rows (consumed by the
-    // full pass) and the stakes (gathered by the stake sequence and the dilution)
-    if (lane == 0) {
-        const int kq = (K + 3) & ~3;
-        for (int q = 0; q < kPfAhead; ++q) {
-            const int r0 = 4 * (warp + q * nwarps);
-            if (r0 < kq) l2_prefetch_bulk(c.H + static_cast<long long>(r0) * Mp, static_cast<unsigned>(min(4, kq - r0) * Mp * 8));
-        }
-        if (warp == 0 && (N & 1) == 0) l2_prefetch_bulk(c.stake, static_cast<unsigned>(N * 8));
-    }
+    // L2 prefetch of the stakes (gathered by the stake sequence)
+    if (tid == 0 && (N & 1) == 0) l2_prefetch_bulk(G.stake, static_cast<unsigned>(N * 8));
     // marketmove!: every thread evaluates the same draw (no barrier)
     double mret;
     {
@@ -811,16 +865,16 @@ __device__ FSB_FP_INLINE void phase_shocks(const int t)
             const uint4 w = draw_block_s(c.rng, SITE_MKT, static_cast<uint32_t>(t), 0, 0);
             z = det_norminv(u52(w.x, w.y));
         }
-        const double mprev = c.market[mslot(c, t - 1)];
+        const double mprev = G.market[mslot(c, t - 1)];
         const double g = (1.0 + c.drift) + c.marketvol * z;
         const double mnew = mprev * g;
         mret = ddiv(mnew - mprev, mprev);
         if (tid == 0) {
-            c.market[mslot(c, t)] = mnew;
-            double peak = *c.mkt_peak;
-            if (mnew > peak) { peak = mnew; *c.mkt_peak = peak; }
+            G.market[mslot(c, t)] = mnew;
+            double peak = *G.mkt_peak;
+            if (mnew > peak) { peak = mnew; *G.mkt_peak = peak; }
             const double dd = ddiv(peak - mnew, peak);
-            if (dd > *c.mkt_dd) *c.mkt_dd = dd;
+            if (dd > *G.mkt_dd) *G.mkt_dd = dd;
         }
     }
     // stockmove!, two assets per thread (one Philox block = two uniforms)
@@ -830,8 +884,8 @@ __device__ FSB_FP_INLINE void phase_shocks(const int t)
         const int m = 2 * m2;
         if (m < M) {
             const double2 prev = reinterpret_cast<const double2 *>(Pprev)[m2];
-            const double2 be = reinterpret_cast<const double2 *>(c.beta)[m2];
-            const double2 vo = reinterpret_cast<const double2 *>(c.vol)[m2];
+            const double2 be = reinterpret_cast<const double2 *>(G.beta)[m2];
+            const double2 vo = reinterpret_cast<const double2 *>(G.vol)[m2];
             double z0, z1 = 0.0;
             if (c.z_stock) {
                 const double *zs = c.z_stock + static_cast<long long>(M) * (t - 1 - c.tape_toff);
@@ -855,15 +909,15 @@ __device__ FSB_FP_INLINE void phase_shocks(const int t)
         int idle = 0;  // investors already in cash when the day starts (none in a run from initialise)
 #pragma unroll 2
         for (int n = tid; n < ((N + 7) & ~7); n += NT) {
-            const int f = (n < N) ? c.pos[n] : -1;
+            const int f = (n < N) ? G.pos[n] : -1;
             c.pos16_()[n] = static_cast<short>(f);
-            c.hor16_()[n] = static_cast<unsigned short>((n < N) ? c.horizon[n] : 0);
+            c.hor16_()[n] = static_cast<unsigned short>((n < N) ? G.horizon[n] : 0);
             idle += (f == K);
         }
         idle = __reduce_add_sync(0xffffffffu, idle);
         if (lane == 0) c.wcnt_()[nwarps + warp] = idle;
     }
-    for (int k = tid; k < K; k += NT) { c.stl_()[k] = c.stakeless[k]; c.hz_()[k] = c.hzero[k]; }
+    for (int k = tid; k < K; k += NT) { c.stl_()[k] = G.stakeless[k]; c.hz_()[k] = G.hzero[k]; }
     for (int q = tid; q < (K + 31) / 32; q += NT) { c.fmod_()[q] = 0; c.fsel_()[q] = 0; }
     for (int q = tid; q < cap; q += NT) c.nzf_()[q] = 0;
     FSB_MARK(20);
@@ -907,9 +961,10 @@ __device__ FSB_FP_INLINE void phase_shocks(const int t)
 // Review pass: 8 lanes per reviewer, 4 reviewers per warp; the reviewed fund's row against the opening
 // prices and the history columns t-h and h.  Returns the number of divestments (< 0: event overflow).
 // ------------------------------------------------------------------------------------------------
-__device__ FSB_FP_INLINE int phase_review(const int t)
+__device__ FSB_FP_INLINE int phase_review(const DevState &s, const int t)
 {
     Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq);
     FSB_TH;
     const int K = c.K, Mp = c.Mp, cap = c.cap, half = Mp >> 1;
     const int j8 = lane & 7, g4 = lane >> 3;
@@ -934,15 +989,15 @@ __device__ FSB_FP_INLINE int phase_review(const int t)
         bool valid = on && f < K;
         double thr = 0.0, amt = 0.0;
         if (valid) {  // (loaded together with the row and the columns: one memory latency)
-            thr = c.threshold[n];
-            amt = c.amount[n];
+            thr = G.threshold[n];
+            amt = G.amount[n];
         }
         const int h = c.hor16_()[n];
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
         if (valid) {
-            const double2 *row = reinterpret_cast<const double2 *>(c.H + static_cast<long long>(f) * Mp);
-            const double2 *c1 = reinterpret_cast<const double2 *>(c.P + static_cast<long long>(pcol(c, t - h)) * Mp);
-            const double2 *c2 = reinterpret_cast<const double2 *>(c.P + static_cast<long long>(pcol(c, h)) * Mp);
+            const double2 *row = reinterpret_cast<const double2 *>(G.H + static_cast<long long>(f) * Mp);
+            const double2 *c1 = reinterpret_cast<const double2 *>(G.P + static_cast<long long>(pcol(c, t - h)) * Mp);
+            const double2 *c2 = reinterpret_cast<const double2 *>(G.P + static_cast<long long>(pcol(c, h)) * Mp);
             const double2 *c0 = reinterpret_cast<const double2 *>(po);
 #pragma unroll 4
             for (int e2 = j8; e2 < half; e2 += 8) {
@@ -957,7 +1012,7 @@ __device__ FSB_FP_INLINE int phase_review(const int t)
         int flag = 0;
         if (valid) flag = (ddiv(a0 - a1, a2) < thr) ? 1 : 0;
         if (on && j8 == 0) {
-            if (valid) c.nav_open[f] = a0;
+            if (valid) G.nav_open[f] = a0;
             c.rev_()[i] = n;
             c.rfund_()[i] = f;
             c.flags_()[i] = flag;
@@ -982,9 +1037,9 @@ __device__ FSB_FP_INLINE int phase_review(const int t)
     }
     __syncwarp();
     if (tid == 0) {
-        c.cnt[CNT_REVIEWS] += nrev;
-        c.cnt[CNT_DIVEST] += nd;
-        c.cnt[CNT_STEPS] += 1;
+        G.cnt[CNT_REVIEWS] += nrev;
+        G.cnt[CNT_DIVEST] += nd;
+        G.cnt[CNT_STEPS] += 1;
         c.isc_()[I_NREV] = nrev;
         c.isc_()[I_IDLE] = idle_cash;
     }
@@ -996,9 +1051,10 @@ __device__ FSB_FP_INLINE int phase_review(const int t)
 // T2: liquidate! (:183-201), trackvolume! (:467), marketmake! (:205-211), executeorder!(Sell)
 // (:213-224), disburse! cash (:243-252).  Returns 1 when a fund's stakes sum to zero (:471).
 // ------------------------------------------------------------------------------------------------
-__device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
+__device__ FSB_FP_INLINE int phase_liquidate(const DevState &s, const int t, const int nd)
 {
     Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq);
     FSB_TH;
     const int K = c.K, M = c.M, N = c.N, Mp = c.Mp;
     const int j8 = lane & 7, g4 = lane >> 3;
@@ -1007,10 +1063,6 @@ __device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
     // members (ascending investor id) are gathered into a per-warp list (16-byte scans of the shared
     // investor->fund map) with their stakes, the fund's divestments are applied in order on the list and
     // the stakes written back once
-    if (warp == 1 % nwarps) {  // history columns of the leavers' horizons: wanted in L2 by the column staging
-        for (int o = lane; o < nd; o += 32)
-            l2_prefetch_bulk(c.P + static_cast<long long>(pcol(c, t - c.hor16_()[c.d_inv_()[o]])) * Mp, static_cast<unsigned>(Mp * 8));
-    }
     FSB_MARK(17);
     {
         const int capm = (c.wsd * 2) / 3;
@@ -1048,7 +1100,7 @@ __device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
                 while (mask) {
                     const int q = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    if (w < capm) { mn[w] = n0 + q; mv[w] = c.stake[n0 + q]; }
+                    if (w < capm) { mn[w] = n0 + q; mv[w] = G.stake[n0 + q]; }
                     ++w;
                 }
                 cntm += __shfl_sync(0xffffffffu, incl, 31);
@@ -1072,20 +1124,20 @@ __device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
                         for (int q = lane; q < cntm; q += 32) mv[q] = qdiv(mv[q], tot);
                     __syncwarp();
                 }
-                for (int q = lane; q < cntm; q += 32) c.stake[mn[q]] = mv[q];
+                for (int q = lane; q < cntm; q += 32) G.stake[mn[q]] = mv[q];
             } else {  // list does not fit: work on the global stakes; member i of the fund goes to lane i % 32
 #pragma unroll 1
                 for (int o2 = o; o2 < nd; ++o2) {
                     if (c.d_fund_()[o2] != f) continue;
                     const int inv = c.d_inv_()[o2];
-                    if (lane == 0) { c.d_stake_()[o2] = c.stake[inv]; c.stake[inv] = 0.0; }
+                    if (lane == 0) { c.d_stake_()[o2] = G.stake[inv]; G.stake[inv] = 0.0; }
                     __syncwarp();
                     int seen = 0;
                     tot = 0.0;
                     for (int b = 0; b < N; b += 32) {
                         const int n = b + lane;
                         const bool mem = (n < N) && (c.pos16_()[n] == f);
-                        const double v = mem ? c.stake[n] : 0.0;
+                        const double v = mem ? G.stake[n] : 0.0;
                         unsigned m = __ballot_sync(0xffffffffu, mem);
                         while (m) {
                             const int q = __ffs(m) - 1;
@@ -1099,7 +1151,7 @@ __device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
                     for (int sft = 16; sft >= 1; sft >>= 1) tot = tot + __shfl_xor_sync(0xffffffffu, tot, sft);
                     if (tot > 0.0) {
                         for (int n = lane; n < N; n += 32)
-                            if (c.pos16_()[n] == f) c.stake[n] = qdiv(c.stake[n], tot);
+                            if (c.pos16_()[n] == f) G.stake[n] = qdiv(G.stake[n], tot);
                     }
                     __syncwarp();
                 }
@@ -1107,7 +1159,7 @@ __device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
             if (lane == 0) {
                 const unsigned char sl = (tot == 0.0) ? 1 : 0;
                 c.stl_()[f] = sl;
-                c.stakeless[f] = sl;
+                G.stakeless[f] = sl;
             }
         }
     }
@@ -1118,7 +1170,7 @@ __device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
 #pragma unroll 1
     for (int m = tid; m < M; m += NT) {
         const double p = pc[m];
-        const double imp = c.impact[m];
+        const double imp = G.impact[m];
         double net = 0.0;
 #pragma unroll 1
         for (int o0 = 0; o0 < nd; o0 += 4) {
@@ -1132,16 +1184,16 @@ __device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
             double hq[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q)  // (a missing order re-reads the first row: no predicated array)
-                hq[q] = c.H[static_cast<long long>(fq[q] >= 0 ? fq[q] : fq[0]) * Mp + m];
+                hq[q] = G.H[static_cast<long long>(fq[q] >= 0 ? fq[q] : fq[0]) * Mp + m];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (q < n4) {
                     const int o = o0 + q;
                     const double sk = c.d_stake_()[o];
-                    double *hpn = c.H + static_cast<long long>(fq[q]) * Mp + m;
+                    double *hpn = G.H + static_cast<long long>(fq[q]) * Mp + m;
                     const double h = dup ? *hpn : hq[q];
                     const double v = (-sk) * (h * p);
-                    order_row(c, o)[m] = v;
+                    order_row(c, G.scratch, o)[m] = v;
                     net = net + v;
                     const double hn = h * (1.0 - sk);
                     *hpn = hn;
@@ -1153,7 +1205,7 @@ __device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
         double v = (1.0 + net * imp) * p;
         int fl = 0;
         if (v < kPriceFloor) { v = kPriceFloor; fl = 1; }
-        if (c.volume) c.volume[static_cast<long long>(t - 1) * Mp + m] -= net;
+        if (G.volume) G.volume[static_cast<long long>(t - 1) * Mp + m] -= net;
         c.pick_()[m] = fl;
         pc[m] = v;
         c.ratio_()[m] = ddiv(v, p);  // priceratio, :217
@@ -1165,12 +1217,12 @@ __device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
     for (int ob = warp * 4; ob < nd; ob += nwarps * 4) {
         const int o = ob + g4;
         const bool on = o < nd;
-        const double cash = -sumprod8(order_row(c, on ? o : ob), c.ratio_(), M, j8, on);
+        const double cash = -sumprod8(order_row(c, G.scratch, on ? o : ob), c.ratio_(), M, j8, on);
         if (on && j8 == 0) {
             const int inv = c.d_inv_()[o];
             c.d_cash_()[o] = cash;
-            c.amount[inv] = cash;  // Q8: assigned, not accumulated
-            c.pos[inv] = K;
+            G.amount[inv] = cash;  // Q8: assigned, not accumulated
+            G.pos[inv] = K;
             c.pos16_()[inv] = static_cast<short>(K);
         }
     }
@@ -1183,13 +1235,13 @@ __device__ FSB_FP_INLINE int phase_liquidate(const int t, const int nd)
                 const int e = static_cast<int>((__double_as_longlong(flow) >> 52) & 0x7ff) - 1023;
                 bin = min(kFlowBins - 1, e + 1);
             }
-            c.flow_hist[bin] += 1;
+            G.flow_hist[bin] += 1;
         }
         for (int o = lane; o < nd; o += 32) {  // the last order of a fund decides whether its row is all zero
             const int f = c.d_fund_()[o];
             bool last = true;
             for (int q = o + 1; q < nd; ++q) last = last && (c.d_fund_()[q] != f);
-            if (last) { const unsigned char z = c.nzf_()[o] ? 0 : 1; c.hz_()[f] = z; c.hzero[f] = z; }
+            if (last) { const unsigned char z = c.nzf_()[o] ? 0 : 1; c.hz_()[f] = z; G.hzero[f] = z; }
         }
     }
     floor_account(t, 0);
@@ -1311,7 +1363,7 @@ __device__ __noinline__ int phase_respawn(const int t, const int nd, const int f
             }
         }
         __syncthreads();
-        double *bo = order_row(c, i);
+        double *bo = order_row(c, c.scratch, i);
         for (int m = tid; m < Mp; m += NT) {
             double val = 0.0;
             if (m < M) {
@@ -1375,7 +1427,7 @@ __device__ __noinline__ int phase_respawn(const int t, const int nd, const int f
     __syncthreads();
     for (int m = tid; m < M; m += NT) {
         double net = 0.0;
-        for (int i = 0; i < neggs; ++i) net = net + order_row(c, i)[m];
+        for (int i = 0; i < neggs; ++i) net = net + order_row(c, c.scratch, i)[m];
         if (c.volume && !(flags & FSB_RUN_NO_VOLUME_QUIRK)) c.volume[static_cast<long long>(t - 1) * Mp + m] -= c.sellsum_()[m];  // :474 (Q3)
         const double ni = net * c.impact[m];
         double v = (1.0 + ni) * pc[m];
@@ -1385,7 +1437,7 @@ __device__ __noinline__ int phase_respawn(const int t, const int nd, const int f
         pc[m] = v;
         for (int i = 0; i < neggs; ++i) {
             double *hpn = c.H + static_cast<long long>(c.eggs_()[i]) * Mp + m;
-            const double hn = *hpn + qdiv(order_row(c, i)[m], v);
+            const double hn = *hpn + qdiv(order_row(c, c.scratch, i)[m], v);
             *hpn = hn;
             if (hn != 0.0) c.nzf_()[i] = 1;
         }
@@ -1402,9 +1454,10 @@ __device__ __noinline__ int phase_respawn(const int t, const int nd, const int f
 // T4: cash holders (:481, :339) and their distinct horizons, by warp 0; ends with B7.
 // Returns the number of cash holders (< 0: event overflow).
 // ------------------------------------------------------------------------------------------------
-__device__ FSB_FP_INLINE int phase_cashlist(const int nd)
+__device__ FSB_FP_INLINE int phase_cashlist(const DevState &s, const int nd)
 {
     Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq);
     FSB_TH;
     const int K = c.K, N = c.N, cap = c.cap;
     if (warp == 0) {
@@ -1423,7 +1476,7 @@ __device__ FSB_FP_INLINE int phase_cashlist(const int nd)
             for (int b = 0; b < N; b += 32) {
                 const int n = b + lane;
                 bool p = (n < N) && (c.pos16_()[n] == K);
-                if (p) p = c.amount[n] > 0.0;
+                if (p) p = G.amount[n] > 0.0;
                 const unsigned m = __ballot_sync(0xffffffffu, p);
                 if (p) {
                     const int k = cnt + __popc(m & ((1u << lane) - 1u));
@@ -1453,57 +1506,68 @@ __device__ FSB_FP_INLINE int phase_cashlist(const int nd)
     return (ncash > cap) ? -1 : ncash;
 }
 
-// stage the history columns t-h of a chunk: bulk asynchronous copies (TMA unit) issued by one thread; ends with B8
-__device__ FSB_FP_INLINE void phase_stage_columns(const int t, const int c0, const int nc)
+// stage the columns of a chunk into shared memory: bulk asynchronous copies (TMA unit) issued by one
+// thread.  first: also the opening prices (handoff) into slot 0 and the post-impact prices (the day's
+// column of the price history, written by the events-1 kernel) into slot 1.  Ends with a block barrier.
+__device__ FSB_FP_INLINE void phase_stage_columns(const DevState &s, const int t, const int c0, const int nc, const bool first, const bool open_day)
 {
     Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq);
     FSB_TH;
     const int Mp = c.Mp;
-    if (nc > 0) {
+    const int ncopies = nc + (first ? (open_day ? 1 : 2) : 0);
+    if (ncopies > 0) {
         const unsigned phase = c.mbar_phase;
         if (tid == 0) {
             fence_proxy_async();
-            mbar_expect_tx(c.mbar, static_cast<unsigned>(nc * Mp * 8));
+            mbar_expect_tx(c.mbar, static_cast<unsigned>(ncopies * Mp * 8));
+            if (first) {
+                bulk_g2s(c.cols_(), G.hand_p, static_cast<unsigned>(Mp * 8), c.mbar);
+                if (!open_day)
+                    bulk_g2s(c.cols_() + c.cpk, G.P + static_cast<long long>(pcol(c, t)) * Mp, static_cast<unsigned>(Mp * 8), c.mbar);
+            }
             for (int q = 0; q < nc; ++q)
-                bulk_g2s(c.cols_() + (2 + q) * c.cpk, c.P + static_cast<long long>(pcol(c, t - c.hcols_()[c0 + q])) * Mp,
+                bulk_g2s(c.cols_() + (2 + q) * c.cpk, G.P + static_cast<long long>(pcol(c, t - c.hcols_()[c0 + q])) * Mp,
                          static_cast<unsigned>(Mp * 8), c.mbar);
         }
         mbar_wait(c.mbar, phase);
     }
-    __syncthreads();  // B8 (pads; also orders the previous chunk's readers before this chunk's results)
-    if (nc > 0 && tid == 0) c.mbar_phase ^= 1u;  // (every thread has read the phase before the barrier)
+    __syncthreads();  // (also orders the previous chunk's readers before this chunk's results)
+    if (ncopies > 0 && tid == 0) c.mbar_phase ^= 1u;  // (every thread has read the phase before the barrier)
     FSB_MARK(9);
 }
 
-// T6: fund choice of the cash holders whose horizon is in the chunk [c0, c0 + nc) (:344-353, 381-415)
-__device__ FSB_FP_INLINE void phase_choice(const int t, const int c0, const int nc, const int ncash, const int selector)
+// T6: fund choice of the cash holders (:344-353, 381-415); the horizon returns of all ncols columns are in
+// the replication's key rows (written by the pass kernel)
+__device__ FSB_FP_INLINE void phase_choice(const DevState &s, const int t, const int ncols, const int ncash, const int selector)
 {
     Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq);
     FSB_TH;
     const int K = c.K;
     if (selector == FSB_SEL_PROBABILISTIC) {
-        // rank rule: p_k = rank_k / (K(K+1)/2) per column, into the (now free) staged column
+        // rank rule: p_k = rank_k / (K(K+1)/2) per column, into the warp's probability row
+        double *prob_k = c.cols_() + (2 + warp) * c.cpk;
 #pragma unroll 1
-        for (int jc = warp; jc < nc; jc += nwarps) {
-            const unsigned long long *keys = c.keys + static_cast<long long>(jc) * c.kq;
-            double *prob_k = c.cols_() + (2 + jc) * c.cpk;
+        for (int jc = warp; jc < ncols; jc += nwarps) {
+            const unsigned long long *keys = G.keys + static_cast<long long>(jc) * c.kq;
             if (c.rank256) warp_rank256(keys, K, prob_k, c.ranktab);
             else warp_rank_count(keys, K, prob_k, c.ranktab);
             __syncwarp();
             FSB_MARK(23);
             // the same warp samples the choice of every cash holder whose horizon is this column
             for (int i = lane; i < ncash; i += 32) {
-                if (c.r_col_()[i] != c0 + jc) continue;
+                if (c.r_col_()[i] != jc) continue;
                 c.r_choice_()[i] = select_fund_prob(c, t, c.cash_()[i], prob_k);
             }
+            __syncwarp();
         }
         FSB_MARK(11);
     } else {
 #pragma unroll 1
         for (int i = warp; i < ncash; i += nwarps) {
             const int col = c.r_col_()[i];
-            if (col < c0 || col >= c0 + nc) continue;
-            const int choice = select_fund_warp(t, c.cash_()[i], c.keys + static_cast<long long>(col - c0) * c.kq, selector);
+            const int choice = select_fund_warp(t, c.cash_()[i], G.keys + static_cast<long long>(col) * c.kq, selector);
             if (lane == 0) c.r_choice_()[i] = choice;
         }
     }
@@ -1514,17 +1578,18 @@ __device__ FSB_FP_INLINE void phase_choice(const int t, const int c0, const int 
 // ------------------------------------------------------------------------------------------------
 // T7-T9: reinvest! (:335-373): stake dilution (Q7), buy orders, executeorder!(Buy), disburse! shares
 // ------------------------------------------------------------------------------------------------
-__device__ FSB_FP_INLINE void phase_reinvest(const int t, const int ncash, const int flags)
+__device__ FSB_FP_INLINE void phase_reinvest(const DevState &s, const int t, const int ncash, const int flags)
 {
     Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq);
     FSB_TH;
     const int K = c.K, M = c.M, N = c.N, Mp = c.Mp, cap = c.cap;
     const int j8 = lane & 7, g4 = lane >> 3;
     double *const pc = p_cur(c);
     for (int i = tid; i < ncash; i += NT) {
         const int ch = c.r_choice_()[i];
-        const double inj = c.amount[c.cash_()[i]];
-        const double fv = c.nav_()[ch];  // == holdings[choice,:]' * stockvals[:,t], :360
+        const double inj = G.amount[c.cash_()[i]];
+        const double fv = G.nav_close[ch];  // == holdings[choice,:]' * stockvals[:,t], :360 (pass kernel)
         c.r_inj_()[i] = inj;
         c.r_fval_()[i] = fv;
         c.r_ncap_()[i] = fv + inj;
@@ -1534,7 +1599,7 @@ __device__ FSB_FP_INLINE void phase_reinvest(const int t, const int ncash, const
     for (int o = tid; o < cap; o += NT) c.nzf_()[o] = 0;
     __syncthreads();  // B13
     FSB_MARK(13);
-    if (tid == 0) c.cnt[CNT_REINVEST] += ncash;
+    if (tid == 0) G.cnt[CNT_REINVEST] += ncash;
     if (c.trace >= 0) trace_phase(t, 4, ncash, 0);
     // stakes (:363-366), sequential over reinvestors per investor (Q7), parallel over investors
 #pragma unroll 1
@@ -1550,7 +1615,7 @@ __device__ FSB_FP_INLINE void phase_reinvest(const int t, const int ncash, const
         }
         if (!touched) continue;
         mypos = c.pos16_()[n];
-        double st = c.stake[n];
+        double st = G.stake[n];
         for (int i = 0; i < ncash; ++i) {
             const int ch = c.r_choice_()[i];
             if (c.cash_()[i] == n) {
@@ -1560,9 +1625,9 @@ __device__ FSB_FP_INLINE void phase_reinvest(const int t, const int ncash, const
                 st = qdiv(st * c.r_fval_()[i], c.r_ncap_()[i]);
             }
         }
-        c.pos[n] = mypos;
+        G.pos[n] = mypos;
         c.pos16_()[n] = static_cast<short>(mypos);
-        c.stake[n] = st;
+        G.stake[n] = st;
         if (st != 0.0 && mypos < K) c.stl_()[mypos] = 0;
     }
     FSB_MARK(24);
@@ -1570,25 +1635,25 @@ __device__ FSB_FP_INLINE void phase_reinvest(const int t, const int ncash, const
 #pragma unroll 1
     for (int m = tid; m < M; m += NT) {
         const double p = pc[m];
-        const double imp = c.impact[m];
+        const double imp = G.impact[m];
         double net = 0.0;
 #pragma unroll 1
         for (int i0 = 0; i0 < ncash; i0 += 4) {  // holdings do not change in this loop: 4 rows in flight
             const int n4 = min(4, ncash - i0);
             double hq[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) hq[q] = c.H[static_cast<long long>(c.r_choice_()[q < n4 ? i0 + q : i0]) * Mp + m];
+            for (int q = 0; q < 4; ++q) hq[q] = G.H[static_cast<long long>(c.r_choice_()[q < n4 ? i0 + q : i0]) * Mp + m];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (q < n4) {
                     const int i = i0 + q;
                     const double v = qdiv(hq[q] * p, c.r_fval_()[i]) * c.r_inj_()[i];
-                    order_row(c, i)[m] = v;
+                    order_row(c, G.scratch, i)[m] = v;
                     net = net + v;
                 }
             }
         }
-        if (c.volume && !(flags & FSB_RUN_NO_VOLUME_QUIRK)) c.volume[static_cast<long long>(t - 1) * Mp + m] -= c.sellsum_()[m];  // :484 (Q3)
+        if (G.volume && !(flags & FSB_RUN_NO_VOLUME_QUIRK)) G.volume[static_cast<long long>(t - 1) * Mp + m] -= c.sellsum_()[m];  // :484 (Q3)
         double v = (1.0 + net * imp) * p;
         int fl = 0;
         if (v < kPriceFloor) { v = kPriceFloor; fl = 1; }
@@ -1603,13 +1668,13 @@ __device__ FSB_FP_INLINE void phase_reinvest(const int t, const int ncash, const
             const bool dup = (fq[1] == fq[0]) || (fq[2] == fq[0]) || (fq[2] == fq[1]) || (fq[3] == fq[0]) || (fq[3] == fq[1]) || (fq[3] == fq[2]);
             double hq[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) hq[q] = c.H[static_cast<long long>(fq[q] >= 0 ? fq[q] : fq[0]) * Mp + m];
+            for (int q = 0; q < 4; ++q) hq[q] = G.H[static_cast<long long>(fq[q] >= 0 ? fq[q] : fq[0]) * Mp + m];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (q < n4) {
                     const int i = i0 + q;
-                    double *hpn = c.H + static_cast<long long>(fq[q]) * Mp + m;
-                    const double hn = (dup ? *hpn : hq[q]) + qdiv(order_row(c, i)[m], v);
+                    double *hpn = G.H + static_cast<long long>(fq[q]) * Mp + m;
+                    const double hn = (dup ? *hpn : hq[q]) + qdiv(order_row(c, G.scratch, i)[m], v);
                     *hpn = hn;
                     if (hn != 0.0) c.nzf_()[i] = 1;
                 }
@@ -1627,100 +1692,185 @@ __device__ FSB_FP_INLINE void phase_reinvest(const int t, const int ncash, const
         const int f = c.r_choice_()[on ? i : ib];
         if (on)
             for (int q = i + 1; q < ncash; ++q) on = on && (c.r_choice_()[q] != f);
-        const double v = dot8(c.H + static_cast<long long>(f) * Mp, pc, M, j8, on);
-        if (on && j8 == 0) c.nav_close[f] = v;
+        const double v = dot8(G.H + static_cast<long long>(f) * Mp, pc, M, j8, on);
+        if (on && j8 == 0) G.nav_close[f] = v;
     }
     for (int i = tid; i < ncash; i += NT) {
         const int f = c.r_choice_()[i];
         bool last = true;
         for (int q = i + 1; q < ncash; ++q) last = last && (c.r_choice_()[q] != f);
         if (last) {
-            c.hzero[f] = c.nzf_()[i] ? 0 : 1;
-            c.stakeless[f] = c.stl_()[f];
+            G.hzero[f] = c.nzf_()[i] ? 0 : 1;
+            G.stakeless[f] = c.stl_()[f];
         }
     }
     floor_account(t, 2);
 }
 
 // the day's closing prices into the history; ends the step
-__device__ FSB_FP_INLINE void phase_store_prices(const int t)
+__device__ FSB_FP_INLINE void phase_store_prices(const DevState &s, const int t)
 {
     Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq);
     FSB_TH;
     const int half = c.Mp >> 1;
-    double *Pt = c.P + static_cast<long long>(pcol(c, t)) * c.Mp;
+    double *Pt = G.P + static_cast<long long>(pcol(c, t)) * c.Mp;
     const double *pc = p_cur(c);
     for (int m2 = tid; m2 < half; m2 += NT) reinterpret_cast<double2 *>(Pt)[m2] = reinterpret_cast<const double2 *>(pc)[m2];
     __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
-// one time step of one replication
+// The step is three kernels (DESIGN.md "Why three kernels"): events-1 (shocks .. cash list), the holdings
+// pass (NAVs + horizon returns) and events-2 (choice .. buy impact).  What crosses a kernel boundary goes
+// through small per-replication handoff arrays in global memory:
+//   hand_p [Mp]      opening prices of the day              (the post-impact prices go into the day's
+//                                                             column of the price history)
+//   hand_i [..]      HI_T step stamp, HI_OPEN, HI_NCOLS, HI_NCASH, fmod bitmap, hcols[], cash[], r_col[]
+//   hand_s [Mp]      the day's net sale per asset (keep_history only: Q3 volume bookkeeping)
+//   keys   [kc][kq]  horizon returns per column (pass -> events-2)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void step_replication(Ctx &c, const int t, const int selector, const int flags)
+enum { HI_T = 0, HI_OPEN, HI_NCOLS, HI_NCASH, HI_FMOD = 8 };
+__host__ __device__ inline int hand_ints(int K, int cap) { return ((HI_FMOD + (K + 31) / 32 + 3 * cap) + 3) & ~3; }
+
+enum { KIND_EVENTS1 = 0, KIND_PASS = 1, KIND_EVENTS2 = 2 };
+
+// events-1: one time step of one replication up to the cash list
+__device__ __forceinline__ void step_events1(const DevState &s, Ctx &c, const int t, const int flags)
 {
+    FSB_TH;
+    const Rep G = rep_ptrs(s, c.r, c.kq);
     const bool traced = (c.trace >= 0);
-    phase_shocks(t);
-    const int nd = phase_review(t);
+    const int nf = (c.K + 31) / 32, cap = c.cap, half = c.Mp >> 1;
+    phase_shocks(s, t);
+    const int nd = phase_review(s, t);
     if (nd < 0) {
-        if (threadIdx.x == 0) atomicOr(c.err, FSB_REP_EVENT_OVERFLOW);
+        if (tid == 0) atomicOr(c.err, FSB_REP_EVENT_OVERFLOW);
         return;
     }
     if (traced) trace_phase(t, 0, c.isc_()[I_NREV], nd);  // (only thread 0 reads I_NREV, which it wrote itself)
-    if (nd == 0) {  // :464 -- nothing else happens this step: nav_open = nav_close = H * p_open
-        if (c.fast) full_pass<1, true, true>(0, 1, 0);
-        else full_pass<1, true, false>(0, 1, 0);
-        if (threadIdx.x == 0) c.flow_hist[0] += 1;
-        phase_store_prices(t);
-        FSB_MARK(3);
-        if (traced) trace_phase(t, 3, 0, 0);
-        return;
+    int ncash = 0, ncols = 0;
+    if (nd > 0) {
+        const int any_dead = phase_liquidate(s, t, nd);
+        if (traced) trace_phase(t, 1, nd, 0);
+        if (any_dead && phase_respawn(t, nd, flags)) return;
+        if (traced) trace_phase(t, 2, 0, 0);
+        FSB_MARK(7);
+        ncash = phase_cashlist(s, nd);
+        if (ncash < 0 || c.isc_()[I_NCOLS] > c.kc) {
+            if (tid == 0) atomicOr(c.err, FSB_REP_EVENT_OVERFLOW);
+            return;
+        }
+        ncols = c.isc_()[I_NCOLS];
+    } else if (tid == 0) {
+        G.flow_hist[0] += 1;  // :464 -- nothing else happens this step
     }
-    const int any_dead = phase_liquidate(t, nd);
-    if (traced) trace_phase(t, 1, nd, 0);
-    if (any_dead && phase_respawn(t, nd, flags)) return;
-    if (traced) trace_phase(t, 2, 0, 0);
-    FSB_MARK(7);
-    const int ncash = phase_cashlist(nd);
-    if (ncash < 0) {
-        if (threadIdx.x == 0) atomicOr(c.err, FSB_REP_EVENT_OVERFLOW);
-        return;
+    // ---- handoff ---------------------------------------------------------------------------------
+    int *hi = G.hand_i;
+    if (tid == 0) { hi[HI_T] = t; hi[HI_OPEN] = (nd == 0) ? 1 : 0; hi[HI_NCOLS] = ncols; hi[HI_NCASH] = ncash; }
+    for (int q = tid; q < nf; q += NT) hi[HI_FMOD + q] = c.fmod_()[q];
+    for (int q = tid; q < ncols; q += NT) hi[HI_FMOD + nf + q] = c.hcols_()[q];
+    for (int q = tid; q < ncash; q += NT) { hi[HI_FMOD + nf + cap + q] = c.cash_()[q]; hi[HI_FMOD + nf + 2 * cap + q] = c.r_col_()[q]; }
+    {
+        const double2 *po2 = reinterpret_cast<const double2 *>(p_open(c)), *pc2 = reinterpret_cast<const double2 *>(p_cur(c));
+        double2 *Pt = reinterpret_cast<double2 *>(G.P + static_cast<long long>(pcol(c, t)) * c.Mp);
+        double2 *hp = reinterpret_cast<double2 *>(G.hand_p);
+        for (int m2 = tid; m2 < half; m2 += NT) { hp[m2] = po2[m2]; Pt[m2] = pc2[m2]; }
+        if (G.hand_s && nd > 0) {
+            double2 *hs = reinterpret_cast<double2 *>(G.hand_s);
+            const double2 *ss = reinterpret_cast<const double2 *>(c.sellsum_());
+            for (int m2 = tid; m2 < half; m2 += NT) hs[m2] = ss[m2];
+        }
     }
-    const int ncols = c.isc_()[I_NCOLS];
-    const int cmax = c.cmax;
-    const int want_keys = (selector == FSB_SEL_PROBABILISTIC) ? 1 : 0;
-    // fundrevalue!(1:K) at :460 and :479 + horizon returns of reinvest! (:335-379)
-    // first chunk: the two price columns + up to cmax horizons; later chunks: up to cmax - 2 horizons
+    FSB_MARK(15);
+}
+
+// the holdings pass: fundrevalue!(1:K) at :460 and :479 + horizon returns of reinvest! (:335-379)
+__device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t, const int selector)
+{
+    FSB_TH;
+    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const int nf = (c.K + 31) / 32;
+    const int *hi = G.hand_i;
+    if (hi[HI_T] != t) return;  // (events-1 stopped this replication: its error flag is set)
+    const int open_day = hi[HI_OPEN], ncols = hi[HI_NCOLS];
+    for (int q = tid; q < nf; q += NT) c.fmod_()[q] = hi[HI_FMOD + q];
+    for (int q = tid; q < ncols; q += NT) c.hcols_()[q] = hi[HI_FMOD + nf + q];
+    __syncthreads();
+    if (open_day) {  // nav_open = nav_close = H * p_open
+        phase_stage_columns(s, t, 0, 0, true, true);
+        if (c.fast) full_pass<1, true, true>(s, 0, 1, 0, 0);
+        else full_pass<1, true, false>(s, 0, 1, 0, 0);
+    } else {
+        const int cmax = c.cmax;
+        const int want_keys = (selector == FSB_SEL_PROBABILISTIC) ? 1 : 0;
+        // first chunk: the two price columns + up to cmax horizons; later chunks: up to cmax - 2 horizons
 #pragma unroll 1
-    for (int c0 = 0; c0 == 0 || c0 < ncols; c0 += (c0 == 0 ? cmax : cmax - 2)) {
-        const int nc = min(c0 == 0 ? cmax : cmax - 2, ncols - c0);
-        phase_stage_columns(t, c0, nc);
-        full_pass_dispatch(c, c0 == 0 ? 0 : 2, c0 == 0 ? 2 + nc : nc, want_keys);
-        __syncthreads();  // B9: keys[] holds the horizon returns (or their sort keys) of this chunk
-        FSB_MARK(10);
-        if (nc > 0) phase_choice(t, c0, nc, ncash, selector);
+        for (int c0 = 0; c0 == 0 || c0 < ncols; c0 += (c0 == 0 ? cmax : cmax - 2)) {
+            const int nc = min(c0 == 0 ? cmax : cmax - 2, ncols - c0);
+            phase_stage_columns(s, t, c0, nc, c0 == 0, false);
+            full_pass_dispatch(s, c, c0 == 0 ? 0 : 2, c0 == 0 ? 2 + nc : nc, want_keys, c0);
+            __syncthreads();  // (the next chunk overwrites the staged columns)
+            FSB_MARK(10);
+        }
     }
-    if (traced) trace_phase(t, 3, 0, 0);
+    if (c.trace >= 0) {
+        __syncthreads();
+        trace_phase(t, 3, 0, 0);
+    }
+}
+
+// events-2: fund choice, reinvestment, buy impact
+__device__ __forceinline__ void step_events2(const DevState &s, Ctx &c, const int t, const int selector, const int flags)
+{
+    FSB_TH;
+    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const int K = c.K, N = c.N, cap = c.cap, nf = (K + 31) / 32, half = c.Mp >> 1;
+    const int *hi = G.hand_i;
+    if (hi[HI_T] != t || hi[HI_OPEN]) return;
+    const int ncash = hi[HI_NCASH], ncols = hi[HI_NCOLS];
+    if (ncash == 0) return;  // (uniform: nobody reinvests, the prices of the day are final)
+    // ---- the day's state into shared memory ---------------------------------------------------------
+    if (tid < 16) c.isc_()[tid] = 0;
+    for (int q = tid; q < ncash; q += NT) { c.cash_()[q] = hi[HI_FMOD + nf + cap + q]; c.r_col_()[q] = hi[HI_FMOD + nf + 2 * cap + q]; }
+    {
+        const double2 *Pt = reinterpret_cast<const double2 *>(G.P + static_cast<long long>(pcol(c, t)) * c.Mp);
+        double2 *pc2 = reinterpret_cast<double2 *>(p_cur(c));
+        for (int m2 = tid; m2 < half; m2 += NT) pc2[m2] = Pt[m2];
+        if (G.hand_s) {
+            const double2 *hs = reinterpret_cast<const double2 *>(G.hand_s);
+            double2 *ss = reinterpret_cast<double2 *>(c.sellsum_());
+            for (int m2 = tid; m2 < half; m2 += NT) ss[m2] = hs[m2];
+        }
+    }
+#pragma unroll 2
+    for (int n = tid; n < ((N + 7) & ~7); n += NT) c.pos16_()[n] = static_cast<short>((n < N) ? G.pos[n] : -1);
+    for (int k = tid; k < K; k += NT) c.stl_()[k] = G.stakeless[k];
+    for (int q = tid; q < nf; q += NT) c.fsel_()[q] = 0;
+    __syncthreads();
+    phase_choice(s, t, ncols, ncash, selector);
     if (c.isc_()[I_ERR]) {
-        if (threadIdx.x == 0) atomicOr(c.err, c.isc_()[I_ERR]);
+        if (tid == 0) atomicOr(c.err, c.isc_()[I_ERR]);
         return;
     }
-    if (ncash > 0) phase_reinvest(t, ncash, flags);
-    phase_store_prices(t);
+    phase_reinvest(s, t, ncash, flags);
+    phase_store_prices(s, t);
     FSB_MARK(15);
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel: persistent CTAs pull replications from a work counter
+// kernels: persistent CTAs pull replications from a work counter (one counter pair per kernel kind)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kStepThreads, 4) fsb_step_kernel(const DevState s, const StepArgs a, const int launch_parity)
+template <int KIND>
+__device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepArgs &a, const int launch_parity)
 {
     static_assert(sizeof(Ctx) <= kCtxBytes, "Ctx outgrew its shared-memory slot");
     Ctx &c = ctx();
     __shared__ long long r_sh;
     __shared__ __align__(8) unsigned long long mbar_sh;
     const int nwarps = blockDim.x >> 5;
-    const SmemLayout L = make_layout(s.K, s.Mp, s.N, s.cap_ev, s.cmax, nwarps);
+    const int nslots = (KIND == KIND_PASS) ? s.cmax + 2 : (KIND == KIND_EVENTS1 ? s.slots_a : s.slots_c);
+    const SmemLayout L = make_layout(s.K, s.Mp, s.N, s.cap_ev, nslots, nwarps);
     double *sd = reinterpret_cast<double *>(fsb_smem + kCtxBytes);
     if (threadIdx.x == 0) {
         c.K = s.K; c.M = s.M; c.N = s.N; c.Mp = s.Mp; c.T = s.T; c.W = s.W; c.cap = s.cap_ev; c.cmax = s.cmax;
@@ -1728,6 +1878,8 @@ __global__ void __launch_bounds__(kStepThreads, 4) fsb_step_kernel(const DevStat
         c.cp = L.cp; c.cpk = L.cpk; c.kq = L.kq; c.srows = L.srows; c.wsd = L.wsd;
         c.rank256 = (s.K <= 256) ? 1 : 0;  // the in-register rank sort holds 256 keys
         c.fast = (s.K <= 256 && s.Mp == 256) ? 1 : 0;
+        c.pf_ahead = s.pf_ahead;
+        c.kc = s.kc;
         const int bd = kCtxBytes, bi = bd + 8 * L.ndoubles, bs = bi + 4 * L.nints;  // byte offsets of the double / int / 16-bit regions
         c.o_cols = bd + 8 * L.off_cols; c.o_ratio = bd + 8 * L.off_ratio; c.o_sellsum = bd + 8 * L.off_sellsum;
         c.o_nav = bd + 8 * L.off_nav; c.o_d_stake = bd + 8 * L.off_dstake; c.o_d_cash = bd + 8 * L.off_dcash;
@@ -1742,7 +1894,6 @@ __global__ void __launch_bounds__(kStepThreads, 4) fsb_step_kernel(const DevStat
         c.mbar = &mbar_sh; c.mbar_phase = 0;
         c.tmark = clock64();
         c.scratch = s.scratch + static_cast<long long>(blockIdx.x) * s.cap_ev * s.Mp;
-        c.keys = s.keys + static_cast<long long>(blockIdx.x) * s.cmax * L.kq;
         c.ranktab = s.ranktab;
         c.rng.k0 = static_cast<uint32_t>(s.seed); c.rng.k1 = static_cast<uint32_t>(s.seed >> 32);
         mbar_init(&mbar_sh, 1);
@@ -1750,9 +1901,10 @@ __global__ void __launch_bounds__(kStepThreads, 4) fsb_step_kernel(const DevStat
     for (int q = threadIdx.x; q < L.ndoubles; q += blockDim.x) sd[q] = 0.0;  // zero pads once
     __syncthreads();
 
-    if (blockIdx.x == 0 && threadIdx.x == 0) s.queue[launch_parity ^ 1] = 0;  // reset the next launch's counter
+    int *const queue = s.queue + 2 * KIND;
+    if (blockIdx.x == 0 && threadIdx.x == 0) queue[launch_parity ^ 1] = 0;  // reset the next launch's counter
     for (;;) {
-        if (threadIdx.x == 0) r_sh = atomicAdd(&s.queue[launch_parity], 1);
+        if (threadIdx.x == 0) r_sh = atomicAdd(&queue[launch_parity], 1);
         __syncthreads();
         const long long r = r_sh;
         if (r >= s.R) break;
@@ -1781,6 +1933,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) fsb_step_kernel(const DevStat
             c.log_liquidated = s.log_liquidated + lb; c.log_replacedby = s.log_replacedby + lb;
             c.log_failtime = s.log_failtime + lb; c.log_ninv = s.log_ninv + lb; c.log_nstocks = s.log_nstocks + lb;
             c.log_size = s.log_size + lb; c.log_liquidity = s.log_liquidity + lb;
+            c.keys = s.keys + r * (static_cast<long long>(s.kc) * L.kq);
             c.z_mkt = s.any_tape ? s.z_mkt[r] : nullptr;
             c.z_stock = s.any_tape ? s.z_stock[r] : nullptr;
             c.u_review = s.any_tape ? s.u_review[r] : nullptr;
@@ -1800,13 +1953,25 @@ __global__ void __launch_bounds__(kStepThreads, 4) fsb_step_kernel(const DevStat
         }
         __syncthreads();  // context visible; also keeps r_sh stable until every thread has read it
         if (frozen) continue;  // frozen replication (uniform)
-        for (int q = 0; q < a.n_steps; ++q) {
-            FSB_MARK(0);
-            step_replication(c, a.t_first + q, a.selector, a.flags);
-            __syncthreads();
-            if (s.err[r] & ~FSB_REP_TRACE_OVERFLOW) break;  // written by this CTA's thread 0 before the sync
-        }
+        FSB_MARK(0);
+        if (KIND == KIND_EVENTS1) step_events1(s, c, a.t_first, a.flags);
+        else if (KIND == KIND_PASS) step_pass(s, c, a.t_first, a.selector);
+        else step_events2(s, c, a.t_first, a.selector, a.flags);
+        __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(kStepThreads, 4) fsb_events1_kernel(const DevState s, const StepArgs a, const int launch_parity)
+{
+    phase_kernel_body<KIND_EVENTS1>(s, a, launch_parity);
+}
+__global__ void __launch_bounds__(kStepThreads, 4) fsb_pass_kernel(const DevState s, const StepArgs a, const int launch_parity)
+{
+    phase_kernel_body<KIND_PASS>(s, a, launch_parity);
+}
+__global__ void __launch_bounds__(kStepThreads, 4) fsb_events2_kernel(const DevState s, const StepArgs a, const int launch_parity)
+{
+    phase_kernel_body<KIND_EVENTS2>(s, a, launch_parity);
 }
 
 }  // namespace fsb
