@@ -89,6 +89,13 @@ struct fsb_engine {
     int64_t device_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // replication batches: each runs its three kernels per step on its own stream, so that the memory-bound
+    // holdings pass of one batch overlaps the latency-bound event kernels of another
+    int n_batches = 1;
+    std::vector<cudaStream_t> bstream;
+    std::vector<cudaEvent_t> bjoin;
+    cudaEvent_t fork = nullptr;
+    int occ[3] = {1, 1, 1};
     int grid[3] = {0, 0, 0}, block = 256, smem_bytes[3] = {0, 0, 0}, init_smem = 0;
     int launch_parity = 0;
     bool fast = false;
@@ -213,14 +220,17 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     CU(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     const int nw = e->block / 32;
-    int want_ctas = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : 4;
+    d.ring_stages = (d.K <= 256 && d.Mp == 256) ? kRingStages : 0;
+    if (getenv("FSB_NO_TMA")) d.ring_stages = 0;
+    int want_ctas = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : (d.ring_stages ? 2 : 4);
     if (const char *ev = getenv("FSB_CTAS_PER_SM")) want_ctas = std::max(1, atoi(ev));
     const int budget = std::min(smem_max, smem_sm / want_ctas - 1024);
     d.cmax = kMaxCols;
     d.pf_ahead = kPfAheadDefault;
     if (const char *ev = getenv("FSB_PF_AHEAD")) d.pf_ahead = std::max(0, atoi(ev));
-    if (const char *ev = getenv("FSB_CMAX")) d.cmax = std::min(kMaxCols, std::max(2, ((atoi(ev) + 2) / 4) * 4 - 2));
-    while (make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax + 2, nw).bytes + 64 > budget && d.cmax > 2) d.cmax -= 4;
+    if (const char *ev = getenv("FSB_CMAX")) d.cmax = std::min(kMaxCols, std::max(6, ((atoi(ev) + 2) / 4) * 4 - 2));
+    // (a chunk after the first holds cmax - 2 columns: cmax stays >= 6)
+    while (make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax + 2, nw, d.ring_stages).bytes + 64 > budget && d.cmax > 6) d.cmax -= 4;
     d.slots_a = 2 + 6;
     d.slots_c = 2 + std::max(nw, 6);
     if (const char *ev = getenv("FSB_EVENT_ROWS")) { d.slots_a = 2 + std::max(1, atoi(ev)); d.slots_c = 2 + std::max(nw, atoi(ev)); }
@@ -234,18 +244,31 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
         const int slots[3] = {d.slots_a, d.cmax + 2, d.slots_c};
         const void *kern[3] = {(const void *)fsb_events1_kernel, (const void *)fsb_pass_kernel, (const void *)fsb_events2_kernel};
         for (int k = 0; k < 3; ++k) {
-            const SmemLayout L = make_layout(d.K, d.Mp, d.N, d.cap_ev, slots[k], nw);
+            const SmemLayout L = make_layout(d.K, d.Mp, d.N, d.cap_ev, slots[k], nw, k == 1 ? d.ring_stages : 0);
             if (L.bytes + 64 > smem_max) { delete e; return fail(FSB_ERR_BAD_PARAMS, "shapes need %d bytes of shared memory per CTA (> %d)", L.bytes, smem_max); }
             e->smem_bytes[k] = L.bytes;
             CU(cudaFuncSetAttribute(kern[k], cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
             int occ = 0;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern[k], e->block, L.bytes));
             if (occ < 1) { delete e; return fail(FSB_ERR_CUDA, "step kernel %d cannot be resident (smem %d)", k, L.bytes); }
-            if (cfg->blocks_per_sm > 0) occ = std::min(occ, cfg->blocks_per_sm);
+            if (cfg->blocks_per_sm > 0 && k == 1) occ = std::min(occ, cfg->blocks_per_sm);
+            if (const char *ev = getenv(k == 1 ? "FSB_PASS_CTAS" : "FSB_EVENT_CTAS")) occ = std::min(occ, std::max(1, atoi(ev)));
+            e->occ[k] = occ;
             e->grid[k] = static_cast<int>(std::min<long long>(d.R, static_cast<long long>(sms) * occ));
         }
     }
     e->fast = (d.K <= 256);
+    // batches: with more than one, every kernel takes only a share of each SM so that kernels of different
+    // batches are co-resident (pass: 2 CTAs per SM, events: 3)
+    e->n_batches = (d.R >= 4096) ? 2 : 1;
+    if (const char *ev = getenv("FSB_BATCHES")) e->n_batches = std::max(1, std::min(8, atoi(ev)));
+    if (e->n_batches > d.R) e->n_batches = 1;
+    if (e->n_batches > 1) {
+        int share[3] = {3, 2, 3};
+        if (const char *ev = getenv("FSB_SHARE_EVENTS")) share[0] = share[2] = std::max(1, atoi(ev));
+        if (const char *ev = getenv("FSB_SHARE_PASS")) share[1] = std::max(1, atoi(ev));
+        for (int k = 0; k < 3; ++k) e->grid[k] = sms * std::min(e->occ[k], share[k]);
+    }
 
     // points + tables
     std::vector<double> tables;
@@ -284,12 +307,13 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     A(err, R); A(cnt, R * kCnt);
     A(mkt_peak, R); A(mkt_dd, R);
     A(flow_hist, R * kFlowBins);
-    A(scratch, static_cast<size_t>(std::max(e->grid[0], std::max(e->grid[1], e->grid[2]))) * d.cap_ev * d.Mp);
+    d.scratch_ctas = std::max(e->grid[0], std::max(e->grid[1], e->grid[2]));
+    A(scratch, static_cast<size_t>(3 * e->n_batches) * d.scratch_ctas * d.cap_ev * d.Mp);
     A(keys, R * d.kc * ((d.K + 3) & ~3));
     A(hand_i, R * d.hi_stride);
     A(hand_p, R * d.Mp);
     if (d.keep_history) A(hand_s, R * d.Mp);
-    A(queue, 6);
+    A(queue, 6 * 8);
 #undef A
     {
         DevPoint *pd = nullptr; double *td = nullptr, *rt = nullptr;
@@ -309,8 +333,15 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     e->z_mkt.assign(R, nullptr); e->z_stock.assign(R, nullptr); e->u_review.assign(R, nullptr);
     e->ev_tape.assign(R, nullptr); e->ev_n.assign(R, 0); e->trace_slot.assign(R, -1);
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess)
+        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming) != cudaSuccess)
         return cleanup(fail(FSB_ERR_CUDA, "cannot create stream/events"));
+    for (int b = 0; b < e->n_batches && e->n_batches > 1; ++b) {
+        cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
+            return cleanup(fail(FSB_ERR_CUDA, "cannot create batch streams"));
+        e->bstream.push_back(st); e->bjoin.push_back(ev);
+    }
     *out = e;
     return FSB_OK;
 }
@@ -321,6 +352,9 @@ extern "C" int32_t fsb_destroy(fsb_engine *e)
     cudaSetDevice(e->cfg.device);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void *p : e->allocs) cudaFree(p);
+    for (cudaStream_t st : e->bstream) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : e->bjoin) cudaEventDestroy(ev);
+    if (e->fork) cudaEventDestroy(e->fork);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -570,16 +604,31 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
         ++e->last_launches;
     }
     if (t_last >= t_first) {
-        CU(cudaMemsetAsync(d.queue, 0, 6 * sizeof(int), e->stream));
-        // one simulated day = three kernels on the engine's stream: events-1, holdings pass, events-2
-        for (int64_t t = t_first; t <= t_last; ++t) {
-            StepArgs a{static_cast<int>(t), 1, selector, flags};
-            fsb_events1_kernel<<<e->grid[0], e->block, e->smem_bytes[0], e->stream>>>(d, a, e->launch_parity);
-            fsb_pass_kernel<<<e->grid[1], e->block, e->smem_bytes[1], e->stream>>>(d, a, e->launch_parity);
-            fsb_events2_kernel<<<e->grid[2], e->block, e->smem_bytes[2], e->stream>>>(d, a, e->launch_parity);
-            e->launch_parity ^= 1;
-            e->last_launches += 3;
+        CU(cudaMemsetAsync(d.queue, 0, 6 * 8 * sizeof(int), e->stream));
+        // one simulated day = three kernels per replication batch (events-1, holdings pass, events-2), every
+        // batch on its own stream; the engine's stream forks before the first day and joins after the last
+        const int nb = e->n_batches;
+        if (nb > 1) {
+            CU(cudaEventRecord(e->fork, e->stream));
+            for (int b = 0; b < nb; ++b) CU(cudaStreamWaitEvent(e->bstream[b], e->fork, 0));
         }
+        for (int64_t t = t_first; t <= t_last; ++t) {
+            for (int b = 0; b < nb; ++b) {
+                cudaStream_t st = nb > 1 ? e->bstream[b] : e->stream;
+                StepArgs a{static_cast<int>(t), 1, selector, flags, b, (d.R * b) / nb, (d.R * (b + 1)) / nb};
+                const long long rb = a.r_end - a.r_begin;
+                fsb_events1_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[0])), e->block, e->smem_bytes[0], st>>>(d, a, e->launch_parity);
+                fsb_pass_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[1])), e->block, e->smem_bytes[1], st>>>(d, a, e->launch_parity);
+                fsb_events2_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[2])), e->block, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
+                e->last_launches += 3;
+            }
+            e->launch_parity ^= 1;
+        }
+        if (nb > 1)
+            for (int b = 0; b < nb; ++b) {
+                CU(cudaEventRecord(e->bjoin[b], e->bstream[b]));
+                CU(cudaStreamWaitEvent(e->stream, e->bjoin[b], 0));
+            }
         CU(cudaGetLastError());
         e->t_done = t_last;
     }

@@ -255,6 +255,7 @@ __device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, unsigned 
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Julia's isless on Float64: total order, -0.0 < +0.0, NaN last

@@ -29,6 +29,7 @@ struct DevState {
     int kc;         // key columns (distinct reinvestor horizons) a replication can have per step
     int hi_stride;  // ints per replication in hand_i
     int slots_a, slots_c;  // shared-memory column slots of the events-1 / events-2 kernels
+    int ring_stages;       // per-warp holdings ring of the pass kernel (kRingStages on the default shape, else 0)
     int n_points;
     long long R, rep_offset, reps_per_point;
     long long h_stride;  // doubles per replication in H
@@ -72,7 +73,8 @@ struct DevState {
     fsb_trace_rec *tr_recs;                // [slots][cap_trace]
     int *tr_n;                             // [slots]
     // per-CTA scratch + work queue
-    double *scratch;  // [grid][cap_ev][Mp] order rows beyond the shared-memory ones
+    double *scratch;  // [batches * 3][scratch_ctas][cap_ev][Mp] order rows beyond the shared-memory ones
+    int scratch_ctas;
     unsigned long long *keys;  // [R][kc][K4] horizon returns of the step being processed (pass kernel -> events-2 kernel)
     // handoff between the three kernels of a step (fsb_step.cuh)
     int *hand_i;               // [R][hi_stride]

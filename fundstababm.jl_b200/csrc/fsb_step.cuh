@@ -35,12 +35,16 @@ constexpr double kPriceFloor = 0.000000001;  // functions.jl:208-209 (Q10)
 constexpr int kMaxCols = 14;                 // horizon columns per full pass (4 groups x 4 columns, minus the 2 price columns)
 constexpr int kPfAheadDefault = 2;           // holdings rounds prefetched into L2 ahead of the loads (DevState::pf_ahead)
 constexpr int kStepThreads = 128;
+constexpr int kRingStages = 3;         // per-warp ring of holdings stages (pass kernel, default shape)
+constexpr int kStageBytes = 8 * 512;   // a stage = 8 rows x 4 word steps (512 bytes per row)
 #ifndef FSB_FP_INLINE
 #define FSB_FP_INLINE __forceinline__
 #endif
 
 struct StepArgs {
     int t_first, n_steps, selector, flags;
+    int batch;                 // replication batch (its own stream and work counters)
+    long long r_begin, r_end;  // replications [r_begin, r_end) of this engine
 };
 
 // shared-memory carve-up; sizes depend on the engine's shapes (host computes the same layout)
@@ -58,12 +62,13 @@ struct SmemLayout {
     int srows;  // order rows that fit in the staged-column region while it is not holding columns
     int wsd;    // doubles of that region per warp (member lists of the stake sequence)
     int ndoubles, nints, nshorts;
+    int off_ring, off_bars;  // byte offsets (pass kernel only)
     int bytes;
 };
 
 // nslots: column slots of `cols` (slot 0: opening prices, 1: current prices, 2..: staged history columns /
 // order rows / probability rows, depending on the kernel)
-__host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap, int nslots, int nwarps)
+__host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap, int nslots, int nwarps, int ring_stages = 0)
 {
     SmemLayout L;
     L.cp = (Mp + 127) & ~127;  // == Mp: the engine rounds Mp up to 128 itself
@@ -110,6 +115,9 @@ __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap,
     L.off_hor16 = h; h += (N + 7) & ~7;
     L.nshorts = h;
     L.bytes = 1024 /* kCtxBytes */ + d * 8 + i * 4 + h * 2 + 2 * ((K + 15) & ~15);  // Ctx + arrays + stl[K], hz[K] bytes
+    L.off_ring = (L.bytes + 127) & ~127;
+    L.off_bars = L.off_ring + nwarps * ring_stages * kStageBytes;
+    if (ring_stages > 0) L.bytes = L.off_bars + nwarps * ring_stages * 8 + nwarps * 8;  // + per-warp running stage counters
     return L;
 }
 
@@ -120,12 +128,12 @@ constexpr int kCtxBytes = 1024;
 // Phase functions receive a reference to it; thread-private ids are recomputed from threadIdx.
 struct Ctx {
     // shapes / configuration (copies of DevState fields)
-    int K, M, N, Mp, T, W, cap, cmax, keep_history, cap_log, cap_trace, fast, rank256, pf_ahead, kc;
+    int K, M, N, Mp, T, W, cap, cmax, keep_history, cap_log, cap_trace, fast, rank256, pf_ahead, kc, slot, ring_stages;
     int cp, cpk, kq, srows, wsd;
     // shared arrays: byte offsets into the dynamic shared memory (accessors below keep the address space known)
     int o_cols, o_ratio, o_sellsum, o_nav, o_d_stake, o_d_cash, o_r_inj, o_r_fval, o_r_ncap, o_scal;
     int o_rev, o_rfund, o_d_inv, o_d_fund, o_cash, o_r_choice, o_r_col, o_hcols, o_eggs, o_wl, o_wcnt, o_flags, o_nzf, o_pick, o_fmod, o_fsel, o_isc;
-    int o_pos16, o_hor16, o_stl, o_hz;
+    int o_pos16, o_hor16, o_stl, o_hz, o_ring, o_bars;
     unsigned long long *mbar;
     unsigned mbar_phase;
     // replication
@@ -224,7 +232,7 @@ struct Rep {
     int *hand_i;
     double *hand_p, *hand_s;
 };
-__device__ __forceinline__ Rep rep_ptrs(const DevState &s, const long long r, const int kq)
+__device__ __forceinline__ Rep rep_ptrs(const DevState &s, const long long r, const int kq, const int slot)
 {
     Rep g;
     g.H = s.H + r * s.h_stride;
@@ -239,7 +247,7 @@ __device__ __forceinline__ Rep rep_ptrs(const DevState &s, const long long r, co
     g.cnt = s.cnt + r * kCnt;
     g.mkt_peak = s.mkt_peak + r; g.mkt_dd = s.mkt_dd + r;
     g.flow_hist = s.flow_hist + r * kFlowBins;
-    g.scratch = s.scratch + static_cast<long long>(blockIdx.x) * s.cap_ev * s.Mp;
+    g.scratch = s.scratch + (static_cast<long long>(slot) * s.scratch_ctas + blockIdx.x) * (static_cast<long long>(s.cap_ev) * s.Mp);
     g.keys = s.keys + r * (static_cast<long long>(s.kc) * kq);
     g.hand_i = s.hand_i + r * s.hi_stride;
     g.hand_p = s.hand_p + r * s.Mp;
@@ -623,11 +631,9 @@ __device__ __noinline__ void warp_rank_count(const unsigned long long *keys, int
 // reduction of N partial sums over the 8 lanes of a group, transposing: after the butterfly steps
 // 4, 2, 1 every lane keeps only the sums it owns.  Each sum is formed as (own + partner's) at every
 // level, i.e. exactly the values of tree8() (IEEE addition commutes), with about a third of the shuffles.
-// Ownership afterwards (b2, b1, b0 = bits of the lane's position j in its group):
-//   N = 4 : v[0] = sum 2*b2 + b1                      (lane pairs hold the same sum)
-//   N = 8 : v[0] = sum 4*b2 + 2*b1 + b0 = j
-//   N = 12: v[0] = sum 6*b2 + 3*b1 + b0, v[1] = sum 6*b2 + 3*b1 + 2   (v[1] shared by a lane pair)
-//   N = 16: v[q] = sum 8*b2 + 4*b1 + 2*b0 + q, q = 0, 1
+// Ownership afterwards (b2, b1, b0 = bits of the lane's position j in its group), N a multiple of 8:
+//   v[q] = sum (N/2)*b2 + (N/4)*b1 + (N/8)*b0 + q,  q < N/8
+// and for N = 4: v[0] = sum 2*b2 + b1 (lane pairs hold the same sum).
 // ------------------------------------------------------------------------------------------------
 template <int N, int n>
 __device__ __forceinline__ void halve(double (&v)[N], const bool b, const int mask)
@@ -647,117 +653,89 @@ __device__ __forceinline__ void halve(double (&v)[N], const bool b, const int ma
 template <int N>
 __device__ __forceinline__ void reduce8_transposed(double (&v)[N], int j)
 {
-    static_assert(N == 4 || N == 8 || N == 12 || N == 16, "unsupported tile");
+    static_assert(N == 4 || (N % 8) == 0, "unsupported tile");
     const bool b2 = (j & 4) != 0, b1 = (j & 2) != 0, b0 = (j & 1) != 0;
     halve<N, N>(v, b2, 4);
     halve<N, N / 2>(v, b1, 2);
-    halve<N, N / 4>(v, b0, 1);   // N/4 = 1 (N=4), 2 (8), 3 (12), 4 (16)
+    halve<N, N / 4>(v, b0, 1);
 }
 template <int N>
 __device__ __forceinline__ int owned_sum(int j, int q)  // index of the sum in v[q] after reduce8_transposed
 {
     const int b2 = (j >> 2) & 1, b1 = (j >> 1) & 1, b0 = j & 1;
     if (N == 4) return 2 * b2 + b1;
-    if (N == 8) return j;
-    if (N == 12) return 6 * b2 + 3 * b1 + (q == 0 ? b0 : 2);
-    return 8 * b2 + 4 * b1 + 2 * b0 + q;
+    return (N / 2) * b2 + (N / 4) * b1 + (N / 8) * b0 + q;
 }
 
 // ------------------------------------------------------------------------------------------------
-// the full pass: every holdings row against the shared-memory columns cb .. cb + 4*NCG - 1.
-// A round of a warp = 4 consecutive rows.  Lane (g, j): g = lane / 8 owns the columns cb + g + 4*cc,
-// j = lane % 8 owns the double2 words j, j+8, ... of a row (the canonical chains).  All four groups load
-// the same holdings words (one 128-byte request per row and step, served once), every group a different
-// column word: 8 FMAs per 128-bit shared-memory load.  The loop runs over the zero-padded pitch cp
-// (fma(0, 0, acc) == acc exactly).  Holdings are loaded four steps ahead of their use (register ring,
-// loop body = 4 steps so that the ring is indexed statically) and rounds are L2-prefetched pf_ahead
-// rounds ahead.
-// OPEN: only column 0 (a day without divestments): every group owns its own round of 4 rows instead.
+// the holdings pass: every holdings row against the shared-memory columns cb .. cb + 2*C - 1.
+// A trip of a warp = 8 consecutive rows.  The warp's four 8-lane groups form a 2 x 2 arrangement:
+// group (qa, qb) owns the rows 4*qa .. 4*qa+3 of the trip and the columns cb + qb + 2*cc, cc < C; lane j of
+// a group owns the double2 words j, j+8, ... of a row (the canonical chains).  Per word step a lane issues
+// 4 holdings loads and C column loads for 8*C FMAs; a 128-bit load costs the LSU four wavefronts however
+// many lanes share an address, and this arrangement needs the fewest of them per row ((4 + C) * 4 per
+// 8 rows, against (4 + C/2) * 4 per 4 rows when every group reads all rows).
+// The loop runs over the zero-padded pitch (Mp is a multiple of 128: no tails, no masks).  Holdings are
+// loaded D steps ahead of their use (register ring, loop body = D steps so that the ring is indexed
+// statically).
+// OPEN: only column 0 (a day without divestments): every group owns 4 rows of a 16-row trip instead.
 // Results: column 0 -> nav_open (unless the row was modified before this pass: its opening NAV was
 // taken in the review pass), column 1 -> nav / nav_close, column q >= 2 -> horizon return
 // (nav - vh) / vh (:375-379), stored as its order-preserving 64-bit key (rank rule) or as raw bits.
 // ------------------------------------------------------------------------------------------------
-template <int NCG, bool OPEN, bool FAST>
+template <int C, bool OPEN, bool FAST>
 __device__ FSB_FP_INLINE void full_pass(const DevState &s, const int cb, const int nreal, const int want_keys, const int kcol0)
 {
+    constexpr int R = 4;                    // rows per lane
+    constexpr int D = (C >= 8) ? 2 : 4;     // ring depth in word steps
+    constexpr int NS = OPEN ? R : R * C;    // partial sums per lane
     Ctx &c = ctx();
-    const Rep G = rep_ptrs(s, c.r, c.kq);
-    constexpr int R = 4;
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
     const int K = c.K;
-    const int half = FAST ? 128 : (c.Mp >> 1);     // double2 words per row (Mp is a multiple of 128: no tail, no masks)
+    const int half = FAST ? 128 : (c.Mp >> 1);     // double2 words per row
     const int cstride = FAST ? 128 : (c.cpk >> 1);  // double2 words per shared-memory column
     const int nsteps = FAST ? 16 : (c.Mp >> 4);     // word steps per row: a multiple of 8
-    const int j = lane & 7, g = lane >> 3;
-    const int nrounds = (K + R - 1) / R;  // rounds of 4 rows (rows K.. of the last one are zero padding)
-    const double2 *colp = reinterpret_cast<const double2 *>(c.cols_()) + (OPEN ? 0 : (cb + g)) * cstride + j;
+    const int j = lane & 7, q4 = lane >> 3;
+    const int qa = OPEN ? q4 : (q4 >> 1), qb = OPEN ? 0 : (q4 & 1);
+    constexpr int rows_per_trip = OPEN ? 16 : 8;
+    const int K4 = (K + 3) & ~3;
+    const int ntrips = (K4 + rows_per_trip - 1) / rows_per_trip;
+    const double2 *colp = reinterpret_cast<const double2 *>(c.cols_()) + (cb + qb) * cstride + j;
     const double2 *H2 = reinterpret_cast<const double2 *>(G.H) + j;
-    // the unit a warp pulls per trip: OPEN: 4 rounds (one per group), else 1 round
-    constexpr int upw = OPEN ? 4 : 1;
-    const int ntrips = (nrounds + upw - 1) / upw;
-    auto round_of = [&](int trip) { return OPEN ? 4 * trip + g : trip; };
     auto rowptr = [&](int trip) {
-        int rd = round_of(trip);
-        if (rd >= nrounds) rd = nrounds - 1;  // (idle group of the last OPEN trip re-reads the last round)
-#ifdef FSB_EXPERIMENTS
-        if (c.pf_ahead == 99) rd = 0;  // timing experiment: L2-hot holdings (results are wrong)
-#endif
-        return H2 + static_cast<long long>(rd) * R * half;
+        int r0 = trip * rows_per_trip + R * qa;
+        if (r0 >= K4) r0 = K4 - R;  // (idle group of the last trip re-reads the last rows)
+        return H2 + static_cast<long long>(r0) * half;
     };
     int trip = warp;
     if (trip >= ntrips) return;
-    double2 hb[4][R];
+    double2 hb[D][R];
     auto load = [&](double2(&dst)[R], const double2 *rp, int w) {  // w = first word of the step
 #pragma unroll
         for (int r = 0; r < R; ++r) dst[r] = __ldcg(rp + r * half + w);
     };
     const double2 *cur = rowptr(trip);
 #pragma unroll
-    for (int st = 0; st < 4; ++st) load(hb[st], cur, 8 * st);
+    for (int st = 0; st < D; ++st) load(hb[st], cur, 8 * st);
     const double *const keep_nav = c.nav_();
-    const long long rowbytes = static_cast<long long>(c.Mp) * 8;
 #pragma unroll 1
     for (; trip < ntrips; trip += nwarps) {
-        {   // L2 prefetch of the round(s) this warp reads pf_ahead trips from now
-            const int pfd = c.pf_ahead % 100, pfm = c.pf_ahead / 100;
-            const int tp = trip + pfd * nwarps;
-            if (pfd > 0 && tp < ntrips) {
-                const int r0 = upw * tp * R;
-                const int nr = min(upw * R, ((K + 3) & ~3) - r0);
-                const char *src = reinterpret_cast<const char *>(G.H) + r0 * rowbytes;
-                if (pfm == 0) {
-                    if (lane == 0) l2_prefetch_bulk(src, static_cast<unsigned>(nr * rowbytes));
-                } else if (pfm == 1) {  // one 128-byte line per lane and instruction
-                    for (long long off = lane * 128LL; off < nr * rowbytes; off += 32 * 128)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off));
-                } else if (pfm == 2) {  // touch loads: real loads whose result is never used (one sector per line)
-                    for (long long off = lane * 128LL; off < nr * rowbytes; off += 32 * 128) {
-                        unsigned dummy;
-                        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(dummy) : "l"(src + off));
-                    }
-                } else {                // touch loads covering every 32-byte sector
-                    for (long long off = lane * 32LL; off < nr * rowbytes; off += 32 * 32) {
-                        unsigned dummy;
-                        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(dummy) : "l"(src + off));
-                    }
-                }
-            }
-        }
         const int tn = (trip + nwarps < ntrips) ? trip + nwarps : trip;
         const double2 *nxt = rowptr(tn);
-        double acc[R * NCG];
+        double acc[NS];
 #pragma unroll
-        for (int q = 0; q < R * NCG; ++q) acc[q] = 0.0;
+        for (int q = 0; q < NS; ++q) acc[q] = 0.0;
         const double2 *cp_i = colp;
 #pragma unroll 1
-        for (int i0 = 0; i0 < nsteps; i0 += 4) {
-            // the ring is refilled 4 steps ahead: from this row block, or from the next trip's on the last iteration
-            const double2 *lp = (i0 + 4 < nsteps) ? cur + 8 * (i0 + 4) : nxt;
+        for (int i0 = 0; i0 < nsteps; i0 += D) {
+            // the ring is refilled D steps ahead: from this row block, or from the next trip's on the last iteration
+            const double2 *lp = (i0 + D < nsteps) ? cur + 8 * (i0 + D) : nxt;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < D; ++q) {
 #pragma unroll
-                for (int cc = 0; cc < NCG; ++cc) {
-                    const double2 p = cp_i[4 * cc * cstride + 8 * q];
+                for (int cc = 0; cc < (OPEN ? 1 : C); ++cc) {
+                    const double2 p = cp_i[2 * cc * cstride + 8 * q];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         acc[r + R * cc] = fma(hb[q][r].x, p.x, acc[r + R * cc]);
@@ -766,28 +744,27 @@ __device__ FSB_FP_INLINE void full_pass(const DevState &s, const int cb, const i
                 }
                 load(hb[q], lp, 8 * q);
             }
-            cp_i += 32;
+            cp_i += 8 * D;
         }
         cur = nxt;
         // ---- epilogue ----------------------------------------------------------------------------
-        reduce8_transposed<R * NCG>(acc, j);
-        constexpr int NF = (R * NCG > 8) ? 2 : 1;
-        const int rd = round_of(trip);
+        reduce8_transposed<NS>(acc, j);
+        constexpr int NF = (NS >= 8) ? NS / 8 : 1;
+        const int row0 = trip * rows_per_trip + R * qa;
         int own[NF];
 #pragma unroll
-        for (int q = 0; q < NF; ++q) own[q] = owned_sum<R * NCG>(j, q);
+        for (int q = 0; q < NF; ++q) own[q] = owned_sum<NS>(j, q);
         if (OPEN) {
-            const int k = rd * R + own[0];
-            if (rd < nrounds && k < K && (j & 1) == 0) { G.nav_open[k] = acc[0]; G.nav_close[k] = acc[0]; }
+            const int k = row0 + own[0];
+            if (k < K && (j & 1) == 0) { G.nav_open[k] = acc[0]; G.nav_close[k] = acc[0]; }
             continue;
         }
         // column 1 first: the day's NAV is the numerator of every horizon return of the row
         if (cb == 0) {
 #pragma unroll
             for (int q = 0; q < NF; ++q) {
-                const int col = g + 4 * (own[q] >> 2), k = rd * R + (own[q] & 3);
-                const bool mine = (R * NCG == 4 || (R * NCG == 12 && q == 1)) ? ((j & 1) == 0) : true;
-                if (mine && k < K) {
+                const int col = qb + 2 * (own[q] >> 2), k = row0 + (own[q] & 3);
+                if (k < K) {
                     if (col == 0) {
                         if (!((c.fmod_()[k >> 5] >> (k & 31)) & 1)) G.nav_open[k] = acc[q];
                     } else if (col == 1) {
@@ -800,34 +777,153 @@ __device__ FSB_FP_INLINE void full_pass(const DevState &s, const int cb, const i
         }
 #pragma unroll
         for (int q = 0; q < NF; ++q) {
-            const int col = cb + g + 4 * (own[q] >> 2), k = rd * R + (own[q] & 3);
-            const bool mine = (R * NCG == 4 || (R * NCG == 12 && q == 1)) ? ((j & 1) == 0) : true;
-            if (col >= 2 && col - cb < nreal && k < K) {   // (all lanes divide; only the owner stores)
+            const int col = cb + qb + 2 * (own[q] >> 2), k = row0 + (own[q] & 3);
+            if (col >= 2 && col - cb < nreal && k < K) {
                 const double navk = keep_nav[k], v = acc[q];
                 const double rho = ddiv(navk - v, v);
                 const unsigned long long word = want_keys ? sort_key(rho) : static_cast<unsigned long long>(__double_as_longlong(rho));
-                if (mine) __stcg(G.keys + static_cast<long long>(kcol0 + col - 2) * c.kq + k, word);
+                __stcg(G.keys + static_cast<long long>(kcol0 + col - 2) * c.kq + k, word);
             }
         }
     }
 }
 
-// nc columns starting at cb are processed by the instantiation with ceil(nc / 4) columns per group
+// ------------------------------------------------------------------------------------------------
+// the holdings pass of the default shape (Mp == 256, K <= 256), fed by the TMA unit: same arithmetic and
+// lane arrangement as full_pass<C>, but the holdings reach the lanes through a per-warp ring of
+// kRingStages stages in shared memory.  A stage = 8 rows x 4 word steps (8 x 512 bytes) fetched by eight
+// bulk asynchronous copies (lanes 0..7 issue one row each) that complete on the stage's mbarrier; the
+// ring runs kRingStages - 1 stages (8 KB per warp) ahead of the arithmetic, which the register ring of
+// full_pass cannot afford, so the loads no longer stall the FMA stream (ncu: stall_long_scoreboard was
+// the top stall of the pass).  Reading a holdings word from shared memory costs the LSU the same four
+// wavefronts as the global load did.
+// open_day: a day without divestments; column 0 gives nav_open AND nav_close (column 1 is not staged).
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, const int nreal, const int want_keys, const int kcol0, const int open_day)
+{
+    constexpr int R = 4, NS = R * C, S = kRingStages;
+    Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
+    FSB_TH;
+    const int K = c.K, K4 = (K + 3) & ~3;
+    const int j = lane & 7, q4 = lane >> 3, qa = q4 >> 1, qb = q4 & 1;
+    const int ntrips = (K4 + 7) >> 3;
+    const int my_trips = (ntrips - warp + nwarps - 1) / nwarps;
+    if (my_trips <= 0) return;
+    const int nstages = my_trips * 4;
+    unsigned char *ring = fsb_smem + c.o_ring + warp * (S * kStageBytes);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(fsb_smem + c.o_bars) + warp * S;
+    // the ring's mbarriers are initialised once per kernel; gbase = stages this warp has consumed so far
+    // (slot and phase parity of a stage follow from its running index)
+    long long *gcount = reinterpret_cast<long long *>(fsb_smem + c.o_bars + nwarps * S * 8) + warp;
+    const long long gbase = *gcount;
+    const char *Hb = reinterpret_cast<const char *>(G.H);
+    auto issue = [&](int g) {  // stage g of this warp's sequence -> slot g % S
+        const int slot = static_cast<int>((gbase + g) % S), tg = warp + (g >> 2) * nwarps, part = g & 3;
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bars + slot, kStageBytes);
+        }
+        if (lane < 8) {
+            int row = 8 * tg + lane;
+            if (row >= K4) row = K4 - 1;  // (rows past the last one re-read it; their results are dropped)
+            bulk_g2s(ring + slot * kStageBytes + lane * 512, Hb + static_cast<long long>(row) * 2048 + part * 512, 512, bars + slot);
+        }
+    };
+#pragma unroll 1
+    for (int g = 0; g < S - 1 && g < nstages; ++g) issue(g);
+    const double2 *colp = reinterpret_cast<const double2 *>(c.cols_()) + (cb + qb) * 128 + j;
+    const double *const keep_nav = c.nav_();
+#pragma unroll 1
+    for (int g0 = 0; g0 < nstages; g0 += 4) {
+        double acc[NS];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) acc[q] = 0.0;
+#pragma unroll 1
+        for (int part = 0; part < 4; ++part) {
+            const int g = g0 + part;
+            if (g + S - 1 < nstages) issue(g + S - 1);
+            const int slot = static_cast<int>((gbase + g) % S);
+            mbar_wait(bars + slot, static_cast<unsigned>(((gbase + g) / S) & 1));
+            const double2 *hs = reinterpret_cast<const double2 *>(ring + slot * kStageBytes) + (R * qa) * 32 + j;
+            const double2 *cp_i = colp + 32 * part;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double2 h[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) h[r] = hs[r * 32 + 8 * q];
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) {
+                    const double2 p = cp_i[2 * cc * 128 + 8 * q];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        acc[r + R * cc] = fma(h[r].x, p.x, acc[r + R * cc]);
+                        acc[r + R * cc] = fma(h[r].y, p.y, acc[r + R * cc]);
+                    }
+                }
+            }
+        }
+        const int g = g0 + 3;
+        // ---- epilogue of the trip -----------------------------------------------------------------
+        reduce8_transposed<NS>(acc, j);
+        constexpr int NF = NS / 8;
+        const int row0 = 8 * (warp + (g >> 2) * nwarps) + R * qa;
+        int own[NF];
+#pragma unroll
+        for (int q = 0; q < NF; ++q) own[q] = owned_sum<NS>(j, q);
+        if (cb == 0) {  // column 1 first: the day's NAV is the numerator of every horizon return of the row
+#pragma unroll
+            for (int q = 0; q < NF; ++q) {
+                const int col = qb + 2 * (own[q] >> 2), k = row0 + (own[q] & 3);
+                if (k < K) {
+                    if (col == 0) {
+                        if (!((c.fmod_()[k >> 5] >> (k & 31)) & 1)) G.nav_open[k] = acc[q];
+                        if (open_day) G.nav_close[k] = acc[q];
+                    } else if (col == 1 && !open_day) {
+                        c.nav_()[k] = acc[q];
+                        G.nav_close[k] = acc[q];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < NF; ++q) {
+            const int col = cb + qb + 2 * (own[q] >> 2), k = row0 + (own[q] & 3);
+            if (col >= 2 && col - cb < nreal && k < K) {
+                const double navk = keep_nav[k], v = acc[q];
+                const double rho = ddiv(navk - v, v);
+                const unsigned long long word = want_keys ? sort_key(rho) : static_cast<unsigned long long>(__double_as_longlong(rho));
+                __stcg(G.keys + static_cast<long long>(kcol0 + col - 2) * c.kq + k, word);
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *gcount = gbase + nstages;
+    __syncwarp();
+}
+
+// nc columns starting at cb are processed by the instantiation with C = 2, 4, 6 or 8 columns per lane
 // (spare columns of finite stale data are multiplied and dropped: cols[] always holds cmax + 2 columns).
 // c.fast: Mp == 256 and K <= 256 (the default shape): strides and trip counts are compile-time constants.
 __device__ __forceinline__ void full_pass_dispatch(const DevState &s, Ctx &c, int cb, int nc, int want_keys, int kcol0)
 {
-    const int ncg = (nc + 3) >> 2;
-    if (c.fast) {
-        if (ncg <= 1) full_pass<1, false, true>(s, cb, nc, want_keys, kcol0);
-        else if (ncg == 2) full_pass<2, false, true>(s, cb, nc, want_keys, kcol0);
-        else if (ncg == 3) full_pass<3, false, true>(s, cb, nc, want_keys, kcol0);
-        else full_pass<4, false, true>(s, cb, nc, want_keys, kcol0);
+    if (c.fast && c.ring_stages > 0) {
+        if (nc <= 4) full_pass_tma<2>(s, cb, nc, want_keys, kcol0, 0);
+        else if (nc <= 8) full_pass_tma<4>(s, cb, nc, want_keys, kcol0, 0);
+        else if (nc <= 12) full_pass_tma<6>(s, cb, nc, want_keys, kcol0, 0);
+        else full_pass_tma<8>(s, cb, nc, want_keys, kcol0, 0);
+    } else if (c.fast) {
+        if (nc <= 4) full_pass<2, false, true>(s, cb, nc, want_keys, kcol0);
+        else if (nc <= 8) full_pass<4, false, true>(s, cb, nc, want_keys, kcol0);
+        else if (nc <= 12) full_pass<6, false, true>(s, cb, nc, want_keys, kcol0);
+        else full_pass<8, false, true>(s, cb, nc, want_keys, kcol0);
     } else {
-        if (ncg <= 1) full_pass<1, false, false>(s, cb, nc, want_keys, kcol0);
-        else if (ncg == 2) full_pass<2, false, false>(s, cb, nc, want_keys, kcol0);
-        else if (ncg == 3) full_pass<3, false, false>(s, cb, nc, want_keys, kcol0);
-        else full_pass<4, false, false>(s, cb, nc, want_keys, kcol0);
+        if (nc <= 4) full_pass<2, false, false>(s, cb, nc, want_keys, kcol0);
+        else if (nc <= 8) full_pass<4, false, false>(s, cb, nc, want_keys, kcol0);
+        else if (nc <= 12) full_pass<6, false, false>(s, cb, nc, want_keys, kcol0);
+        else full_pass<8, false, false>(s, cb, nc, want_keys, kcol0);
     }
 }
 
@@ -849,7 +945,7 @@ __device__ __forceinline__ int chunk_list_get(const Ctx &c, int nwarps, int i)
 __device__ FSB_FP_INLINE void phase_shocks(const DevState &s, const int t)
 {
     Ctx &c = ctx();
-    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
     const int K = c.K, M = c.M, N = c.N, Mp = c.Mp, cap = c.cap, hp = c.cp >> 1;
     const double *Pprev = G.P + static_cast<long long>(pcol(c, t - 1)) * Mp;
@@ -964,7 +1060,7 @@ __device__ FSB_FP_INLINE void phase_shocks(const DevState &s, const int t)
 __device__ FSB_FP_INLINE int phase_review(const DevState &s, const int t)
 {
     Ctx &c = ctx();
-    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
     const int K = c.K, Mp = c.Mp, cap = c.cap, half = Mp >> 1;
     const int j8 = lane & 7, g4 = lane >> 3;
@@ -1054,7 +1150,7 @@ __device__ FSB_FP_INLINE int phase_review(const DevState &s, const int t)
 __device__ FSB_FP_INLINE int phase_liquidate(const DevState &s, const int t, const int nd)
 {
     Ctx &c = ctx();
-    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
     const int K = c.K, M = c.M, N = c.N, Mp = c.Mp;
     const int j8 = lane & 7, g4 = lane >> 3;
@@ -1457,7 +1553,7 @@ __device__ __noinline__ int phase_respawn(const int t, const int nd, const int f
 __device__ FSB_FP_INLINE int phase_cashlist(const DevState &s, const int nd)
 {
     Ctx &c = ctx();
-    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
     const int K = c.K, N = c.N, cap = c.cap;
     if (warp == 0) {
@@ -1512,7 +1608,7 @@ __device__ FSB_FP_INLINE int phase_cashlist(const DevState &s, const int nd)
 __device__ FSB_FP_INLINE void phase_stage_columns(const DevState &s, const int t, const int c0, const int nc, const bool first, const bool open_day)
 {
     Ctx &c = ctx();
-    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
     const int Mp = c.Mp;
     const int ncopies = nc + (first ? (open_day ? 1 : 2) : 0);
@@ -1542,7 +1638,7 @@ __device__ FSB_FP_INLINE void phase_stage_columns(const DevState &s, const int t
 __device__ FSB_FP_INLINE void phase_choice(const DevState &s, const int t, const int ncols, const int ncash, const int selector)
 {
     Ctx &c = ctx();
-    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
     const int K = c.K;
     if (selector == FSB_SEL_PROBABILISTIC) {
@@ -1581,7 +1677,7 @@ __device__ FSB_FP_INLINE void phase_choice(const DevState &s, const int t, const
 __device__ FSB_FP_INLINE void phase_reinvest(const DevState &s, const int t, const int ncash, const int flags)
 {
     Ctx &c = ctx();
-    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
     const int K = c.K, M = c.M, N = c.N, Mp = c.Mp, cap = c.cap;
     const int j8 = lane & 7, g4 = lane >> 3;
@@ -1711,7 +1807,7 @@ __device__ FSB_FP_INLINE void phase_reinvest(const DevState &s, const int t, con
 __device__ FSB_FP_INLINE void phase_store_prices(const DevState &s, const int t)
 {
     Ctx &c = ctx();
-    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
     const int half = c.Mp >> 1;
     double *Pt = G.P + static_cast<long long>(pcol(c, t)) * c.Mp;
@@ -1739,7 +1835,7 @@ enum { KIND_EVENTS1 = 0, KIND_PASS = 1, KIND_EVENTS2 = 2 };
 __device__ __forceinline__ void step_events1(const DevState &s, Ctx &c, const int t, const int flags)
 {
     FSB_TH;
-    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     const bool traced = (c.trace >= 0);
     const int nf = (c.K + 31) / 32, cap = c.cap, half = c.Mp >> 1;
     phase_shocks(s, t);
@@ -1789,7 +1885,7 @@ __device__ __forceinline__ void step_events1(const DevState &s, Ctx &c, const in
 __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t, const int selector)
 {
     FSB_TH;
-    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     const int nf = (c.K + 31) / 32;
     const int *hi = G.hand_i;
     if (hi[HI_T] != t) return;  // (events-1 stopped this replication: its error flag is set)
@@ -1799,7 +1895,8 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
     __syncthreads();
     if (open_day) {  // nav_open = nav_close = H * p_open
         phase_stage_columns(s, t, 0, 0, true, true);
-        if (c.fast) full_pass<1, true, true>(s, 0, 1, 0, 0);
+        if (c.fast && c.ring_stages > 0) full_pass_tma<2>(s, 0, 1, 0, 0, 1);
+        else if (c.fast) full_pass<1, true, true>(s, 0, 1, 0, 0);
         else full_pass<1, true, false>(s, 0, 1, 0, 0);
     } else {
         const int cmax = c.cmax;
@@ -1824,7 +1921,7 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
 __device__ __forceinline__ void step_events2(const DevState &s, Ctx &c, const int t, const int selector, const int flags)
 {
     FSB_TH;
-    const Rep G = rep_ptrs(s, c.r, c.kq);
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     const int K = c.K, N = c.N, cap = c.cap, nf = (K + 31) / 32, half = c.Mp >> 1;
     const int *hi = G.hand_i;
     if (hi[HI_T] != t || hi[HI_OPEN]) return;
@@ -1870,7 +1967,7 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
     __shared__ __align__(8) unsigned long long mbar_sh;
     const int nwarps = blockDim.x >> 5;
     const int nslots = (KIND == KIND_PASS) ? s.cmax + 2 : (KIND == KIND_EVENTS1 ? s.slots_a : s.slots_c);
-    const SmemLayout L = make_layout(s.K, s.Mp, s.N, s.cap_ev, nslots, nwarps);
+    const SmemLayout L = make_layout(s.K, s.Mp, s.N, s.cap_ev, nslots, nwarps, (KIND == KIND_PASS) ? s.ring_stages : 0);
     double *sd = reinterpret_cast<double *>(fsb_smem + kCtxBytes);
     if (threadIdx.x == 0) {
         c.K = s.K; c.M = s.M; c.N = s.N; c.Mp = s.Mp; c.T = s.T; c.W = s.W; c.cap = s.cap_ev; c.cmax = s.cmax;
@@ -1880,6 +1977,7 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         c.fast = (s.K <= 256 && s.Mp == 256) ? 1 : 0;
         c.pf_ahead = s.pf_ahead;
         c.kc = s.kc;
+        c.ring_stages = (KIND == KIND_PASS) ? s.ring_stages : 0;
         const int bd = kCtxBytes, bi = bd + 8 * L.ndoubles, bs = bi + 4 * L.nints;  // byte offsets of the double / int / 16-bit regions
         c.o_cols = bd + 8 * L.off_cols; c.o_ratio = bd + 8 * L.off_ratio; c.o_sellsum = bd + 8 * L.off_sellsum;
         c.o_nav = bd + 8 * L.off_nav; c.o_d_stake = bd + 8 * L.off_dstake; c.o_d_cash = bd + 8 * L.off_dcash;
@@ -1891,23 +1989,31 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         c.o_pos16 = bs + 2 * L.off_pos16; c.o_hor16 = bs + 2 * L.off_hor16;
         c.o_stl = bs + 2 * L.nshorts;
         c.o_hz = c.o_stl + ((s.K + 15) & ~15);
+        c.o_ring = L.off_ring; c.o_bars = L.off_bars;
         c.mbar = &mbar_sh; c.mbar_phase = 0;
         c.tmark = clock64();
-        c.scratch = s.scratch + static_cast<long long>(blockIdx.x) * s.cap_ev * s.Mp;
+        c.slot = 3 * a.batch + KIND;  // concurrently running kernels (batches x kinds) get disjoint per-CTA scratch
+        c.scratch = s.scratch + (static_cast<long long>(c.slot) * s.scratch_ctas + blockIdx.x) * (static_cast<long long>(s.cap_ev) * s.Mp);
         c.ranktab = s.ranktab;
         c.rng.k0 = static_cast<uint32_t>(s.seed); c.rng.k1 = static_cast<uint32_t>(s.seed >> 32);
         mbar_init(&mbar_sh, 1);
+        if (KIND == KIND_PASS && s.ring_stages > 0) {
+            unsigned long long *rb = reinterpret_cast<unsigned long long *>(fsb_smem + L.off_bars);
+            for (int q = 0; q < nwarps * s.ring_stages; ++q) mbar_init(rb + q, 1);
+            for (int q = 0; q < nwarps; ++q) rb[nwarps * s.ring_stages + q] = 0ULL;
+        }
+        fence_mbar_init();
     }
     for (int q = threadIdx.x; q < L.ndoubles; q += blockDim.x) sd[q] = 0.0;  // zero pads once
     __syncthreads();
 
-    int *const queue = s.queue + 2 * KIND;
+    int *const queue = s.queue + 2 * (3 * a.batch + KIND);
     if (blockIdx.x == 0 && threadIdx.x == 0) queue[launch_parity ^ 1] = 0;  // reset the next launch's counter
     for (;;) {
         if (threadIdx.x == 0) r_sh = atomicAdd(&queue[launch_parity], 1);
         __syncthreads();
-        const long long r = r_sh;
-        if (r >= s.R) break;
+        const long long r = a.r_begin + r_sh;
+        if (r >= a.r_end) break;
         const int frozen = s.err[r] & ~FSB_REP_TRACE_OVERFLOW;
         if (threadIdx.x == 0 && !frozen) {
             const long long g = s.rep_offset + r;
@@ -1961,7 +2067,10 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
     }
 }
 
-__global__ void __launch_bounds__(kStepThreads, 4) fsb_events1_kernel(const DevState s, const StepArgs a, const int launch_parity)
+#ifndef FSB_EV_CTAS
+#define FSB_EV_CTAS 6
+#endif
+__global__ void __launch_bounds__(kStepThreads, FSB_EV_CTAS) fsb_events1_kernel(const DevState s, const StepArgs a, const int launch_parity)
 {
     phase_kernel_body<KIND_EVENTS1>(s, a, launch_parity);
 }
@@ -1969,7 +2078,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) fsb_pass_kernel(const DevStat
 {
     phase_kernel_body<KIND_PASS>(s, a, launch_parity);
 }
-__global__ void __launch_bounds__(kStepThreads, 4) fsb_events2_kernel(const DevState s, const StepArgs a, const int launch_parity)
+__global__ void __launch_bounds__(kStepThreads, FSB_EV_CTAS) fsb_events2_kernel(const DevState s, const StepArgs a, const int launch_parity)
 {
     phase_kernel_body<KIND_EVENTS2>(s, a, launch_parity);
 }

@@ -3,5 +3,5 @@
 VAR=$1; shift
 for v in "$@"; do
   echo "== $VAR=$v"
-  env $VAR=$v timeout 600 python scripts/prof_step.py --reps 16384 --steps 8 --t0 300 2>&1 | tail -1
+  env $VAR=$v timeout 120 python scripts/prof_step.py --reps 16384 --steps 8 --t0 300 2>&1 | tail -1
 done
