@@ -96,7 +96,7 @@ struct fsb_engine {
     std::vector<cudaEvent_t> bjoin;
     cudaEvent_t fork = nullptr;
     int occ[3] = {1, 1, 1};
-    int grid[3] = {0, 0, 0}, block = 256, smem_bytes[3] = {0, 0, 0}, init_smem = 0;
+    int grid[3] = {0, 0, 0}, block = 256, block_pass = 256, smem_bytes[3] = {0, 0, 0}, init_smem = 0;
     int launch_parity = 0;
     bool fast = false;
     bool log_built = false, state_set = false;
@@ -220,6 +220,9 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     CU(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     const int nw = e->block / 32;
+    e->block_pass = (d.K <= 256 && d.Mp == 256 && !getenv("FSB_NO_TMA")) ? kPassThreads : e->block;
+    if (const char *ev = getenv("FSB_PASS_THREADS")) e->block_pass = std::max(32, std::min(kPassThreads, (atoi(ev) / 32) * 32));
+    const int nwp = e->block_pass / 32;
     d.ring_stages = (d.K <= 256 && d.Mp == 256) ? kRingStages : 0;
     if (getenv("FSB_NO_TMA")) d.ring_stages = 0;
     int want_ctas = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : (d.ring_stages ? 2 : 4);
@@ -230,7 +233,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     if (const char *ev = getenv("FSB_PF_AHEAD")) d.pf_ahead = std::max(0, atoi(ev));
     if (const char *ev = getenv("FSB_CMAX")) d.cmax = std::min(kMaxCols, std::max(6, ((atoi(ev) + 2) / 4) * 4 - 2));
     // (a chunk after the first holds cmax - 2 columns: cmax stays >= 6)
-    while (make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax + 2, nw, d.ring_stages).bytes + 64 > budget && d.cmax > 6) d.cmax -= 4;
+    while (make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax + 2, nwp, d.ring_stages).bytes + 64 > budget && d.cmax > 6) d.cmax -= 4;
     d.slots_a = 2 + 6;
     d.slots_c = 2 + std::max(nw, 6);
     if (const char *ev = getenv("FSB_EVENT_ROWS")) { d.slots_a = 2 + std::max(1, atoi(ev)); d.slots_c = 2 + std::max(nw, atoi(ev)); }
@@ -244,12 +247,13 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
         const int slots[3] = {d.slots_a, d.cmax + 2, d.slots_c};
         const void *kern[3] = {(const void *)fsb_events1_kernel, (const void *)fsb_pass_kernel, (const void *)fsb_events2_kernel};
         for (int k = 0; k < 3; ++k) {
-            const SmemLayout L = make_layout(d.K, d.Mp, d.N, d.cap_ev, slots[k], nw, k == 1 ? d.ring_stages : 0);
+            const int blk = (k == 1) ? e->block_pass : e->block;
+            const SmemLayout L = make_layout(d.K, d.Mp, d.N, d.cap_ev, slots[k], blk / 32, k == 1 ? d.ring_stages : 0);
             if (L.bytes + 64 > smem_max) { delete e; return fail(FSB_ERR_BAD_PARAMS, "shapes need %d bytes of shared memory per CTA (> %d)", L.bytes, smem_max); }
             e->smem_bytes[k] = L.bytes;
             CU(cudaFuncSetAttribute(kern[k], cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
             int occ = 0;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern[k], e->block, L.bytes));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern[k], blk, L.bytes));
             if (occ < 1) { delete e; return fail(FSB_ERR_CUDA, "step kernel %d cannot be resident (smem %d)", k, L.bytes); }
             if (cfg->blocks_per_sm > 0 && k == 1) occ = std::min(occ, cfg->blocks_per_sm);
             if (const char *ev = getenv(k == 1 ? "FSB_PASS_CTAS" : "FSB_EVENT_CTAS")) occ = std::min(occ, std::max(1, atoi(ev)));
@@ -618,7 +622,7 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                 StepArgs a{static_cast<int>(t), 1, selector, flags, b, (d.R * b) / nb, (d.R * (b + 1)) / nb};
                 const long long rb = a.r_end - a.r_begin;
                 fsb_events1_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[0])), e->block, e->smem_bytes[0], st>>>(d, a, e->launch_parity);
-                fsb_pass_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[1])), e->block, e->smem_bytes[1], st>>>(d, a, e->launch_parity);
+                fsb_pass_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[1])), e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity);
                 fsb_events2_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[2])), e->block, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
                 e->last_launches += 3;
             }

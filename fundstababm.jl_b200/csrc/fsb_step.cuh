@@ -35,7 +35,8 @@ constexpr double kPriceFloor = 0.000000001;  // functions.jl:208-209 (Q10)
 constexpr int kMaxCols = 14;                 // horizon columns per full pass (4 groups x 4 columns, minus the 2 price columns)
 constexpr int kPfAheadDefault = 2;           // holdings rounds prefetched into L2 ahead of the loads (DevState::pf_ahead)
 constexpr int kStepThreads = 128;
-constexpr int kRingStages = 3;         // per-warp ring of holdings stages (pass kernel, default shape)
+constexpr int kRingStages = 2;         // per-warp ring of holdings stages (pass kernel, default shape)
+constexpr int kPassThreads = 256;      // the pass kernel's CTA: 8 warps share the staged columns
 constexpr int kStageBytes = 8 * 512;   // a stage = 8 rows x 4 word steps (512 bytes per row)
 #ifndef FSB_FP_INLINE
 #define FSB_FP_INLINE __forceinline__
@@ -70,6 +71,8 @@ struct SmemLayout {
 // order rows / probability rows, depending on the kernel)
 __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap, int nslots, int nwarps, int ring_stages = 0)
 {
+    // ring_stages > 0 marks the pass kernel, which needs none of the per-asset / per-investor event arrays
+    const bool lean = ring_stages > 0;
     SmemLayout L;
     L.cp = (Mp + 127) & ~127;  // == Mp: the engine rounds Mp up to 128 itself
     L.kq = (K + 3) & ~3;
@@ -79,8 +82,8 @@ __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap,
     L.off_cols = d; d += nslots * L.cpk;
     L.srows = ((nslots - 2) * L.cpk) / L.cp;
     L.wsd = (((nslots - 2) * L.cpk) / nwarps) & ~1;
-    L.off_ratio = d; d += L.cp;
-    L.off_sellsum = d; d += L.cp;
+    L.off_ratio = d; d += lean ? 0 : L.cp;
+    L.off_sellsum = d; d += lean ? 0 : L.cp;
     L.off_nav = d; d += L.kq;
     L.off_dstake = d; d += cap;
     L.off_dcash = d; d += cap;
@@ -100,19 +103,19 @@ __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap,
     L.off_rcol = i; i += cap;
     L.off_hcols = i; i += cap;
     L.off_eggs = i; i += cap;
-    L.off_wl = i; i += nwarps * cap;
+    L.off_wl = i; i += lean ? 0 : nwarps * cap;
     L.off_wcnt = i; i += 2 * nwarps;
     L.off_flags = i; i += cap;
     L.off_nzf = i; i += cap;
-    L.off_pick = i; i += L.cp;
+    L.off_pick = i; i += lean ? 0 : L.cp;
     L.off_fmod = i; i += (K + 31) / 32;
     L.off_fsel = i; i += (K + 31) / 32;
     L.off_isc = i; i += 16;
     i = (i + 3) & ~3;  // 16-bit arrays start 16-byte aligned (int4 scans of pos16)
     L.nints = i;
     int h = 0;
-    L.off_pos16 = h; h += (N + 7) & ~7;  // padded with -1 to whole 16-byte words
-    L.off_hor16 = h; h += (N + 7) & ~7;
+    L.off_pos16 = h; h += lean ? 0 : ((N + 7) & ~7);  // padded with -1 to whole 16-byte words
+    L.off_hor16 = h; h += lean ? 0 : ((N + 7) & ~7);
     L.nshorts = h;
     L.bytes = 1024 /* kCtxBytes */ + d * 8 + i * 4 + h * 2 + 2 * ((K + 15) & ~15);  // Ctx + arrays + stl[K], hz[K] bytes
     L.off_ring = (L.bytes + 127) & ~127;
@@ -2074,7 +2077,7 @@ __global__ void __launch_bounds__(kStepThreads, FSB_EV_CTAS) fsb_events1_kernel(
 {
     phase_kernel_body<KIND_EVENTS1>(s, a, launch_parity);
 }
-__global__ void __launch_bounds__(kStepThreads, 4) fsb_pass_kernel(const DevState s, const StepArgs a, const int launch_parity)
+__global__ void __launch_bounds__(kPassThreads, 2) fsb_pass_kernel(const DevState s, const StepArgs a, const int launch_parity)
 {
     phase_kernel_body<KIND_PASS>(s, a, launch_parity);
 }
