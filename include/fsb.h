@@ -91,9 +91,10 @@ typedef struct fsb_config {
     int32_t event_capacity; /* max reviewers / orders per replication-step; 0 = auto            */
     int32_t log_capacity;   /* liquidation-log rows per replication; 0 = auto (K + 1024)        */
     int32_t trace_capacity; /* trace records per traced replication; 0 = auto                   */
-    int32_t steps_per_launch; /* time steps fused per kernel launch; 0/1 = one launch per step  */
+    int32_t steps_per_launch; /* kept for ABI compatibility and ignored: a simulated day is always
+                                 three launches (events-1, holdings pass, events-2), DESIGN.md 4    */
     int32_t block_threads;  /* 0 = auto                                                         */
-    int32_t blocks_per_sm;  /* 0 = auto                                                         */
+    int32_t blocks_per_sm;  /* CTAs per SM of the holdings-pass kernel; 0 = auto                */
 } fsb_config;
 
 typedef struct fsb_engine fsb_engine;
@@ -197,8 +198,9 @@ int32_t fsb_stats(fsb_engine *e, uint64_t *out);
 int32_t fsb_stats_all(fsb_engine **engines, int32_t n, uint64_t *out);
 
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------- */
-/* device time of the last fsb_run (CUDA events on the engine's stream): total and the part
- * spent in step-kernel launches; number of kernel launches of the last fsb_run */
+/* device time of the last fsb_run (CUDA events): total on the engine's stream, and the time summed over
+ * the launches of the dominant kernel (the holdings pass, fsb_pass_kernel; events on the stream of every
+ * launch); number of kernel launches of the last fsb_run (three per simulated day and replication batch) */
 int32_t fsb_last_run_timing(fsb_engine *e, double *total_ms, double *step_kernel_ms, int64_t *launches);
 /* asynchronous variant used for overlapping several engines in one process */
 int32_t fsb_run_async(fsb_engine *e, int64_t t_first, int64_t t_last, int32_t selector, int32_t flags);

@@ -10,7 +10,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 has() { [[ " $WHAT " == *" $1 "* ]]; }
 BENCH="python bench.py --steps 6 --warmup 3"
-PROF="python scripts/prof_step.py --reps 4096 --steps 3 --t0 300"
+PROF="env FSB_BATCHES=1 python scripts/prof_step.py --reps 8192 --steps 3 --t0 300"
 if has tests; then
     python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest_gpu_$TAG.log
     python __graft_entry__.py smoke > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/smoke_$TAG.log
@@ -26,10 +26,14 @@ if has launches; then
     echo "launches rc=$?"
 fi
 if has full; then
+    # one launch of each of the three kernels of a step (the pass kernel is the dominant one)
     $PROF > $OUT/prof_plain_$TAG.log 2>&1 &&
-    ncu --set full --clock-control none --import-source on -k regex:fsb_step_kernel -s 1 -c 2 -f -o $OUT/prof_${TAG}_step \
-        $PROF > $OUT/ncu_full_$TAG.log 2>&1
-    echo "full rc=$?"; cat $OUT/prof_plain_$TAG.log
+    for k in events1 pass events2; do
+        ncu --set full --clock-control none --import-source on -k regex:fsb_${k}_kernel -s 1 -c 1 -f -o $OUT/prof_${TAG}_$k \
+            $PROF > $OUT/ncu_full_${TAG}_$k.log 2>&1
+        echo "full $k rc=$?"
+    done
+    cat $OUT/prof_plain_$TAG.log
 fi
 if has phases; then
     python scripts/phase_cycles.py --reps 8192 --steps 8 > $OUT/phases_$TAG.log 2>&1; echo "phases rc=$?"; cat $OUT/phases_$TAG.log

@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 out, prof = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(prof, exist_ok=True)
 
@@ -33,54 +33,56 @@ if os.path.exists(src):
         f.write("# share of device time by kernel: " + ", ".join(f"{k} {100 * v / tot:.1f}%" for k, v in sorted(by.items(), key=lambda kv: -kv[1])) + "\n")
     print("wrote", f"profiles/{tag}_launches.csv")
 
-# ---- full capture of the step kernel -------------------------------------------------------------
-rep = os.path.join(out, f"prof_{tag}_step.ncu-rep")
-if os.path.exists(rep):
+# ---- full captures of the three kernels of a step ---------------------------------------------------------
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__icc_request_hit_rate.pct",
+        "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max"]
+lines = [f"# {tag}: ncu --set full --clock-control none, one launch of each kernel of a step", "",
+         f"Command: `FSB_BATCHES=1 python scripts/prof_step.py --reps {reps} --steps 3 --t0 300` (default Params shape, "
+         "probabilistic selector).  Numbers under a profiler are not bench values.", ""]
+traffic = {}
+for kname in ("events1", "pass", "events2"):
+    rep = os.path.join(out, f"prof_{tag}_{kname}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-            "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
-            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__maximum_warps_per_active_cycle_pct",
-            "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
-            "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
-            "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.sum",
-            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts.sum",
-            "sm__cycles_elapsed.max", "smsp__cycles_active.avg"]
-    stall = [h for h in hdr if h.startswith("smsp__average_warp") and "issue_stalled" in h and h.endswith("_per_warp_active.pct")]
-    lines = [f"# {tag}: ncu --set full --clock-control none of fsb_step_kernel", "",
-             f"Command: `python scripts/prof_step.py --reps {reps} --steps 3 --t0 300` (default Params shape, probabilistic selector); "
-             "one row per captured launch.  Numbers under a profiler are not bench values.", ""]
-    traffic = []
-    for r in rows[2:]:
-        lines.append(f"## launch {r[hdr.index('ID')]}: {r[hdr.index('Kernel Name')]}")
-        lines.append("")
-        lines.append("| metric | value | unit |")
-        lines.append("|---|---|---|")
-        vals = {}
-        for w in want + stall:
-            if w in hdr:
-                i = hdr.index(w)
-                vals[w] = r[i]
-                lines.append(f"| {w} | {r[i]} | {units[i]} |")
+    hdr, units, r = rows[0], rows[1], rows[2]
+    lines += [f"## fsb_{kname}_kernel", "", "| metric | value | unit |", "|---|---|---|"]
+    for w in want:
+        if w in hdr:
+            lines.append(f"| {w} | {r[hdr.index(w)]} | {units[hdr.index(w)]} |")
+    st = []
+    for i, h in enumerate(hdr):
+        if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h:
+            try:
+                st.append((float(r[i]), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+            except ValueError:
+                pass
+    lines.append("| warp stalls per issue (top) | " + ", ".join(f"{h} {v:.2f}" for v, h in sorted(st, reverse=True)[:6]) + " | |")
 
-        def num(key):
-            i = hdr.index(key)
-            v = float(r[i].replace(",", ""))
-            u = units[i].lower()
-            return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "tbyte": 1e12}.get(u, 1.0)
-        dram = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-        traffic.append(dram / reps)
-        inst = float(vals["smsp__inst_executed.sum"].replace(",", ""))
-        lines += ["", f"DRAM bytes per replication-step: {dram / reps / 1e3:.1f} KB (algorithmic: 528.0 KB); "
-                      f"warp instructions per replication-step: {inst / reps:.0f}", ""]
-    open(os.path.join(prof, f"{tag}_step_kernel.md"), "w").write("\n".join(lines) + "\n")
-    json.dump({"tag": tag, "dram_bytes_per_replication_step": sum(traffic) / len(traffic),
-               "source": f"profiles/{tag}_step_kernel.md (dram__bytes_read.sum + dram__bytes_write.sum over {reps} replication-steps per launch)"},
+    def num(key):
+        i = hdr.index(key)
+        v = float(r[i].replace(",", ""))
+        return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "tbyte": 1e12}.get(units[i].lower(), 1.0)
+    dram = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+    traffic[kname] = dram / reps
+    inst = float(r[hdr.index("smsp__inst_executed.sum")].replace(",", ""))
+    lines += ["", f"DRAM bytes per replication-step: {dram / reps / 1e3:.1f} KB; warp instructions per replication-step: {inst / reps:.0f}", ""]
+if traffic:
+    open(os.path.join(prof, f"{tag}_step_kernels.md"), "w").write("\n".join(lines) + "\n")
+    json.dump({"tag": tag, "kernel": "fsb_pass_kernel", "dram_bytes_per_replication_step": traffic.get("pass"),
+               "all_kernels": traffic,
+               "source": f"profiles/{tag}_step_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum over {reps} replication-steps per launch)"},
               open(os.path.join(prof, "traffic_per_launch.json"), "w"), indent=1)
-    print("wrote", f"profiles/{tag}_step_kernel.md", "traffic/rep-step KB:", [round(t / 1e3, 1) for t in traffic])
+    print("wrote", f"profiles/{tag}_step_kernels.md", {k: round(v / 1e3, 1) for k, v in traffic.items()})
 
 # ---- the bench line itself ---------------------------------------------------------------------
 for name in (f"bench_{tag}.json", f"bench_ref_{tag}.json"):
