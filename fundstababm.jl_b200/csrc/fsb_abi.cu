@@ -266,7 +266,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     e->fast = (d.K <= 256);
     // batches: with more than one, every kernel takes only a share of each SM so that kernels of different
     // batches are co-resident (pass: 2 CTAs per SM, events: 3)
-    e->n_batches = (d.R >= 4096) ? 2 : 1;
+    e->n_batches = 1;  // (FSB_BATCHES > 1: kernels of different batches overlap; measured gain 3 % at most)
     if (const char *ev = getenv("FSB_BATCHES")) e->n_batches = std::max(1, std::min(8, atoi(ev)));
     if (e->n_batches > d.R) e->n_batches = 1;
     if (e->n_batches > 1 && (getenv("FSB_SHARE_EVENTS") || getenv("FSB_SHARE_PASS"))) {
