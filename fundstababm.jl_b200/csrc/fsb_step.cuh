@@ -1098,7 +1098,7 @@ __device__ FSB_FP_INLINE int phase_review(const DevState &s, const int t)
             const double2 *c1 = reinterpret_cast<const double2 *>(G.P + static_cast<long long>(pcol(c, t - h)) * Mp);
             const double2 *c2 = reinterpret_cast<const double2 *>(G.P + static_cast<long long>(pcol(c, h)) * Mp);
             const double2 *c0 = reinterpret_cast<const double2 *>(po);
-#pragma unroll 4
+#pragma unroll 8
             for (int e2 = j8; e2 < half; e2 += 8) {
                 const double2 hv = row[e2], p0 = c0[e2], p1 = c1[e2], p2 = c2[e2];
                 a0 = fma(hv.x, p0.x, a0); a0 = fma(hv.y, p0.y, a0);

@@ -367,3 +367,38 @@ def test_error_behaviour(fsb):
         with pytest.raises(L.FsbError) as ei:
             eng.upload_state(0, market, stocks, investors, funds)
         assert ei.value.code == L.ERR_BAD_STATE
+
+
+@pytest.mark.parametrize("env", [
+    {"FSB_CMAX": "6"},                          # small column chunks: several holdings passes per day
+    {"FSB_NO_TMA": "1"},                        # register-ring pass (the path of non-default shapes) on the default shape
+    {"FSB_NO_TMA": "1", "FSB_CMAX": "6"},
+    {"FSB_BATCHES": "3"},                       # replication batches on separate streams
+    {"FSB_EVENT_ROWS": "1"},                    # order rows spill to the global scratch
+], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_schedule_variants_are_invisible(fsb, orc, env, monkeypatch):
+    """Launch-schedule knobs (column chunking, TMA-fed or register-fed pass, replication batches, order-row
+    spilling) must not change a single bit: default shape, a few replications against the default
+    schedule and against the oracle."""
+    p = fsb.Params.default()
+    R, t_last = 12, 180
+    with fsb.Engine(p, R, rep_offset=77) as ref:
+        ref.init_device(SEED)
+        ref.run(t_last=t_last)
+        want = [ref.download_compact(r) for r in range(R)]
+        want_stats = ref.stats_raw().tolist()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    with fsb.Engine(p, R, rep_offset=77) as eng:
+        eng.init_device(SEED)
+        eng.run(t_last=t_last)
+        assert not eng.rep_status().any()
+        for r in range(R):
+            got = eng.download_compact(r)
+            for k in got:
+                assert H.eq(got[k], want[r][k]), (k, r)
+        assert eng.stats_raw().tolist() == want_stats
+    w = H.oracle_world(orc, p, SEED, 77, trace=False)
+    assert w.modelrun(t_last=t_last) == 0
+    assert H.eq(want[0]["holdings"], w.holdings) and H.eq(want[0]["nav_close"], w.nav_close)
+    w.close()
