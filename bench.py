@@ -354,8 +354,8 @@ def main():
                          "kernel": "fsb_pass_kernel", "avg_launch_ms": per_launch_ms, "launches_timed": n_pass,
                          "share_of_step_time": pass_ms / dev_ms,
                          "whole_step": {"algorithmic_bytes_per_fund_step": b_alg(K, M, N),
-                                        "achieved": value * b_alg(K, M, N) / 1e9, "frac": value * b_alg(K, M, N) / 1e9 / peak,
-                                        "what": "all three kernels of a step (events-1, pass, events-2) against SURVEY 8d's bytes"}},
+                                        "achieved": value / world * b_alg(K, M, N) / 1e9, "frac": value / world * b_alg(K, M, N) / 1e9 / peak,
+                                        "what": "per GPU: all three kernels of a step (events-1, pass, events-2) against SURVEY 8d's bytes"}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "checks": {"error_replications": status_bad, "replication_steps_counted": int(stats[0][8])},
         }
