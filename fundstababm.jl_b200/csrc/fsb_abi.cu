@@ -231,8 +231,6 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     if (const char *ev = getenv("FSB_CTAS_PER_SM")) want_ctas = std::max(1, atoi(ev));
     const int budget = std::min(smem_max, smem_sm / want_ctas - 1024);
     d.cmax = kMaxCols;
-    d.pf_ahead = kPfAheadDefault;
-    if (const char *ev = getenv("FSB_PF_AHEAD")) d.pf_ahead = std::max(0, atoi(ev));
     if (const char *ev = getenv("FSB_CMAX")) d.cmax = std::min(kMaxCols, std::max(6, ((atoi(ev) + 2) / 4) * 4 - 2));
     // (a chunk after the first holds cmax - 2 columns: cmax stays >= 6)
     while (make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax + 2, nwp, d.ring_stages).bytes + 64 > budget && d.cmax > 6) d.cmax -= 4;

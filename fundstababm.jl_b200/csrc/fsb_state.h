@@ -25,7 +25,6 @@ struct DevState {
     int mkt_len;    // T (keep_history) or 2
     int keep_history;
     int cap_ev, cap_log, cap_trace, cmax;
-    int pf_ahead;   // holdings rounds prefetched into L2 ahead of the full pass's loads
     int kc;         // key columns (distinct reinvestor horizons) a replication can have per step
     int hi_stride;  // ints per replication in hand_i
     int slots_a, slots_c;  // shared-memory column slots of the events-1 / events-2 kernels
