@@ -402,3 +402,26 @@ def test_schedule_variants_are_invisible(fsb, orc, env, monkeypatch):
     assert w.modelrun(t_last=t_last) == 0
     assert H.eq(want[0]["holdings"], w.holdings) and H.eq(want[0]["nav_close"], w.nav_close)
     w.close()
+
+
+@pytest.mark.parametrize("shape", [
+    dict(bigk=300, bign=700, bigm=40, bigt=70, perfwindow=(1, 9), portfsizerange=(3, 20)),    # K > 256: rank by counting
+    dict(bigk=20, bign=90, bigm=300, bigt=60, perfwindow=(1, 8), portfsizerange=(5, 120)),    # M > 256: column pitch 384
+    dict(bigk=260, bign=600, bigm=270, bigt=55, perfwindow=(1, 6), portfsizerange=(10, 200)),  # both (config-4 like, scaled down)
+], ids=["K300", "M300", "K260_M270"])
+def test_large_shapes_general_path(fsb, orc, shape):
+    """Shapes beyond the default one (BASELINE.json configs[3] scaled down): the general, untuned code paths
+    (register-fed pass, rank by counting, wider columns) against the oracle, all selectors' hot one included."""
+    p = fsb.Params.default(reviewprobability=0.12, invcaprange=(10, 1000), **shape)
+    R = 3
+    with fsb.Engine(p, R, keep_history=True) as eng:
+        eng.init_device(SEED)
+        eng.run(selector="probabilistic")
+        assert not eng.rep_status().any()
+        for r in range(R):
+            w = H.oracle_world(orc, p, SEED, r, trace=False)
+            assert w.modelrun(selector="probabilistic") == 0
+            w.finalise_fund_value(p.bigt)
+            H.assert_state_equal(eng.download_state(r), w)
+            H.assert_log_equal(eng.download_log(r), w.log())
+            w.close()
