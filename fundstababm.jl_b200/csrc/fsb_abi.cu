@@ -22,6 +22,8 @@
 
 using namespace fsb;
 
+constexpr int kMaxBatches = 4;  // replication batches (streams) an engine can run concurrently
+
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int32_t fail(int32_t code, const char *fmt, ...)
@@ -265,7 +267,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     // batches: with more than one, every kernel takes only a share of each SM so that kernels of different
     // batches are co-resident (pass: 2 CTAs per SM, events: 3)
     e->n_batches = 1;  // (FSB_BATCHES > 1: kernels of different batches overlap; measured gain 3 % at most)
-    if (const char *ev = getenv("FSB_BATCHES")) e->n_batches = std::max(1, std::min(8, atoi(ev)));
+    if (const char *ev = getenv("FSB_BATCHES")) e->n_batches = std::max(1, std::min(kMaxBatches, atoi(ev)));
     if (e->n_batches > d.R) e->n_batches = 1;
     if (e->n_batches > 1 && (getenv("FSB_SHARE_EVENTS") || getenv("FSB_SHARE_PASS"))) {
         int share[3] = {3, 2, 3};
@@ -311,13 +313,13 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     A(err, R); A(cnt, R * kCnt);
     A(mkt_peak, R); A(mkt_dd, R);
     A(flow_hist, R * kFlowBins);
-    d.scratch_ctas = std::max(e->grid[0], std::max(e->grid[1], e->grid[2]));
-    A(scratch, static_cast<size_t>(3 * e->n_batches) * d.scratch_ctas * d.cap_ev * d.Mp);
+    d.scratch_ctas = std::max(e->grid[0], e->grid[2]);  // (only the event kernels spill order rows)
+    A(scratch, static_cast<size_t>(2 * kMaxBatches) * d.scratch_ctas * d.cap_ev * d.Mp);
     A(keys, R * d.kc * ((d.K + 3) & ~3));
     A(hand_i, R * d.hi_stride);
     A(hand_p, R * d.Mp);
     if (d.keep_history) A(hand_s, R * d.Mp);
-    A(queue, 6 * 8);
+    A(queue, 6 * kMaxBatches);
 #undef A
     {
         DevPoint *pd = nullptr; double *td = nullptr, *rt = nullptr;
@@ -340,7 +342,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming) != cudaSuccess)
         return cleanup(fail(FSB_ERR_CUDA, "cannot create stream/events"));
-    for (int b = 0; b < e->n_batches && e->n_batches > 1; ++b) {
+    for (int b = 0; b < kMaxBatches; ++b) {
         cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
         if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
             return cleanup(fail(FSB_ERR_CUDA, "cannot create batch streams"));
@@ -592,7 +594,15 @@ extern "C" int32_t fsb_set_trace(fsb_engine *e, int64_t rep, int32_t on)
 }
 
 // ---- the hot path -----------------------------------------------------------------------------
-static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32_t selector, int32_t flags)
+// host buffers of a batched one-step tape (fsb_run_step_hosttape): copied slice by slice on the batch streams so
+// that the transfers of one replication batch overlap the kernels of another
+struct HostTape {
+    const double *z_mkt = nullptr, *z_stock = nullptr, *u_review = nullptr;
+    double *nav_open_out = nullptr;
+};
+
+static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32_t selector, int32_t flags,
+                           int nb_override = 0, const HostTape *ht = nullptr)
 {
     if (!e) return fail(FSB_ERR_BAD_PARAMS, "null engine");
     const DevState &d = e->d;
@@ -610,10 +620,12 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
         ++e->last_launches;
     }
     if (t_last >= t_first) {
-        CU(cudaMemsetAsync(d.queue, 0, 6 * 8 * sizeof(int), e->stream));
+        CU(cudaMemsetAsync(d.queue, 0, 6 * kMaxBatches * sizeof(int), e->stream));
         // one simulated day = three kernels per replication batch (events-1, holdings pass, events-2), every
         // batch on its own stream; the engine's stream forks before the first day and joins after the last
-        const int nb = e->n_batches;
+        int nb = nb_override > 0 ? nb_override : e->n_batches;
+        nb = static_cast<int>(std::min<long long>(std::min<size_t>(nb, e->bstream.size()), d.R));
+        if (nb < 1) nb = 1;
         if (nb > 1) {
             CU(cudaEventRecord(e->fork, e->stream));
             for (int b = 0; b < nb; ++b) CU(cudaStreamWaitEvent(e->bstream[b], e->fork, 0));
@@ -623,6 +635,11 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                 cudaStream_t st = nb > 1 ? e->bstream[b] : e->stream;
                 StepArgs a{static_cast<int>(t), 1, selector, flags, b, (d.R * b) / nb, (d.R * (b + 1)) / nb};
                 const long long rb = a.r_end - a.r_begin;
+                if (ht) {  // this batch's slice of the step's shocks: host -> device on the batch's stream
+                    CU(cudaMemcpyAsync(e->st_zmkt + a.r_begin, ht->z_mkt + a.r_begin, rb * 8, cudaMemcpyHostToDevice, st));
+                    CU(cudaMemcpyAsync(e->st_zstock + a.r_begin * d.M, ht->z_stock + a.r_begin * d.M, rb * d.M * 8, cudaMemcpyHostToDevice, st));
+                    CU(cudaMemcpyAsync(e->st_urev + a.r_begin * d.N, ht->u_review + a.r_begin * d.N, rb * d.N * 8, cudaMemcpyHostToDevice, st));
+                }
                 fsb_events1_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[0])), e->block, e->smem_bytes[0], st>>>(d, a, e->launch_parity);
                 const bool timed = e->kev_used + 2 <= 4096;  // (the dominant kernel is timed launch by launch: bench.py's roofline)
                 if (timed) {
@@ -631,6 +648,8 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                 }
                 fsb_pass_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[1])), e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity);
                 if (timed) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st)); e->kev_used += 2; }
+                if (ht && ht->nav_open_out)  // the NAVs of :460 are final after the pass: device -> host while events-2 runs
+                    CU(cudaMemcpyAsync(ht->nav_open_out + a.r_begin * d.K, d.nav_open + a.r_begin * d.K, rb * d.K * 8, cudaMemcpyDeviceToHost, st));
                 fsb_events2_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[2])), e->block, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
                 e->last_launches += 3;
             }
@@ -694,18 +713,15 @@ extern "C" int32_t fsb_run_step_hosttape(fsb_engine *e, int64_t t, int32_t selec
     if (!e->st_zmkt) {
         TRY(dalloc(e, &e->st_zmkt, R, false)); TRY(dalloc(e, &e->st_zstock, R * d.M, false)); TRY(dalloc(e, &e->st_urev, R * d.N, false));
     }
-    CU(cudaMemcpyAsync(e->st_zmkt, z_mkt, R * 8, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(e->st_zstock, z_stock, R * d.M * 8, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(e->st_urev, u_review, R * d.N * 8, cudaMemcpyHostToDevice, e->stream));
     d.st_zmkt = e->st_zmkt; d.st_zstock = e->st_zstock; d.st_urev = e->st_urev;
     d.step_tape = 1;
-    const int spl = e->cfg.steps_per_launch;
-    e->cfg.steps_per_launch = 1;
-    const int32_t rc = run_enqueue(e, t, t, selector, flags);
-    e->cfg.steps_per_launch = spl;
+    HostTape ht;
+    ht.z_mkt = z_mkt; ht.z_stock = z_stock; ht.u_review = u_review; ht.nav_open_out = nav_open_out;
+    int nbh = 4;
+    if (const char *ev = getenv("FSB_HOSTTAPE_BATCHES")) nbh = std::max(1, std::min(kMaxBatches, atoi(ev)));
+    const int32_t rc = run_enqueue(e, t, t, selector, flags, nbh, &ht);
     d.step_tape = 0;
     TRY(rc);
-    if (nav_open_out) CU(cudaMemcpyAsync(nav_open_out, d.nav_open, R * d.K * 8, cudaMemcpyDeviceToHost, e->stream));
     return fsb_sync(e);
 }
 

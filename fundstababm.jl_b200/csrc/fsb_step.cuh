@@ -1994,7 +1994,7 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         c.o_ring = L.off_ring; c.o_bars = L.off_bars;
         c.mbar = &mbar_sh; c.mbar_phase = 0;
         c.tmark = clock64();
-        c.slot = 3 * a.batch + KIND;  // concurrently running kernels (batches x kinds) get disjoint per-CTA scratch
+        c.slot = 2 * a.batch + (KIND == KIND_EVENTS2 ? 1 : 0);  // concurrently running event kernels get disjoint per-CTA scratch
         c.scratch = s.scratch + (static_cast<long long>(c.slot) * s.scratch_ctas + blockIdx.x) * (static_cast<long long>(s.cap_ev) * s.Mp);
         c.ranktab = s.ranktab;
         c.rng.k0 = static_cast<uint32_t>(s.seed); c.rng.k1 = static_cast<uint32_t>(s.seed >> 32);

@@ -425,3 +425,35 @@ def test_large_shapes_general_path(fsb, orc, shape):
             H.assert_state_equal(eng.download_state(r), w)
             H.assert_log_equal(eng.download_log(r), w.log())
             w.close()
+
+
+def test_hosttape_steps_match_the_oracle_on_the_same_draws(fsb, orc):
+    """fsb_run_step_hosttape (the e2e path of bench.py): every step's shocks come from host buffers, replication
+    batches run on separate streams with their transfers; the oracle gets the same draws as dense tapes."""
+    p = H.small_params(fsb, bigk=7, bign=60, bigm=12)
+    R, T0, NS = 9, p.perfwindow[-1] + 2, 25
+    rng = np.random.default_rng(99)
+    zm = rng.standard_normal((NS, R))
+    zs = rng.standard_normal((NS, R, p.bigm))
+    ur = rng.random((NS, R, p.bign))
+    with fsb.Engine(p, R) as eng:
+        eng.init_device(SEED)
+        nav = np.zeros((R, p.bigk))
+        navs = []
+        for i in range(NS):
+            eng.run_step_hosttape(T0 + i, np.ascontiguousarray(zm[i]), np.ascontiguousarray(zs[i]), np.ascontiguousarray(ur[i]), nav)
+            navs.append(nav.copy())
+        assert not eng.rep_status().any()
+        got = [eng.download_compact(r) for r in range(R)]
+    for r in (0, 4, 8):
+        w = H.oracle_world(orc, p, SEED, r, trace=True)
+        z_mkt = np.zeros(p.bigt); z_stock = np.zeros((p.bigm, p.bigt), order="F"); u_rev = np.zeros((p.bign, p.bigt), order="F")
+        for i in range(NS):
+            z_mkt[T0 + i - 1] = zm[i, r]; z_stock[:, T0 + i - 1] = zs[i, r]; u_rev[:, T0 + i - 1] = ur[i, r]
+        w.set_dense_tape(z_mkt, z_stock, u_rev)
+        assert w.modelrun(T0, T0 + NS - 1, "probabilistic", 0) == 0
+        assert H.eq(got[r]["holdings"], w.holdings) and H.eq(got[r]["nav_close"], w.nav_close)
+        assert H.eq(got[r]["price_now"], w.stock_value[:, T0 + NS - 2])
+        for i in range(NS):
+            assert H.eq(navs[i][r], w.trace_nav_open[:, T0 + i - 1]), i
+        w.close()
