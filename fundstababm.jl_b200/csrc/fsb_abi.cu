@@ -2,6 +2,7 @@
 // Owns device memory, the stream, the launch schedule of the per-step kernel and the NCCL
 // communicator (libnccl is dlopen'ed on first use so the library has no link-time dependency).
 // There is no CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda.h>  // CUtensorMap and its enums only: the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -84,6 +85,7 @@ static int32_t nccl_load()
 
 // ------------------------------------------------------------------------------------------------
 struct fsb_engine {
+    CUtensorMap tm_h{};  // 2-D view of the holdings of ALL replications: [R * K4 rows][Mp], box = 8 rows x one stage (pass kernel)
     DevState d{};
     fsb_config cfg{};
     std::vector<DevPoint> points;
@@ -299,6 +301,21 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     const size_t R = static_cast<size_t>(d.R);
     A(H, R * d.h_stride);
     A(P, R * d.p_stride);
+    if (d.ring_stages > 0) {  // the pass kernel fetches a stage (8 rows x kStageRowBytes) with ONE tensor copy
+        if (d.h_stride != static_cast<long long>((d.K + 3) & ~3) * d.Mp) return cleanup(fail(FSB_ERR_BAD_PARAMS, "holdings stride is not K4 * Mp"));
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return cleanup(fail(FSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver"));
+        const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d.Mp), static_cast<cuuint64_t>(R) * ((d.K + 3) & ~3)};
+        const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(d.Mp) * 8};
+        const cuuint32_t box[2] = {static_cast<cuuint32_t>(kStageRowBytes / 8), 8}, estr[2] = {1, 1};
+        const CUresult cr = reinterpret_cast<encode_fn>(fn)(&e->tm_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d.H, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return cleanup(fail(FSB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(cr)));
+    }
     A(beta, R * d.Mp); A(vol, R * d.Mp); A(impact, R * d.Mp);
     if (d.keep_history) A(volume, R * d.T * d.Mp);
     A(market, R * d.mkt_len);
@@ -646,7 +663,7 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                     while (e->kev.size() < e->kev_used + 2) { cudaEvent_t ev = nullptr; CU(cudaEventCreate(&ev)); e->kev.push_back(ev); }
                     CU(cudaEventRecord(e->kev[e->kev_used], st));
                 }
-                fsb_pass_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[1])), e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity);
+                fsb_pass_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[1])), e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity, e->tm_h);
                 if (timed) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st)); e->kev_used += 2; }
                 if (ht && ht->nav_open_out)  // the NAVs of :460 are final after the pass: device -> host while events-2 runs
                     CU(cudaMemcpyAsync(ht->nav_open_out + a.r_begin * d.K, d.nav_open + a.r_begin * d.K, rb * d.K * 8, cudaMemcpyDeviceToHost, st));

@@ -255,6 +255,13 @@ __device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, unsigned 
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// one box of a 2-D tensor map (coordinates: c0 = element in the row, c1 = row) -> shared memory (128-byte aligned), on an mbarrier
+__device__ __forceinline__ void tensor_g2s_2d(void *sdst, const void *tmap, int c0, int c1, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(sdst)),
+                 "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -27,6 +27,8 @@
 // Everything variable-length is a fixed-capacity list in shared memory with an overflow flag that
 // raises FSB_REP_EVENT_OVERFLOW (never a silent drop).
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only)
+
 #include "fsb_device.cuh"
 #include "fsb_state.h"
 
@@ -35,9 +37,17 @@ namespace fsb {
 constexpr double kPriceFloor = 0.000000001;  // functions.jl:208-209 (Q10)
 constexpr int kMaxCols = 14;                 // horizon columns per full pass (4 groups x 4 columns, minus the 2 price columns)
 constexpr int kStepThreads = 128;
-constexpr int kRingStages = 2;         // per-warp ring of holdings stages (pass kernel, default shape)
+#ifndef FSB_RING_STAGES
+#define FSB_RING_STAGES 2
+#endif
+#ifndef FSB_STAGE_ROW_BYTES
+#define FSB_STAGE_ROW_BYTES 512
+#endif
+constexpr int kRingStages = FSB_RING_STAGES;  // per-warp ring of holdings stages (pass kernel, default shape)
 constexpr int kPassThreads = 256;      // the pass kernel's CTA: 8 warps share the staged columns
-constexpr int kStageBytes = 8 * 512;   // a stage = 8 rows x 4 word steps (512 bytes per row)
+constexpr int kStageRowBytes = FSB_STAGE_ROW_BYTES;  // bytes of a holdings row per stage (128 per word step)
+constexpr int kStageBytes = 8 * kStageRowBytes;      // a stage = 8 rows
+constexpr int kStagesPerTrip = 2048 / kStageRowBytes;
 #ifndef FSB_FP_INLINE
 #define FSB_FP_INLINE __forceinline__
 #endif
@@ -124,7 +134,7 @@ __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap,
     return L;
 }
 
-extern __shared__ __align__(16) unsigned char fsb_smem[];  // dynamic shared memory: Ctx, then the arrays of SmemLayout
+extern __shared__ __align__(128) unsigned char fsb_smem[];  // dynamic shared memory: Ctx, then the arrays of SmemLayout
 constexpr int kCtxBytes = 1024;
 
 // The step's context: ONE instance per CTA in shared memory, filled by thread 0 per replication.
@@ -139,6 +149,7 @@ struct Ctx {
     int o_pos16, o_hor16, o_stl, o_hz, o_ring, o_bars;
     unsigned long long *mbar;
     unsigned mbar_phase;
+    const CUtensorMap *tm_h;  // pass kernel: the holdings of all replications as one 2-D tensor (kernel parameter space)
     // replication
     double *H, *P, *beta, *vol, *impact, *volume, *market, *stake, *amount, *threshold, *nav_open, *nav_close;
     int *pos, *horizon, *live_row, *cnt;
@@ -805,7 +816,7 @@ __device__ FSB_FP_INLINE void full_pass(const DevState &s, const int cb, const i
 template <int C>
 __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, const int nreal, const int want_keys, const int kcol0, const int open_day)
 {
-    constexpr int R = 4, NS = R * C, S = kRingStages;
+    constexpr int R = 4, NS = R * C, S = kRingStages, PT = kStagesPerTrip, RW = kStageRowBytes / 16, QS = kStageRowBytes / 128;
     Ctx &c = ctx();
     const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
@@ -814,24 +825,23 @@ __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, con
     const int ntrips = (K4 + 7) >> 3;
     const int my_trips = (ntrips - warp + nwarps - 1) / nwarps;
     if (my_trips <= 0) return;
-    const int nstages = my_trips * 4;
+    const int nstages = my_trips * PT;
     unsigned char *ring = fsb_smem + c.o_ring + warp * (S * kStageBytes);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(fsb_smem + c.o_bars) + warp * S;
     // the ring's mbarriers are initialised once per kernel; gbase = stages this warp has consumed so far
     // (slot and phase parity of a stage follow from its running index)
     long long *gcount = reinterpret_cast<long long *>(fsb_smem + c.o_bars + nwarps * S * 8) + warp;
     const long long gbase = *gcount;
-    const char *Hb = reinterpret_cast<const char *>(G.H);
-    auto issue = [&](int g) {  // stage g of this warp's sequence -> slot g % S
-        const int slot = static_cast<int>((gbase + g) % S), tg = warp + (g >> 2) * nwarps, part = g & 3;
+    const CUtensorMap *const tm = c.tm_h;
+    const int grow0 = static_cast<int>(c.r) * K4;  // this replication's first row in the 2-D view of all holdings
+    auto issue = [&](int g) {  // stage g of this warp's sequence -> slot g % S: ONE tensor copy of 8 rows x kStageRowBytes
+        const int slot = static_cast<int>((gbase + g) % S), tg = warp + (g / PT) * nwarps, part = g % PT;
+        __syncwarp();  // every lane is done with the slot's previous contents
         if (lane == 0) {
             fence_proxy_async();
             mbar_expect_tx(bars + slot, kStageBytes);
-        }
-        if (lane < 8) {
-            int row = 8 * tg + lane;
-            if (row >= K4) row = K4 - 1;  // (rows past the last one re-read it; their results are dropped)
-            bulk_g2s(ring + slot * kStageBytes + lane * 512, Hb + static_cast<long long>(row) * 2048 + part * 512, 512, bars + slot);
+            // (rows past K4 - 1 of the last trip belong to the next replication or are zero filled: their results are dropped)
+            tensor_g2s_2d(ring + slot * kStageBytes, tm, part * (kStageRowBytes / 8), grow0 + 8 * tg, bars + slot);
         }
     };
 #pragma unroll 1
@@ -839,23 +849,23 @@ __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, con
     const double2 *colp = reinterpret_cast<const double2 *>(c.cols_()) + (cb + qb) * 128 + j;
     const double *const keep_nav = c.nav_();
 #pragma unroll 1
-    for (int g0 = 0; g0 < nstages; g0 += 4) {
+    for (int g0 = 0; g0 < nstages; g0 += PT) {
         double acc[NS];
 #pragma unroll
         for (int q = 0; q < NS; ++q) acc[q] = 0.0;
 #pragma unroll 1
-        for (int part = 0; part < 4; ++part) {
+        for (int part = 0; part < PT; ++part) {
             const int g = g0 + part;
             if (g + S - 1 < nstages) issue(g + S - 1);
             const int slot = static_cast<int>((gbase + g) % S);
             mbar_wait(bars + slot, static_cast<unsigned>(((gbase + g) / S) & 1));
-            const double2 *hs = reinterpret_cast<const double2 *>(ring + slot * kStageBytes) + (R * qa) * 32 + j;
-            const double2 *cp_i = colp + 32 * part;
+            const double2 *hs = reinterpret_cast<const double2 *>(ring + slot * kStageBytes) + (R * qa) * RW + j;
+            const double2 *cp_i = colp + RW * part;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < QS; ++q) {
                 double2 h[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) h[r] = hs[r * 32 + 8 * q];
+                for (int r = 0; r < R; ++r) h[r] = hs[r * RW + 8 * q];
 #pragma unroll
                 for (int cc = 0; cc < C; ++cc) {
                     const double2 p = cp_i[2 * cc * 128 + 8 * q];
@@ -867,11 +877,10 @@ __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, con
                 }
             }
         }
-        const int g = g0 + 3;
         // ---- epilogue of the trip -----------------------------------------------------------------
         reduce8_transposed<NS>(acc, j);
         constexpr int NF = NS / 8;
-        const int row0 = 8 * (warp + (g >> 2) * nwarps) + R * qa;
+        const int row0 = 8 * (warp + (g0 / PT) * nwarps) + R * qa;
         int own[NF];
 #pragma unroll
         for (int q = 0; q < NF; ++q) own[q] = owned_sum<NS>(j, q);
@@ -1962,7 +1971,7 @@ __device__ __forceinline__ void step_events2(const DevState &s, Ctx &c, const in
 // kernels: persistent CTAs pull replications from a work counter (one counter pair per kernel kind)
 // ------------------------------------------------------------------------------------------------
 template <int KIND>
-__device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepArgs &a, const int launch_parity)
+__device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepArgs &a, const int launch_parity, const CUtensorMap *tm_h)
 {
     static_assert(sizeof(Ctx) <= kCtxBytes, "Ctx outgrew its shared-memory slot");
     Ctx &c = ctx();
@@ -1993,6 +2002,7 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         c.o_hz = c.o_stl + ((s.K + 15) & ~15);
         c.o_ring = L.off_ring; c.o_bars = L.off_bars;
         c.mbar = &mbar_sh; c.mbar_phase = 0;
+        c.tm_h = tm_h;
         c.tmark = clock64();
         c.slot = 2 * a.batch + (KIND == KIND_EVENTS2 ? 1 : 0);  // concurrently running event kernels get disjoint per-CTA scratch
         c.scratch = s.scratch + (static_cast<long long>(c.slot) * s.scratch_ctas + blockIdx.x) * (static_cast<long long>(s.cap_ev) * s.Mp);
@@ -2074,15 +2084,15 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
 #endif
 __global__ void __launch_bounds__(kStepThreads, FSB_EV_CTAS) fsb_events1_kernel(const DevState s, const StepArgs a, const int launch_parity)
 {
-    phase_kernel_body<KIND_EVENTS1>(s, a, launch_parity);
+    phase_kernel_body<KIND_EVENTS1>(s, a, launch_parity, nullptr);
 }
-__global__ void __launch_bounds__(kPassThreads, 2) fsb_pass_kernel(const DevState s, const StepArgs a, const int launch_parity)
+__global__ void __launch_bounds__(kPassThreads, 2) fsb_pass_kernel(const DevState s, const StepArgs a, const int launch_parity, const __grid_constant__ CUtensorMap tm_h)
 {
-    phase_kernel_body<KIND_PASS>(s, a, launch_parity);
+    phase_kernel_body<KIND_PASS>(s, a, launch_parity, &tm_h);
 }
 __global__ void __launch_bounds__(kStepThreads, FSB_EV_CTAS) fsb_events2_kernel(const DevState s, const StepArgs a, const int launch_parity)
 {
-    phase_kernel_body<KIND_EVENTS2>(s, a, launch_parity);
+    phase_kernel_body<KIND_EVENTS2>(s, a, launch_parity, nullptr);
 }
 
 }  // namespace fsb
