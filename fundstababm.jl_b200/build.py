@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libfsb_b200.so")
-SOURCES = ["fsb_abi.cu"]
+SOURCES = ["fsb_abi.cu", "fsb_step_big.cu"]  # (the second one: the same step kernels built for big shapes)
 HEADERS = ["fsb_device.cuh", "fsb_state.h", "fsb_step.cuh", "fsb_aux.cuh", "../../include/fsb.h"]
 
 # -fmad=false: no implicit FMA contraction -- every fused operation in the kernels is an explicit
@@ -30,13 +30,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if force or needs_build():
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         extra = os.environ.get("FSB_NVCC_EXTRA", "").split()  # e.g. -DFSB_PHASE_TIMING for scripts/phase_cycles.py
-        cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or res.returncode != 0:
-            print(res.stdout)
-            print(res.stderr)
-        if res.returncode != 0:
-            raise RuntimeError("nvcc failed building libfsb_b200.so")
+        # one object per translation unit, compiled in parallel (each takes minutes), then one link
+        flags = [f for f in NVCC_FLAGS if f != "-shared"]
+        objs, procs = [], []
+        for src in SOURCES:
+            obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+            objs.append(obj)
+            procs.append(subprocess.Popen([nvcc] + flags + extra + ["-c", "-o", obj, os.path.join(CSRC, src)],
+                                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate()[0] for p in procs]
+        ok = all(p.returncode == 0 for p in procs)
+        cmd = [nvcc, "-shared", "-o", SO] + objs + ["-ldl"]
+        res = subprocess.run(cmd, capture_output=True, text=True) if ok else subprocess.CompletedProcess(cmd, 1, "", "compile failed")
+        res.stdout = "\n".join(outs) + res.stdout
+        for obj in objs:
+            if os.path.exists(obj):
+                os.remove(obj)
         with open(os.path.join(CSRC, "build.log"), "w") as f:
             f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
     return SO

@@ -21,6 +21,12 @@
 #include "fsb_state.h"
 #include "fsb_step.cuh"
 
+namespace fsb {  // the FSB_BIG build of the step kernels (fsb_step_big.cu)
+__global__ void fsb_big_events1_kernel(const DevState s, const StepArgs a, const int launch_parity);
+__global__ void fsb_big_pass_kernel(const DevState s, const StepArgs a, const int launch_parity, const __grid_constant__ CUtensorMap tm_h);
+__global__ void fsb_big_events2_kernel(const DevState s, const StepArgs a, const int launch_parity);
+}  // namespace fsb
+
 using namespace fsb;
 
 constexpr int kMaxBatches = 4;  // replication batches (streams) an engine can run concurrently
@@ -228,31 +234,39 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     const int nw = e->block / 32;
     e->block_pass = (d.K <= 256 && d.Mp == 256 && !getenv("FSB_NO_TMA")) ? kPassThreads : e->block;
     if (const char *ev = getenv("FSB_PASS_THREADS")) e->block_pass = std::max(32, std::min(kPassThreads, (atoi(ev) / 32) * 32));
-    const int nwp = e->block_pass / 32;
+    int nwp = e->block_pass / 32;
     d.ring_stages = (d.K <= 256 && d.Mp == 256) ? kRingStages : 0;
     if (getenv("FSB_NO_TMA")) d.ring_stages = 0;
+    // big shapes: even the leanest events-1 layout (3 column slots) does not fit in shared memory
+    d.big = (make_layout(d.K, d.Mp, d.N, d.cap_ev, 3, nw).bytes + 64 > smem_max || getenv("FSB_FORCE_BIG")) ? 1 : 0;
+    if (d.big) { d.ring_stages = 0; e->block_pass = e->block; }
     int want_ctas = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : (d.ring_stages ? 2 : 4);
     if (const char *ev = getenv("FSB_CTAS_PER_SM")) want_ctas = std::max(1, atoi(ev));
     const int budget = std::min(smem_max, smem_sm / want_ctas - 1024);
     d.cmax = kMaxCols;
     if (const char *ev = getenv("FSB_CMAX")) d.cmax = std::min(kMaxCols, std::max(6, ((atoi(ev) + 2) / 4) * 4 - 2));
     // (a chunk after the first holds cmax - 2 columns: cmax stays >= 6)
-    while (make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax + 2, nwp, d.ring_stages).bytes + 64 > budget && d.cmax > 6) d.cmax -= 4;
+    nwp = e->block_pass / 32;
+    while (!d.big && make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax + 2, nwp, d.ring_stages).bytes + 64 > budget && d.cmax > 6) d.cmax -= 4;
     d.slots_a = 2 + 6;
     d.slots_c = 2 + std::max(nw, 6);
     if (const char *ev = getenv("FSB_EVENT_ROWS")) { d.slots_a = 2 + std::max(1, atoi(ev)); d.slots_c = 2 + std::max(nw, atoi(ev)); }
-    while (make_layout(d.K, d.Mp, d.N, d.cap_ev, d.slots_a, nw).bytes + 64 > smem_max && d.slots_a > 3) --d.slots_a;
-    while (make_layout(d.K, d.Mp, d.N, d.cap_ev, d.slots_c, nw).bytes + 64 > smem_max && d.slots_c > 2 + nw) --d.slots_c;
-    d.kc = std::min(d.W, std::max(32, 2 * kMaxCols));
+    while (!d.big && make_layout(d.K, d.Mp, d.N, d.cap_ev, d.slots_a, nw).bytes + 64 > smem_max && d.slots_a > 3) --d.slots_a;
+    while (!d.big && make_layout(d.K, d.Mp, d.N, d.cap_ev, d.slots_c, nw).bytes + 64 > smem_max && d.slots_c > 2 + nw) --d.slots_c;
+    d.kc = std::min(d.W, std::max(std::max(32, 2 * kMaxCols), d.cap_ev / 2));  // (distinct horizons of a step's cash holders)
     d.hi_stride = hand_ints(d.K, d.cap_ev);
     e->init_smem = (d.W + 2 + d.K) * 8;
     if (e->init_smem > 48 * 1024) CU(cudaFuncSetAttribute(fsb_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->init_smem));
     {
         const int slots[3] = {d.slots_a, d.cmax + 2, d.slots_c};
-        const void *kern[3] = {(const void *)fsb_events1_kernel, (const void *)fsb_pass_kernel, (const void *)fsb_events2_kernel};
+        const void *kern_std[3] = {(const void *)fsb_events1_kernel, (const void *)fsb_pass_kernel, (const void *)fsb_events2_kernel};
+        const void *kern_big[3] = {(const void *)fsb_big_events1_kernel, (const void *)fsb_big_pass_kernel, (const void *)fsb_big_events2_kernel};
+        const void *const *kern = d.big ? kern_big : kern_std;
+        d.big_stride = 0;
         for (int k = 0; k < 3; ++k) {
             const int blk = (k == 1) ? e->block_pass : e->block;
-            const SmemLayout L = make_layout(d.K, d.Mp, d.N, d.cap_ev, slots[k], blk / 32, k == 1 ? d.ring_stages : 0);
+            const SmemLayout L = make_layout(d.K, d.Mp, d.N, d.cap_ev, slots[k], blk / 32, k == 1 ? d.ring_stages : 0, d.big != 0);
+            d.big_stride = std::max(d.big_stride, L.big_bytes);
             if (L.bytes + 64 > smem_max) { delete e; return fail(FSB_ERR_BAD_PARAMS, "shapes need %d bytes of shared memory per CTA (> %d)", L.bytes, smem_max); }
             e->smem_bytes[k] = L.bytes;
             CU(cudaFuncSetAttribute(kern[k], cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
@@ -270,7 +284,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     // batches are co-resident (pass: 2 CTAs per SM, events: 3)
     e->n_batches = 1;  // (FSB_BATCHES > 1: kernels of different batches overlap; measured gain 3 % at most)
     if (const char *ev = getenv("FSB_BATCHES")) e->n_batches = std::max(1, std::min(kMaxBatches, atoi(ev)));
-    if (e->n_batches > d.R) e->n_batches = 1;
+    if (e->n_batches > d.R || d.big) e->n_batches = 1;
     if (e->n_batches > 1 && (getenv("FSB_SHARE_EVENTS") || getenv("FSB_SHARE_PASS"))) {
         int share[3] = {3, 2, 3};
         if (const char *ev = getenv("FSB_SHARE_EVENTS")) share[0] = share[2] = std::max(1, atoi(ev));
@@ -331,7 +345,11 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     A(mkt_peak, R); A(mkt_dd, R);
     A(flow_hist, R * kFlowBins);
     d.scratch_ctas = std::max(e->grid[0], e->grid[2]);  // (only the event kernels spill order rows)
-    A(scratch, static_cast<size_t>(2 * kMaxBatches) * d.scratch_ctas * d.cap_ev * d.Mp);
+    if (d.big) d.scratch_ctas = std::max(d.scratch_ctas, e->grid[1]);  // (the pass kernel stages its columns in bigbuf)
+    // big shapes run one batch at a time (an order-row scratch is cap_ev x Mp doubles per CTA: 11 MB at 2000 x 5000)
+    const size_t scratch_slots = d.big ? 2 : 2 * kMaxBatches;
+    A(scratch, scratch_slots * d.scratch_ctas * d.cap_ev * d.Mp);
+    if (d.big) A(bigbuf, scratch_slots * d.scratch_ctas * static_cast<size_t>(d.big_stride));
     A(keys, R * d.kc * ((d.K + 3) & ~3));
     A(hand_i, R * d.hi_stride);
     A(hand_p, R * d.Mp);
@@ -641,6 +659,7 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
         // one simulated day = three kernels per replication batch (events-1, holdings pass, events-2), every
         // batch on its own stream; the engine's stream forks before the first day and joins after the last
         int nb = nb_override > 0 ? nb_override : e->n_batches;
+        if (d.big) nb = 1;
         nb = static_cast<int>(std::min<long long>(std::min<size_t>(nb, e->bstream.size()), d.R));
         if (nb < 1) nb = 1;
         if (nb > 1) {
@@ -657,17 +676,22 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                     CU(cudaMemcpyAsync(e->st_zstock + a.r_begin * d.M, ht->z_stock + a.r_begin * d.M, rb * d.M * 8, cudaMemcpyHostToDevice, st));
                     CU(cudaMemcpyAsync(e->st_urev + a.r_begin * d.N, ht->u_review + a.r_begin * d.N, rb * d.N * 8, cudaMemcpyHostToDevice, st));
                 }
-                fsb_events1_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[0])), e->block, e->smem_bytes[0], st>>>(d, a, e->launch_parity);
+                const unsigned g1 = static_cast<unsigned>(std::min<long long>(rb, e->grid[0])), g2 = static_cast<unsigned>(std::min<long long>(rb, e->grid[1])),
+                               g3 = static_cast<unsigned>(std::min<long long>(rb, e->grid[2]));
+                if (d.big) fsb_big_events1_kernel<<<g1, e->block, e->smem_bytes[0], st>>>(d, a, e->launch_parity);
+                else fsb_events1_kernel<<<g1, e->block, e->smem_bytes[0], st>>>(d, a, e->launch_parity);
                 const bool timed = e->kev_used + 2 <= 4096;  // (the dominant kernel is timed launch by launch: bench.py's roofline)
                 if (timed) {
                     while (e->kev.size() < e->kev_used + 2) { cudaEvent_t ev = nullptr; CU(cudaEventCreate(&ev)); e->kev.push_back(ev); }
                     CU(cudaEventRecord(e->kev[e->kev_used], st));
                 }
-                fsb_pass_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[1])), e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity, e->tm_h);
+                if (d.big) fsb_big_pass_kernel<<<g2, e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity, e->tm_h);
+                else fsb_pass_kernel<<<g2, e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity, e->tm_h);
                 if (timed) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st)); e->kev_used += 2; }
                 if (ht && ht->nav_open_out)  // the NAVs of :460 are final after the pass: device -> host while events-2 runs
                     CU(cudaMemcpyAsync(ht->nav_open_out + a.r_begin * d.K, d.nav_open + a.r_begin * d.K, rb * d.K * 8, cudaMemcpyDeviceToHost, st));
-                fsb_events2_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid[2])), e->block, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
+                if (d.big) fsb_big_events2_kernel<<<g3, e->block, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
+                else fsb_events2_kernel<<<g3, e->block, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
                 e->last_launches += 3;
             }
             e->launch_parity ^= 1;

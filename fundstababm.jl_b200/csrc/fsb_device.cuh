@@ -79,7 +79,7 @@ __device__ __forceinline__ double det_log(double x)
 }
 
 // inverse normal CDF: Wichura AS241 (PPND16) on det_log
-__device__ __noinline__ double det_norminv(double u)
+static __device__ __noinline__ double det_norminv(double u)
 {
     const double q = u - 0.5;
     double r, num, den;

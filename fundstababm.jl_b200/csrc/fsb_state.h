@@ -28,6 +28,9 @@ struct DevState {
     int kc;         // key columns (distinct reinvestor horizons) a replication can have per step
     int hi_stride;  // ints per replication in hand_i
     int slots_a, slots_c;  // shared-memory column slots of the events-1 / events-2 kernels
+    int big;               // shapes whose per-asset arrays do not fit in shared memory: the FSB_BIG build of the step kernels
+    long long big_stride;  // bytes of a CTA's global buffer for those arrays
+    unsigned char *bigbuf; // [2 * batches][scratch_ctas][big_stride]
     int ring_stages;       // per-warp holdings ring of the pass kernel (kRingStages on the default shape, else 0)
     int n_points;
     long long R, rep_offset, reps_per_point;

@@ -26,8 +26,21 @@
 // and the context lives in shared memory so that phases stay register-lean.
 // Everything variable-length is a fixed-capacity list in shared memory with an overflow flag that
 // raises FSB_REP_EVENT_OVERFLOW (never a silent drop).
+//
+// FSB_BIG (fsb_step_big.cu): a second build of the same code for shapes whose per-asset arrays do not fit in
+// shared memory (BASELINE.json configs[3]: K = 2000, M = 5000).  The price / order / probability rows, the
+// impact ratio, the net supply and the respawn pick table then live in a per-CTA global buffer (L2 resident);
+// only the accessors and the column staging differ, every arithmetic statement is shared.
 #pragma once
 #include <cuda.h>  // CUtensorMap (type only)
+#ifndef FSB_BIG
+#define FSB_BIG 0
+#endif
+#if FSB_BIG
+#define fsb_events1_kernel fsb_big_events1_kernel
+#define fsb_pass_kernel fsb_big_pass_kernel
+#define fsb_events2_kernel fsb_big_events2_kernel
+#endif
 
 #include "fsb_device.cuh"
 #include "fsb_state.h"
@@ -75,11 +88,13 @@ struct SmemLayout {
     int ndoubles, nints, nshorts;
     int off_ring, off_bars;  // byte offsets (pass kernel only)
     int bytes;
+    // big shapes: byte offsets of cols / ratio / sellsum / pick inside the per-CTA global buffer, and its size
+    long long big_cols, big_ratio, big_sellsum, big_pick, big_bytes;
 };
 
 // nslots: column slots of `cols` (slot 0: opening prices, 1: current prices, 2..: staged history columns /
 // order rows / probability rows, depending on the kernel)
-__host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap, int nslots, int nwarps, int ring_stages = 0)
+__host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap, int nslots, int nwarps, int ring_stages = 0, bool big = false)
 {
     // ring_stages > 0 marks the pass kernel, which needs none of the per-asset / per-investor event arrays
     const bool lean = ring_stages > 0;
@@ -89,11 +104,11 @@ __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap,
     const int kp = (L.kq + 127) & ~127;
     L.cpk = L.cp > kp ? L.cp : kp;
     int d = 0;
-    L.off_cols = d; d += nslots * L.cpk;
+    L.off_cols = d; d += big ? 0 : nslots * L.cpk;
     L.srows = ((nslots - 2) * L.cpk) / L.cp;
     L.wsd = (((nslots - 2) * L.cpk) / nwarps) & ~1;
-    L.off_ratio = d; d += lean ? 0 : L.cp;
-    L.off_sellsum = d; d += lean ? 0 : L.cp;
+    L.off_ratio = d; d += (lean || big) ? 0 : L.cp;
+    L.off_sellsum = d; d += (lean || big) ? 0 : L.cp;
     L.off_nav = d; d += L.kq;
     L.off_dstake = d; d += cap;
     L.off_dcash = d; d += cap;
@@ -117,7 +132,7 @@ __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap,
     L.off_wcnt = i; i += 2 * nwarps;
     L.off_flags = i; i += cap;
     L.off_nzf = i; i += cap;
-    L.off_pick = i; i += lean ? 0 : L.cp;
+    L.off_pick = i; i += (lean || big) ? 0 : L.cp;
     L.off_fmod = i; i += (K + 31) / 32;
     L.off_fsel = i; i += (K + 31) / 32;
     L.off_isc = i; i += 16;
@@ -131,6 +146,11 @@ __host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap,
     L.off_ring = (L.bytes + 127) & ~127;
     L.off_bars = L.off_ring + nwarps * ring_stages * kStageBytes;
     if (ring_stages > 0) L.bytes = L.off_bars + nwarps * ring_stages * 8 + nwarps * 8;  // + per-warp running stage counters
+    L.big_cols = 0;
+    L.big_ratio = L.big_cols + 8LL * nslots * L.cpk;
+    L.big_sellsum = L.big_ratio + 8LL * L.cp;
+    L.big_pick = L.big_sellsum + 8LL * L.cp;
+    L.big_bytes = big ? ((L.big_pick + 4LL * L.cp + 255) & ~255LL) : 0;
     return L;
 }
 
@@ -149,6 +169,7 @@ struct Ctx {
     int o_pos16, o_hor16, o_stl, o_hz, o_ring, o_bars;
     unsigned long long *mbar;
     unsigned mbar_phase;
+    unsigned char *big;       // FSB_BIG: this CTA's global buffer for the per-asset arrays
     const CUtensorMap *tm_h;  // pass kernel: the holdings of all replications as one 2-D tensor (kernel parameter space)
     // replication
     double *H, *P, *beta, *vol, *impact, *volume, *market, *stake, *amount, *threshold, *nav_open, *nav_close;
@@ -179,9 +200,14 @@ struct Ctx {
     long long r;
     long long tmark;
     // accessors
-    __device__ __forceinline__ double *cols_() const { return reinterpret_cast<double *>(fsb_smem + o_cols); }
-    __device__ __forceinline__ double *ratio_() const { return reinterpret_cast<double *>(fsb_smem + o_ratio); }
-    __device__ __forceinline__ double *sellsum_() const { return reinterpret_cast<double *>(fsb_smem + o_sellsum); }
+#if FSB_BIG
+#define FSB_ASSET_BASE big
+#else
+#define FSB_ASSET_BASE fsb_smem
+#endif
+    __device__ __forceinline__ double *cols_() const { return reinterpret_cast<double *>(FSB_ASSET_BASE + o_cols); }
+    __device__ __forceinline__ double *ratio_() const { return reinterpret_cast<double *>(FSB_ASSET_BASE + o_ratio); }
+    __device__ __forceinline__ double *sellsum_() const { return reinterpret_cast<double *>(FSB_ASSET_BASE + o_sellsum); }
     __device__ __forceinline__ double *nav_() const { return reinterpret_cast<double *>(fsb_smem + o_nav); }
     __device__ __forceinline__ double *d_stake_() const { return reinterpret_cast<double *>(fsb_smem + o_d_stake); }
     __device__ __forceinline__ double *d_cash_() const { return reinterpret_cast<double *>(fsb_smem + o_d_cash); }
@@ -202,7 +228,7 @@ struct Ctx {
     __device__ __forceinline__ int *wcnt_() const { return reinterpret_cast<int *>(fsb_smem + o_wcnt); }
     __device__ __forceinline__ int *flags_() const { return reinterpret_cast<int *>(fsb_smem + o_flags); }
     __device__ __forceinline__ int *nzf_() const { return reinterpret_cast<int *>(fsb_smem + o_nzf); }
-    __device__ __forceinline__ int *pick_() const { return reinterpret_cast<int *>(fsb_smem + o_pick); }
+    __device__ __forceinline__ int *pick_() const { return reinterpret_cast<int *>(FSB_ASSET_BASE + o_pick); }
     __device__ __forceinline__ int *fmod_() const { return reinterpret_cast<int *>(fsb_smem + o_fmod); }
     __device__ __forceinline__ int *fsel_() const { return reinterpret_cast<int *>(fsb_smem + o_fsel); }
     __device__ __forceinline__ int *isc_() const { return reinterpret_cast<int *>(fsb_smem + o_isc); }
@@ -291,14 +317,14 @@ __device__ __forceinline__ double *order_row(const Ctx &c, double *scratch, int 
 }
 
 // ---- out-of-line building blocks (one copy each in the instruction stream) -------------------------
-__device__ __noinline__ double ddiv(double x, double y) { return x / y; }
+static __device__ __noinline__ double ddiv(double x, double y) { return x / y; }
 // x / y, skipping the division for the very common zero numerator (assets a fund does not hold): for
 // 0 < y < inf the IEEE quotient of a zero is that same signed zero
 __device__ __forceinline__ double qdiv(double x, double y)
 {
     return (x == 0.0 && y > 0.0 && y < 1.7976931348623157e308) ? x : ddiv(x, y);
 }
-__device__ __noinline__ uint4 philox_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+static __device__ __noinline__ uint4 philox_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
     return philox4x32_10(make_uint4(c0, c1, c2, c3), k0, k1);
 }
@@ -312,7 +338,7 @@ __device__ __forceinline__ uint32_t draw_discrete_s(const Rng &g, uint32_t site,
     return __umulhi(word_of(w, idx & 3), n);
 }
 
-__device__ __noinline__ bool tape_lookup_raw(const fsb_tape_rec *tape, long long n_tape, int site, int t, int a, int b, double *out)
+static __device__ __noinline__ bool tape_lookup_raw(const fsb_tape_rec *tape, long long n_tape, int site, int t, int a, int b, double *out)
 {
     const unsigned long long key = (static_cast<unsigned long long>(site & 0xff) << 56) |
                                    (static_cast<unsigned long long>(t & 0xffffff) << 32) |
@@ -332,7 +358,7 @@ __device__ __forceinline__ bool tape_lookup(const Ctx &c, int site, int t, int a
     return tape_lookup_raw(c.tape, c.n_tape, site, t, a, b, out);
 }
 
-__device__ __noinline__ void trace_emit_raw(fsb_trace_rec *recs, int *n_ptr, int cap_trace, int *err_ptr, int t, int kind, int a, int b, double v)
+static __device__ __noinline__ void trace_emit_raw(fsb_trace_rec *recs, int *n_ptr, int cap_trace, int *err_ptr, int t, int kind, int a, int b, double v)
 {
     // single-thread emission (callers guard on tid == 0 and c.trace >= 0)
     const int n = *n_ptr;
@@ -350,7 +376,7 @@ __device__ __forceinline__ void trace_emit(const Ctx &c, int t, int kind, int a,
 }
 // trace points of a traced replication (cold): which = 0 reviewers + divestments, 1 cash-outs + prices
 // after the sale, 2 prices after the respawn, 3 opening NAVs, 4 choices
-__device__ __noinline__ void trace_phase(int t, int which, int n0, int n1)
+static __device__ __noinline__ void trace_phase(int t, int which, int n0, int n1)
 {
     Ctx &c = ctx();
     FSB_TH;
@@ -396,7 +422,7 @@ __device__ __forceinline__ int warp_compact(int lane, int n, int cap, int *out, 
 
 // counts (and, when traced, lists in ascending stock order) the price-floor hits flagged in
 // c.pick_()[] by the preceding marketmake phase; warp 0 only, no barrier inside
-__device__ __noinline__ void floor_account(int t, int phase)
+static __device__ __noinline__ void floor_account(int t, int phase)
 {
     Ctx &c = ctx();
     FSB_TH;
@@ -460,7 +486,7 @@ __device__ __forceinline__ int select_best(const unsigned long long *rho, int K,
 
 // One warp chooses a fund for reinvestor `inv` by "best", "goodenough" or "random"
 // (functions.jl:344-353, 381-395, 412-415); rho = horizonreturns of the reinvestor's column.
-__device__ __noinline__ int select_fund_warp(int t, int inv, const unsigned long long *rho, int selector)
+static __device__ __noinline__ int select_fund_warp(int t, int inv, const unsigned long long *rho, int selector)
 {
     Ctx &c = ctx();
     FSB_TH;
@@ -627,7 +653,7 @@ __device__ FSB_FP_INLINE void warp_rank256(const unsigned long long *keys, int K
 }
 
 // Rank by counting, any K (the general path): rank_k = 1 + #{j : key_j < key_k or (key_j == key_k and j < k)}
-__device__ __noinline__ void warp_rank_count(const unsigned long long *keys, int K, double *prob, const double *ranktab)
+static __device__ __noinline__ void warp_rank_count(const unsigned long long *keys, int K, double *prob, const double *ranktab)
 {
     const int lane = threadIdx.x & 31;
     for (int k = lane; k < K; k += 32) {
@@ -1366,7 +1392,7 @@ __device__ FSB_FP_INLINE int phase_liquidate(const DevState &s, const int t, con
 // step).  Q5: the trigger is the stake sums, the candidates are the all-zero rows.  Returns 0, or != 0
 // when the replication must stop (error flags already raised).
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ int phase_respawn(const int t, const int nd, const int flags)
+static __device__ __noinline__ int phase_respawn(const int t, const int nd, const int flags)
 {
     Ctx &c = ctx();
     FSB_TH;
@@ -1624,6 +1650,23 @@ __device__ FSB_FP_INLINE void phase_stage_columns(const DevState &s, const int t
     FSB_TH;
     const int Mp = c.Mp;
     const int ncopies = nc + (first ? (open_day ? 1 : 2) : 0);
+#if FSB_BIG
+    {   // the staged columns live in the CTA's global buffer: plain cooperative copies
+        __syncthreads();  // the previous chunk's readers are done with the slots
+        const int half = Mp >> 1;
+        for (int q = first ? 0 : 2; q < 2 + nc; ++q) {
+            if (q == 1 && open_day) continue;  // (an open day has no post-impact column)
+            const double *src = (q == 0) ? G.hand_p : (q == 1) ? G.P + static_cast<long long>(pcol(c, t)) * Mp
+                                                              : G.P + static_cast<long long>(pcol(c, t - c.hcols_()[c0 + q - 2])) * Mp;
+            double2 *dst = reinterpret_cast<double2 *>(c.cols_() + static_cast<long long>(q) * c.cpk);
+            const double2 *s2 = reinterpret_cast<const double2 *>(src);
+            for (int m = tid; m < half; m += NT) dst[m] = s2[m];
+        }
+        __syncthreads();
+        FSB_MARK(9);
+        return;
+    }
+#endif
     if (ncopies > 0) {
         const unsigned phase = c.mbar_phase;
         if (tid == 0) {
@@ -1979,7 +2022,7 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
     __shared__ __align__(8) unsigned long long mbar_sh;
     const int nwarps = blockDim.x >> 5;
     const int nslots = (KIND == KIND_PASS) ? s.cmax + 2 : (KIND == KIND_EVENTS1 ? s.slots_a : s.slots_c);
-    const SmemLayout L = make_layout(s.K, s.Mp, s.N, s.cap_ev, nslots, nwarps, (KIND == KIND_PASS) ? s.ring_stages : 0);
+    const SmemLayout L = make_layout(s.K, s.Mp, s.N, s.cap_ev, nslots, nwarps, (KIND == KIND_PASS) ? s.ring_stages : 0, FSB_BIG != 0);
     double *sd = reinterpret_cast<double *>(fsb_smem + kCtxBytes);
     if (threadIdx.x == 0) {
         c.K = s.K; c.M = s.M; c.N = s.N; c.Mp = s.Mp; c.T = s.T; c.W = s.W; c.cap = s.cap_ev; c.cmax = s.cmax;
@@ -1996,11 +2039,18 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         c.o_rev = bi + 4 * L.off_rev; c.o_rfund = bi + 4 * L.off_rfund; c.o_d_inv = bi + 4 * L.off_dinv; c.o_d_fund = bi + 4 * L.off_dfund;
         c.o_cash = bi + 4 * L.off_cash; c.o_r_choice = bi + 4 * L.off_rchoice; c.o_r_col = bi + 4 * L.off_rcol; c.o_hcols = bi + 4 * L.off_hcols;
         c.o_eggs = bi + 4 * L.off_eggs; c.o_wl = bi + 4 * L.off_wl; c.o_wcnt = bi + 4 * L.off_wcnt; c.o_flags = bi + 4 * L.off_flags;
-        c.o_nzf = bi + 4 * L.off_nzf; c.o_pick = bi + 4 * L.off_pick; c.o_fmod = bi + 4 * L.off_fmod; c.o_fsel = bi + 4 * L.off_fsel; c.o_isc = bi + 4 * L.off_isc;
+        c.o_nzf = bi + 4 * L.off_nzf; c.o_pick = bi + 4 * L.off_pick;
+        c.o_fmod = bi + 4 * L.off_fmod; c.o_fsel = bi + 4 * L.off_fsel; c.o_isc = bi + 4 * L.off_isc;
         c.o_pos16 = bs + 2 * L.off_pos16; c.o_hor16 = bs + 2 * L.off_hor16;
         c.o_stl = bs + 2 * L.nshorts;
         c.o_hz = c.o_stl + ((s.K + 15) & ~15);
         c.o_ring = L.off_ring; c.o_bars = L.off_bars;
+        c.big = nullptr;
+#if FSB_BIG
+        c.o_cols = static_cast<int>(L.big_cols); c.o_ratio = static_cast<int>(L.big_ratio); c.o_sellsum = static_cast<int>(L.big_sellsum);
+        c.o_pick = static_cast<int>(L.big_pick);
+        c.big = s.bigbuf + (static_cast<long long>(2 * a.batch + (KIND == KIND_EVENTS2 ? 1 : 0)) * s.scratch_ctas + blockIdx.x) * s.big_stride;
+#endif
         c.mbar = &mbar_sh; c.mbar_phase = 0;
         c.tm_h = tm_h;
         c.tmark = clock64();
@@ -2017,6 +2067,12 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         fence_mbar_init();
     }
     for (int q = threadIdx.x; q < L.ndoubles; q += blockDim.x) sd[q] = 0.0;  // zero pads once
+#if FSB_BIG
+    {
+        double *bz = reinterpret_cast<double *>(s.bigbuf + (static_cast<long long>(2 * a.batch + (KIND == KIND_EVENTS2 ? 1 : 0)) * s.scratch_ctas + blockIdx.x) * s.big_stride);
+        for (long long q = threadIdx.x; q < L.big_bytes / 8; q += blockDim.x) bz[q] = 0.0;
+    }
+#endif
     __syncthreads();
 
     int *const queue = s.queue + 2 * (3 * a.batch + KIND);

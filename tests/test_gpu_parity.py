@@ -375,6 +375,7 @@ def test_error_behaviour(fsb):
     {"FSB_NO_TMA": "1", "FSB_CMAX": "6"},
     {"FSB_BATCHES": "3"},                       # replication batches on separate streams
     {"FSB_EVENT_ROWS": "1"},                    # order rows spill to the global scratch
+    {"FSB_FORCE_BIG": "1"},                     # the big-shape build of the step kernels (per-asset arrays in global memory)
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_schedule_variants_are_invisible(fsb, orc, env, monkeypatch):
     """Launch-schedule knobs (column chunking, TMA-fed or register-fed pass, replication batches, order-row
@@ -414,6 +415,29 @@ def test_large_shapes_general_path(fsb, orc, shape):
     (register-fed pass, rank by counting, wider columns) against the oracle, all selectors' hot one included."""
     p = fsb.Params.default(reviewprobability=0.12, invcaprange=(10, 1000), **shape)
     R = 3
+    with fsb.Engine(p, R, keep_history=True) as eng:
+        eng.init_device(SEED)
+        eng.run(selector="probabilistic")
+        assert not eng.rep_status().any()
+        for r in range(R):
+            w = H.oracle_world(orc, p, SEED, r, trace=False)
+            assert w.modelrun(selector="probabilistic") == 0
+            w.finalise_fund_value(p.bigt)
+            H.assert_state_equal(eng.download_state(r), w)
+            H.assert_log_equal(eng.download_log(r), w.log())
+            w.close()
+
+
+@pytest.mark.parametrize("shape,R", [
+    (dict(bigk=64, bign=256, bigm=5000, bigt=125, portfsizerange=(2500, 5000), reviewprobability=0.1), 3),
+    (dict(bigk=2000, bign=8000, bigm=5000, bigt=104, portfsizerange=(2500, 5000)), 1),
+], ids=["K64_M5000", "config4_K2000_M5000_N8000"])
+def test_big_shapes_per_asset_arrays_in_global_memory(fsb, orc, shape, R):
+    """BASELINE.json configs[3] (2000 funds x 5000 assets, dense overlapping portfolios, N = 4K investors, W = 100)
+    for its first simulated days, and a 5000-asset universe with fewer funds for longer: a price column (40 KB)
+    no longer fits in shared memory next to the event lists, so the engine launches the big-shape build of the
+    three step kernels (fsb_step_big.cu).  Every array against the oracle, bit for bit."""
+    p = fsb.Params.default(**shape)
     with fsb.Engine(p, R, keep_history=True) as eng:
         eng.init_device(SEED)
         eng.run(selector="probabilistic")
