@@ -49,7 +49,10 @@ namespace fsb {
 
 constexpr double kPriceFloor = 0.000000001;  // functions.jl:208-209 (Q10)
 constexpr int kMaxCols = 14;                 // horizon columns per full pass (4 groups x 4 columns, minus the 2 price columns)
-constexpr int kStepThreads = 128;
+#ifndef FSB_STEP_THREADS
+#define FSB_STEP_THREADS 128
+#endif
+constexpr int kStepThreads = FSB_STEP_THREADS;  // CTA of the event kernels
 #ifndef FSB_RING_STAGES
 #define FSB_RING_STAGES 2
 #endif

@@ -179,6 +179,12 @@ class World:
         except Exception:
             pass
 
+    def load_state(self, st):
+        """Overwrite the dense state (after-initialise arrays of a recording / of another world)."""
+        for name in ("market", "stock_value", "beta", "vol", "impact", "volume", "inv_assets", "threshold", "holdings",
+                     "stakes", "fund_value", "horizon"):
+            getattr(self, name)[...] = st[name]
+
     # draws ---------------------------------------------------------------------------------
     def set_rng(self, seed, rep):
         lib().orc_set_rng(self._h, seed, rep)

@@ -13,9 +13,12 @@ ap.add_argument("--t0", type=int, default=102)
 ap.add_argument("--steps-per-launch", type=int, default=1)
 ap.add_argument("--blocks-per-sm", type=int, default=0)
 ap.add_argument("--block-threads", type=int, default=0)
+ap.add_argument("--config4", action="store_true", help="BASELINE.json configs[3]: 2000 funds x 5000 assets, N = 8000, dense portfolios")
 a = ap.parse_args()
 fsb = load_package()
 p = fsb.Params.default()
+if a.config4:
+    p = fsb.Params.default(bigk=2000, bigm=5000, bign=8000, bigt=1101, portfsizerange=(2500, 5000))
 with fsb.Engine(p, a.reps, steps_per_launch=a.steps_per_launch, blocks_per_sm=a.blocks_per_sm,
                 block_threads=a.block_threads) as eng:
     eng.init_device(7)
@@ -24,7 +27,7 @@ with fsb.Engine(p, a.reps, steps_per_launch=a.steps_per_launch, blocks_per_sm=a.
         eng.sync()
     eng.run_async(a.t0, a.t0 + a.steps - 1)  # replications the model itself stops (Q6) stay frozen, not fatal
     eng.sync()
-    ms, _, n = eng.last_run_timing()
+    ms, pass_ms, n = eng.last_run_timing()
     nerr = int((eng.rep_status() != 0).sum())
     print(f"reps={a.reps} steps={a.steps} launches={n} total_ms={ms:.3f} per_launch_ms={ms / n:.4f} "
-          f"fund_steps_per_s={a.reps * p.bigk * a.steps / (ms * 1e-3):.4e} frozen_reps={nerr}")
+          f"fund_steps_per_s={a.reps * p.bigk * a.steps / (ms * 1e-3):.4e} frozen_reps={nerr} pass_ms={pass_ms:.3f}")

@@ -68,3 +68,50 @@ def assert_trace_equal(tr, w, t_range):
     assert eq(tr["nav_open"][:, cols], w.trace_nav_open[:, cols]), "nav_open"
     assert eq(tr["p_sell"][:, cols], w.trace_p_sell[:, cols]), "p_sell"
     assert eq(tr["p_resp"][:, cols], w.trace_p_resp[:, cols]), "p_resp"
+
+
+STATE_FIELDS = ("market", "stock_value", "beta", "vol", "impact", "volume", "inv_assets", "horizon", "threshold",
+                "holdings", "stakes", "fund_value")
+
+
+def world_state(w):
+    return {k: np.array(getattr(w, k), copy=True) for k in STATE_FIELDS}
+
+
+def events_from_trace(fsb, orc, w):
+    """The oracle's own anchors / portfolio sizes and picks / fund choices as event-tape records
+    (site, t, a, b, value), ids 0-based -- what julia/record_tapes.jl captures from the reference."""
+    L = fsb._lib
+    recs, ordinal, pick_j = [], {}, {}
+    for e in w.trace():
+        t = int(e["t"])
+        if e["kind"] == orc.EV_SPAWN:
+            i = ordinal.get(t, 0)
+            ordinal[t] = i + 1
+            recs.append((L.TAPE_ANCHOR, t, i, 0, float(e["b"])))
+            pick_j[t] = (i, 0)
+        elif e["kind"] == orc.EV_SPAWN_N:
+            recs.append((L.TAPE_RPSIZE, t, pick_j[t][0], 0, float(e["b"])))
+        elif e["kind"] == orc.EV_PICK:
+            i, j = pick_j[t]
+            recs.append((L.TAPE_RPPICK, t, i, j, float(e["b"])))
+            pick_j[t] = (i, j + 1)
+        elif e["kind"] == orc.EV_CHOICE:
+            recs.append((L.TAPE_CHOICE_IDX, t, int(e["a"]), 0, float(e["b"])))
+    return recs
+
+
+def oracle_recording(fsb, orc, p, seed, rep, selector):
+    """A recording in the format of julia/record_tapes.jl, with the oracle standing in for the reference:
+    numpy shocks as dense tapes, the oracle's event draws read back from its trace."""
+    rng = np.random.default_rng(seed)
+    dense = dict(z_mkt=rng.standard_normal(p.bigt), z_stock=rng.standard_normal((p.bigm, p.bigt)),
+                 u_review=rng.random((p.bign, p.bigt)))
+    w = oracle_world(orc, p, seed, rep)
+    init = world_state(w)
+    w.set_dense_tape(dense["z_mkt"], dense["z_stock"], dense["u_review"])
+    assert w.modelrun(selector=selector) == 0
+    w.finalise_fund_value(p.bigt)
+    rec = dict(W=p.perfwindow[-1], reviewprobability=p.reviewprobability, selector=selector, seed=seed, init=init,
+               dense=dense, events=events_from_trace(fsb, orc, w), final=world_state(w), log=w.log())
+    return rec, w

@@ -3,10 +3,15 @@ oracle on the same seeded inputs.  Bar (BASELINE.json north_star): discrete outc
 FP64 NAVs, prices and flows within 1e-12 relative -- the engine and the oracle share one
 canonical operation order, so these tests demand bit-equality and fall back to 1e-12 nowhere.
 """
+import importlib
+import os
+
 import numpy as np
 import pytest
 
 import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -481,3 +486,22 @@ def test_hosttape_steps_match_the_oracle_on_the_same_draws(fsb, orc):
         for i in range(NS):
             assert H.eq(navs[i][r], w.trace_nav_open[:, T0 + i - 1]), i
         w.close()
+
+
+def test_replay_of_a_recording_file(fsb, orc, tmp_path):
+    """scripts/replay_reference_tapes.py on a recording in the format julia/record_tapes.jl writes (the oracle
+    stands in for the reference, which cannot run in this image): upload the recorded state, feed the recorded
+    draws, compare with the recorded outcome.  Against the oracle the match is exact."""
+    import importlib.util
+    tf = importlib.import_module(fsb.__name__ + ".tapefile")
+    spec = importlib.util.spec_from_file_location("replay_reference_tapes", os.path.join(ROOT, "scripts", "replay_reference_tapes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    p = H.small_params(fsb, bigk=9, bigm=9, bign=70, bigt=80)
+    rec, w = H.oracle_recording(fsb, orc, p, seed=33, rep=1, selector="probabilistic")
+    w.close()
+    assert len(rec["events"]) > 20
+    path = tmp_path / "rec.fsbtape"
+    tf.write_tape_file(path, **rec)
+    worst = mod.replay(fsb, tf.read_tape_file(path))
+    assert max(worst.values()) == 0.0, worst

@@ -2,11 +2,14 @@
 fails loudly without a CUDA device, and the host-side mirror of the reference's Params / Types API
 behaves like the reference's own tests expect (test/params_test.jl, test/types_test.jl)."""
 import ctypes as C
+import importlib
 import os
 import re
 
 import numpy as np
 import pytest
+
+import helpers as H
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -159,3 +162,30 @@ def test_stats_decoding(fsb):
     assert st["replications"] == 5 and st["liquidations"] == 7 and st["replication_steps"] == 90
     assert st["failtime_hist"][12] == 3 and st["liquidations_per_replication_hist"][2] == 4
     assert len(st["market_drawdown_hist"]) == L.STATS_DD_BINS and len(st["flow_hist"]) == L.STATS_FLOW_BINS
+
+
+def test_recorder_file_round_trip(fsb, orc, tmp_path):
+    """The file format of julia/record_tapes.jl (the recorder around the real reference, which this image cannot
+    run): a recording produced from the oracle is written, read back and replayed through the oracle."""
+    tf = importlib.import_module(fsb.__name__ + ".tapefile")
+    rec, w = H.oracle_recording(fsb, orc, H.small_params(fsb), seed=21, rep=2, selector="probabilistic")
+    path = tmp_path / "rec.fsbtape"
+    tf.write_tape_file(path, **rec)
+    back = tf.read_tape_file(path)
+    assert back["selector"] == "probabilistic" and back["W"] == rec["W"] and back["reviewprobability"] == rec["reviewprobability"]
+    for k in tf.STATE_FIELDS:
+        assert H.eq(back["init"][k], rec["init"][k]) and H.eq(back["final"][k], rec["final"][k]), k
+    assert back["events"] == [tuple(e) for e in rec["events"]]
+    for k in ("z_mkt", "z_stock", "u_review"):
+        assert H.eq(back["dense"][k], rec["dense"][k])
+    # replay through the oracle: a fresh world from the recorded initial state under the recorded tapes
+    p = H.small_params(fsb)
+    w2 = orc.World(p, seed=999, rep=0)
+    w2.load_state(back["init"])
+    w2.set_dense_tape(back["dense"]["z_mkt"], back["dense"]["z_stock"], back["dense"]["u_review"])
+    w2.set_event_tape([e for e in back["events"] if e[0] != fsb._lib.TAPE_CHOICE_U])
+    assert w2.modelrun(selector="random") == 0  # (the taped choice indices override the selector)
+    w2.finalise_fund_value(p.bigt)
+    assert H.eq(w2.holdings, back["final"]["holdings"]) and H.eq(w2.stock_value, back["final"]["stock_value"])
+    assert H.eq(w2.inv_assets, back["final"]["inv_assets"]) and H.eq(w2.stakes, back["final"]["stakes"])
+    w.close(); w2.close()
