@@ -369,6 +369,28 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
             return cleanup(fail(FSB_ERR_CUDA, "cannot upload parameter tables"));
         d.points = pd; d.tables = td; d.ranktab = rt;
     }
+    {   // per-replication pointer table of the step context (order: the pointer block of Ctx, fsb_step.cuh)
+        const unsigned long long K = d.K, N = d.N, Mp = d.Mp, CL = d.cap_log;
+        const unsigned long long kq = (d.K + 3) & ~3;
+        struct { const void *base; unsigned long long stride; } rows[kRepPtrs] = {
+            {d.H, static_cast<unsigned long long>(d.h_stride) * 8}, {d.P, static_cast<unsigned long long>(d.p_stride) * 8},
+            {d.beta, Mp * 8}, {d.vol, Mp * 8}, {d.impact, Mp * 8},
+            {d.volume, d.volume ? static_cast<unsigned long long>(d.T) * Mp * 8 : 0}, {d.market, static_cast<unsigned long long>(d.mkt_len) * 8},
+            {d.stake, N * 8}, {d.amount, N * 8}, {d.threshold, N * 8}, {d.nav_open, K * 8}, {d.nav_close, K * 8},
+            {d.pos, N * 4}, {d.horizon, N * 4}, {d.live_row, K * 4}, {d.cnt, static_cast<unsigned long long>(kCnt) * 4},
+            {d.hzero, K}, {d.stakeless, K}, {d.mkt_peak, 8}, {d.mkt_dd, 8},
+            {d.flow_hist, static_cast<unsigned long long>(kFlowBins) * 4}, {d.err, 4},
+            {d.log_n, 4}, {d.log_liquidated, CL * 4}, {d.log_replacedby, CL * 4}, {d.log_failtime, CL * 4}, {d.log_ninv, CL * 4},
+            {d.log_nstocks, CL * 4}, {d.log_size, CL * 8}, {d.log_liquidity, CL * 8},
+            {d.keys, static_cast<unsigned long long>(d.kc) * kq * 8}};
+        std::vector<ulonglong2> tab(kRepPtrs);
+        for (int i = 0; i < kRepPtrs; ++i) tab[i] = make_ulonglong2(reinterpret_cast<unsigned long long>(rows[i].base), rows[i].stride);
+        ulonglong2 *pt = nullptr;
+        if (dalloc(e, &pt, static_cast<size_t>(kRepPtrs)) != FSB_OK) return cleanup(FSB_ERR_CUDA);
+        if (cudaMemcpy(pt, tab.data(), tab.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice) != cudaSuccess)
+            return cleanup(fail(FSB_ERR_CUDA, "cannot upload the pointer table"));
+        d.ptr_table = pt;
+    }
     e->words_per_point = FSB_STATS_HEADER + (d.T + 1) + FSB_STATS_LIQ_BINS + FSB_STATS_DD_BINS + FSB_STATS_FLOW_BINS;
     if (dalloc(e, &e->stats_dev, static_cast<size_t>(n_points) * e->words_per_point) != FSB_OK) return cleanup(FSB_ERR_CUDA);
     e->z_mkt.assign(R, nullptr); e->z_stock.assign(R, nullptr); e->u_review.assign(R, nullptr);

@@ -83,6 +83,9 @@ struct DevState {
     double *hand_p;            // [R][Mp] opening prices of the day
     double *hand_s;            // [R][Mp] net sale per asset of the day (keep_history only, else null)
     const double *ranktab;     // [K] (i + 1) / (K (K + 1) / 2): rank probabilities of the rank rule (Q14)
+    // per-replication pointers of the step context: [kRepPtrs] x (base address, stride in bytes); lane i of a
+    // CTA computes pointer i of the replication it starts on (order = the pointer block of Ctx, fsb_step.cuh)
+    const ulonglong2 *ptr_table;
     int *queue;       // [3][2] dynamic work counters per kernel kind (double buffered across launches)
     const DevPoint *points;
     const double *tables;

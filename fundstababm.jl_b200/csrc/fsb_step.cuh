@@ -174,7 +174,8 @@ struct Ctx {
     unsigned mbar_phase;
     unsigned char *big;       // FSB_BIG: this CTA's global buffer for the per-asset arrays
     const CUtensorMap *tm_h;  // pass kernel: the holdings of all replications as one 2-D tensor (kernel parameter space)
-    // replication
+    // replication: kRepPtrs pointers = base + r * stride, filled by kRepPtrs lanes from DevState::ptr_table
+    // (same order there; they serve the out-of-line cold paths, the inlined phases use rep_ptrs)
     double *H, *P, *beta, *vol, *impact, *volume, *market, *stake, *amount, *threshold, *nav_open, *nav_close;
     int *pos, *horizon, *live_row, *cnt;
     unsigned char *hzero, *stakeless;
@@ -183,9 +184,9 @@ struct Ctx {
     // liquidation log of the replication (functions.jl:452-456)
     int *log_n, *log_liquidated, *log_replacedby, *log_failtime, *log_ninv, *log_nstocks;
     double *log_size, *log_liquidity;
+    unsigned long long *keys;  // [cmax][kq] horizon returns of the step (sort keys or raw bits), L2 resident
     // per-CTA global scratch
     double *scratch;           // order rows beyond the shared-memory ones
-    unsigned long long *keys;  // [cmax][kq] horizon returns of the step (sort keys or raw bits), L2 resident
     const double *ranktab;
     // draws
     const double *z_mkt, *z_stock, *u_review;
@@ -298,6 +299,9 @@ __device__ __forceinline__ Rep rep_ptrs(const DevState &s, const long long r, co
     return g;
 }
 
+constexpr int kRepPtrs = 31;
+static_assert(offsetof(Ctx, keys) - offsetof(Ctx, H) == (kRepPtrs - 1) * 8, "the replication pointers of Ctx must be one contiguous block");
+static_assert(sizeof(Ctx) <= kCtxBytes, "Ctx outgrew its shared-memory slot");
 __device__ __forceinline__ Ctx &ctx() { return *reinterpret_cast<Ctx *>(fsb_smem); }
 
 #define FSB_TH                                                                               \
@@ -2086,6 +2090,10 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         const long long r = a.r_begin + r_sh;
         if (r >= a.r_end) break;
         const int frozen = s.err[r] & ~FSB_REP_TRACE_OVERFLOW;
+        if (threadIdx.x < kRepPtrs && !frozen) {  // one lane per pointer: base + r * stride
+            const ulonglong2 e = __ldg(s.ptr_table + threadIdx.x);
+            reinterpret_cast<unsigned long long *>(&c.H)[threadIdx.x] = e.x + static_cast<unsigned long long>(r) * e.y;
+        }
         if (threadIdx.x == 0 && !frozen) {
             const long long g = s.rep_offset + r;
             const DevPoint &pt = s.points[s.reps_per_point > 0 ? static_cast<int>(g / s.reps_per_point) : 0];
@@ -2093,24 +2101,6 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
             c.rng.rep = static_cast<uint32_t>(g);
             c.drift = pt.drift; c.marketvol = pt.marketvol; c.reviewprob = pt.reviewprob;
             c.psize_lo = pt.psize_lo; c.psize_hi = pt.psize_hi;
-            c.H = s.H + r * s.h_stride;
-            c.P = s.P + r * s.p_stride;
-            c.beta = s.beta + r * s.Mp; c.vol = s.vol + r * s.Mp; c.impact = s.impact + r * s.Mp;
-            c.volume = s.volume ? s.volume + r * static_cast<long long>(s.T) * s.Mp : nullptr;
-            c.market = s.market + r * s.mkt_len;
-            c.pos = s.pos + r * s.N; c.horizon = s.horizon + r * s.N;
-            c.stake = s.stake + r * s.N; c.amount = s.amount + r * s.N; c.threshold = s.threshold + r * s.N;
-            c.nav_open = s.nav_open + r * s.K; c.nav_close = s.nav_close + r * s.K;
-            c.hzero = s.hzero + r * s.K; c.stakeless = s.stakeless + r * s.K; c.live_row = s.live_row + r * s.K;
-            c.cnt = s.cnt + r * kCnt;
-            c.mkt_peak = s.mkt_peak + r; c.mkt_dd = s.mkt_dd + r;
-            c.flow_hist = s.flow_hist + r * kFlowBins; c.err = s.err + r;
-            const long long lb = r * s.cap_log;
-            c.log_n = s.log_n + r;
-            c.log_liquidated = s.log_liquidated + lb; c.log_replacedby = s.log_replacedby + lb;
-            c.log_failtime = s.log_failtime + lb; c.log_ninv = s.log_ninv + lb; c.log_nstocks = s.log_nstocks + lb;
-            c.log_size = s.log_size + lb; c.log_liquidity = s.log_liquidity + lb;
-            c.keys = s.keys + r * (static_cast<long long>(s.kc) * L.kq);
             c.z_mkt = s.any_tape ? s.z_mkt[r] : nullptr;
             c.z_stock = s.any_tape ? s.z_stock[r] : nullptr;
             c.u_review = s.any_tape ? s.u_review[r] : nullptr;
