@@ -863,15 +863,20 @@ __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, con
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(fsb_smem + c.o_bars) + warp * S;
     // the ring's mbarriers are initialised once per kernel; gbase = stages this warp has consumed so far
     // (slot and phase parity of a stage follow from its running index)
-    long long *gcount = reinterpret_cast<long long *>(fsb_smem + c.o_bars + nwarps * S * 8) + warp;
-    const long long gbase = *gcount;
+    // (a 32-bit counter: S is a power of two, so slot and parity survive its wrap-around)
+    static_assert((S & (S - 1)) == 0, "the ring needs a power-of-two number of stages");
+    constexpr int LS = (S == 1) ? 0 : (S == 2) ? 1 : (S == 4) ? 2 : 3;
+    unsigned *gcount = reinterpret_cast<unsigned *>(fsb_smem + c.o_bars + nwarps * S * 8) + 2 * warp;
+    const unsigned gbase = *gcount;
     const CUtensorMap *const tm = c.tm_h;
     const int grow0 = static_cast<int>(c.r) * K4;  // this replication's first row in the 2-D view of all holdings
     auto issue = [&](int g) {  // stage g of this warp's sequence -> slot g % S: ONE tensor copy of 8 rows x kStageRowBytes
-        const int slot = static_cast<int>((gbase + g) % S), tg = warp + (g / PT) * nwarps, part = g % PT;
-        __syncwarp();  // every lane is done with the slot's previous contents
+        const int slot = static_cast<int>((gbase + g) & (S - 1)), tg = warp + (g / PT) * nwarps, part = g % PT;
+        // every lane is done with the slot's previous contents: their loads have RETURNED (the FMAs that
+        // consumed them precede this point), so the asynchronous proxy may overwrite the slot without a
+        // proxy fence (the write-after-read case; a fence is for generic WRITES the async proxy reads)
+        __syncwarp();
         if (lane == 0) {
-            fence_proxy_async();
             mbar_expect_tx(bars + slot, kStageBytes);
             // (rows past K4 - 1 of the last trip belong to the next replication or are zero filled: their results are dropped)
             tensor_g2s_2d(ring + slot * kStageBytes, tm, part * (kStageRowBytes / 8), grow0 + 8 * tg, bars + slot);
@@ -890,8 +895,8 @@ __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, con
         for (int part = 0; part < PT; ++part) {
             const int g = g0 + part;
             if (g + S - 1 < nstages) issue(g + S - 1);
-            const int slot = static_cast<int>((gbase + g) % S);
-            mbar_wait(bars + slot, static_cast<unsigned>(((gbase + g) / S) & 1));
+            const int slot = static_cast<int>((gbase + g) & (S - 1));
+            mbar_wait(bars + slot, ((gbase + g) >> LS) & 1u);
             const double2 *hs = reinterpret_cast<const double2 *>(ring + slot * kStageBytes) + (R * qa) * RW + j;
             const double2 *cp_i = colp + RW * part;
 #pragma unroll
@@ -945,7 +950,7 @@ __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, con
         }
     }
     __syncwarp();
-    if (lane == 0) *gcount = gbase + nstages;
+    if (lane == 0) *gcount = gbase + static_cast<unsigned>(nstages);
     __syncwarp();
 }
 
