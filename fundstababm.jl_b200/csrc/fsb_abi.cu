@@ -101,6 +101,7 @@ struct fsb_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // replication batches: each runs its three kernels per step on its own stream, so that the memory-bound
     // holdings pass of one batch overlaps the latency-bound event kernels of another
+    int block_e2 = 0;
     int n_batches = 1;
     std::vector<cudaStream_t> bstream;
     std::vector<cudaEvent_t> bjoin;
@@ -232,6 +233,9 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     CU(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     const int nw = e->block / 32;
+    // events-2 may run wider CTAs than events-1 (one warp per horizon column in its rank phase)
+    e->block_e2 = (cfg->block_threads > 0) ? e->block : kE2Threads;
+    const int nw2 = e->block_e2 / 32;
     e->block_pass = (d.K <= 256 && d.Mp == 256 && !getenv("FSB_NO_TMA")) ? kPassThreads : e->block;
     if (const char *ev = getenv("FSB_PASS_THREADS")) e->block_pass = std::max(32, std::min(kPassThreads, (atoi(ev) / 32) * 32));
     int nwp = e->block_pass / 32;
@@ -249,10 +253,10 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     nwp = e->block_pass / 32;
     while (!d.big && make_layout(d.K, d.Mp, d.N, d.cap_ev, d.cmax + 2, nwp, d.ring_stages).bytes + 64 > budget && d.cmax > 6) d.cmax -= 4;
     d.slots_a = 2 + 6;
-    d.slots_c = 2 + std::max(nw, 6);
-    if (const char *ev = getenv("FSB_EVENT_ROWS")) { d.slots_a = 2 + std::max(1, atoi(ev)); d.slots_c = 2 + std::max(nw, atoi(ev)); }
+    d.slots_c = 2 + std::max(nw2, 6);
+    if (const char *ev = getenv("FSB_EVENT_ROWS")) { d.slots_a = 2 + std::max(1, atoi(ev)); d.slots_c = 2 + std::max(nw2, atoi(ev)); }
     while (!d.big && make_layout(d.K, d.Mp, d.N, d.cap_ev, d.slots_a, nw).bytes + 64 > smem_max && d.slots_a > 3) --d.slots_a;
-    while (!d.big && make_layout(d.K, d.Mp, d.N, d.cap_ev, d.slots_c, nw).bytes + 64 > smem_max && d.slots_c > 2 + nw) --d.slots_c;
+    while (!d.big && make_layout(d.K, d.Mp, d.N, d.cap_ev, d.slots_c, nw2).bytes + 64 > smem_max && d.slots_c > 2 + nw2) --d.slots_c;
     d.kc = std::min(d.W, std::max(std::max(32, 2 * kMaxCols), d.cap_ev / 2));  // (distinct horizons of a step's cash holders)
     d.hi_stride = hand_ints(d.K, d.cap_ev);
     e->init_smem = (d.W + 2 + d.K) * 8;
@@ -264,7 +268,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
         const void *const *kern = d.big ? kern_big : kern_std;
         d.big_stride = 0;
         for (int k = 0; k < 3; ++k) {
-            const int blk = (k == 1) ? e->block_pass : e->block;
+            const int blk = (k == 1) ? e->block_pass : (k == 2) ? e->block_e2 : e->block;
             const SmemLayout L = make_layout(d.K, d.Mp, d.N, d.cap_ev, slots[k], blk / 32, k == 1 ? d.ring_stages : 0, d.big != 0);
             d.big_stride = std::max(d.big_stride, L.big_bytes);
             if (L.bytes + 64 > smem_max) { delete e; return fail(FSB_ERR_BAD_PARAMS, "shapes need %d bytes of shared memory per CTA (> %d)", L.bytes, smem_max); }
@@ -712,8 +716,8 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                 if (timed) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st)); e->kev_used += 2; }
                 if (ht && ht->nav_open_out)  // the NAVs of :460 are final after the pass: device -> host while events-2 runs
                     CU(cudaMemcpyAsync(ht->nav_open_out + a.r_begin * d.K, d.nav_open + a.r_begin * d.K, rb * d.K * 8, cudaMemcpyDeviceToHost, st));
-                if (d.big) fsb_big_events2_kernel<<<g3, e->block, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
-                else fsb_events2_kernel<<<g3, e->block, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
+                if (d.big) fsb_big_events2_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
+                else fsb_events2_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
                 e->last_launches += 3;
             }
             e->launch_parity ^= 1;

@@ -53,6 +53,10 @@ constexpr int kMaxCols = 14;                 // horizon columns per full pass (4
 #define FSB_STEP_THREADS 128
 #endif
 constexpr int kStepThreads = FSB_STEP_THREADS;  // CTA of the event kernels
+#ifndef FSB_E2_THREADS
+#define FSB_E2_THREADS FSB_STEP_THREADS
+#endif
+constexpr int kE2Threads = FSB_E2_THREADS;      // CTA of the events-2 kernel
 #ifndef FSB_RING_STAGES
 #define FSB_RING_STAGES 2
 #endif
@@ -2144,7 +2148,10 @@ __global__ void __launch_bounds__(kPassThreads, 2) fsb_pass_kernel(const DevStat
 {
     phase_kernel_body<KIND_PASS>(s, a, launch_parity, &tm_h);
 }
-__global__ void __launch_bounds__(kStepThreads, FSB_EV_CTAS) fsb_events2_kernel(const DevState s, const StepArgs a, const int launch_parity)
+#ifndef FSB_E2_CTAS
+#define FSB_E2_CTAS FSB_EV_CTAS
+#endif
+__global__ void __launch_bounds__(kE2Threads, FSB_E2_CTAS) fsb_events2_kernel(const DevState s, const StepArgs a, const int launch_parity)
 {
     phase_kernel_body<KIND_EVENTS2>(s, a, launch_parity, nullptr);
 }
