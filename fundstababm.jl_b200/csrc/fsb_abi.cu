@@ -232,10 +232,10 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     CU(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     CU(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-    const int nw = e->block / 32;
+    int nw = e->block / 32;
     // events-2 may run wider CTAs than events-1 (one warp per horizon column in its rank phase)
     e->block_e2 = (cfg->block_threads > 0) ? e->block : kE2Threads;
-    const int nw2 = e->block_e2 / 32;
+    int nw2 = e->block_e2 / 32;
     e->block_pass = (d.K <= 256 && d.Mp == 256 && !getenv("FSB_NO_TMA")) ? kPassThreads : e->block;
     if (const char *ev = getenv("FSB_PASS_THREADS")) e->block_pass = std::max(32, std::min(kPassThreads, (atoi(ev) / 32) * 32));
     int nwp = e->block_pass / 32;
@@ -243,6 +243,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     if (getenv("FSB_NO_TMA")) d.ring_stages = 0;
     // big shapes: even the leanest events-1 layout (3 column slots) does not fit in shared memory
     d.big = (make_layout(d.K, d.Mp, d.N, d.cap_ev, 3, nw).bytes + 64 > smem_max || getenv("FSB_FORCE_BIG")) ? 1 : 0;
+    if (d.big && cfg->block_threads <= 0) { e->block = e->block_e2 = kBigStepThreads; nw = nw2 = kBigStepThreads / 32; }
     if (d.big) { d.ring_stages = 0; e->block_pass = getenv("FSB_BIG_PASS_THREADS") ? std::max(32, std::min(kPassThreads, (atoi(getenv("FSB_BIG_PASS_THREADS")) / 32) * 32)) : kPassThreads; }
     int want_ctas = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : (d.ring_stages ? 2 : 4);
     if (const char *ev = getenv("FSB_CTAS_PER_SM")) want_ctas = std::max(1, atoi(ev));

@@ -64,6 +64,7 @@ constexpr int kE2Threads = FSB_E2_THREADS;      // CTA of the events-2 kernel
 #define FSB_STAGE_ROW_BYTES 512
 #endif
 constexpr int kRingStages = FSB_RING_STAGES;  // per-warp ring of holdings stages (pass kernel, default shape)
+constexpr int kBigStepThreads = 256;   // CTA of the event kernels in the big-shape build (fsb_step_big.cu)
 constexpr int kPassThreads = 256;      // the pass kernel's CTA: 8 warps share the staged columns
 constexpr int kStageRowBytes = FSB_STAGE_ROW_BYTES;  // bytes of a holdings row per stage (128 per word step)
 constexpr int kStageBytes = 8 * kStageRowBytes;      // a stage = 8 rows
