@@ -279,7 +279,7 @@ def main():
     peak, peak_src = measured_peak()
     # the dominant kernel: the holdings pass, one launch per simulated day and replication batch, timed launch by
     # launch with CUDA events on the launching streams (fsb_last_run_timing)
-    n_pass = max(1, launches // 3)
+    n_pass = max(1, eng.last_pass_launches())
     per_launch_ms = pass_ms / n_pass
     reps_per_launch = R * args.steps / n_pass
     alg_bytes_per_launch = reps_per_launch * K * b_alg_pass(K, M, N)

@@ -802,6 +802,8 @@ extern "C" int32_t fsb_last_run_timing(fsb_engine *e, double *total_ms, double *
     return FSB_OK;
 }
 
+extern "C" int64_t fsb_last_pass_launches(const fsb_engine *e) { return e ? e->last_pass_launches : 0; }
+
 extern "C" int32_t fsb_rep_status(fsb_engine *e, int32_t *flags)
 {
     if (!e || !flags) return fail(FSB_ERR_BAD_PARAMS, "null argument");

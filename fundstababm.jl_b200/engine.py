@@ -151,6 +151,9 @@ class Engine:
         L.check(L.lib().fsb_last_run_timing(self._h, C.byref(tot), C.byref(stp), C.byref(n)))
         return tot.value, stp.value, n.value
 
+    def last_pass_launches(self):
+        return int(L.lib().fsb_last_pass_launches(self._h))
+
     def rep_status(self):
         out = np.zeros(self.n_reps, dtype=np.int32)
         L.check(L.lib().fsb_rep_status(self._h, out.ctypes.data))

@@ -202,6 +202,8 @@ int32_t fsb_stats_all(fsb_engine **engines, int32_t n, uint64_t *out);
  * the launches of the dominant kernel (the holdings pass, fsb_pass_kernel; events on the stream of every
  * launch); number of kernel launches of the last fsb_run (three per simulated day and replication batch) */
 int32_t fsb_last_run_timing(fsb_engine *e, double *total_ms, double *step_kernel_ms, int64_t *launches);
+/* how many launches of the dominant kernel step_kernel_ms sums over */
+int64_t fsb_last_pass_launches(const fsb_engine *e);
 /* asynchronous variant used for overlapping several engines in one process */
 int32_t fsb_run_async(fsb_engine *e, int64_t t_first, int64_t t_last, int32_t selector, int32_t flags);
 int32_t fsb_sync(fsb_engine *e);
