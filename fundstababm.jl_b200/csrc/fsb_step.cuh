@@ -13,7 +13,7 @@
 //   fsb_pass_kernel     the K x M holdings cross HBM ONCE: up to cmax history columns + the day's two price
 //                          columns staged in shared memory by bulk asynchronous copies; 8-row trips per warp, the
 //                          four 8-lane groups in a 2 x 2 (rows x columns) arrangement, holdings through a per-warp
-//                          TMA-fed ring of shared-memory stages (register ring for non-default shapes).  Results:
+//                          ring of shared-memory stages fed by 2-D tensor copies (register ring for other shapes).  Results:
 //                          NAV at the opening prices, NAV at the post-impact prices, back-cast returns per horizon
 //                          as order-preserving sort keys
 //   fsb_events2_kernel  ranks per horizon by an in-register bitonic sort, fund choice, stake dilution, buy
@@ -843,12 +843,12 @@ __device__ FSB_FP_INLINE void full_pass(const DevState &s, const int cb, const i
 // ------------------------------------------------------------------------------------------------
 // the holdings pass of the default shape (Mp == 256, K <= 256), fed by the TMA unit: same arithmetic and
 // lane arrangement as full_pass<C>, but the holdings reach the lanes through a per-warp ring of
-// kRingStages stages in shared memory.  A stage = 8 rows x 4 word steps (8 x 512 bytes) fetched by eight
-// bulk asynchronous copies (lanes 0..7 issue one row each) that complete on the stage's mbarrier; the
-// ring runs kRingStages - 1 stages (8 KB per warp) ahead of the arithmetic, which the register ring of
-// full_pass cannot afford, so the loads no longer stall the FMA stream (ncu: stall_long_scoreboard was
-// the top stall of the pass).  Reading a holdings word from shared memory costs the LSU the same four
-// wavefronts as the global load did.
+// kRingStages stages in shared memory.  A stage = 8 rows x 4 word steps (8 x 512 bytes) fetched by ONE 2-D
+// tensor copy (a tensor map views the holdings of all replications as one [R * K4][256] matrix; box 8 x 64)
+// that completes on the stage's mbarrier; the ring runs kRingStages - 1 stages (4 KB per warp) ahead of the
+// arithmetic, which the register ring of full_pass cannot afford, so the loads no longer stall the FMA stream
+// (ncu: stall_long_scoreboard was the top stall of the pass).  Reading a holdings word from shared memory
+// costs the LSU the same four wavefronts as the global load did.
 // open_day: a day without divestments; column 0 gives nav_open AND nav_close (column 1 is not staged).
 // ------------------------------------------------------------------------------------------------
 template <int C>
