@@ -275,6 +275,9 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
             if (L.bytes + 64 > smem_max) { delete e; return fail(FSB_ERR_BAD_PARAMS, "shapes need %d bytes of shared memory per CTA (> %d)", L.bytes, smem_max); }
             e->smem_bytes[k] = L.bytes;
             CU(cudaFuncSetAttribute(kern[k], cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
+#if FSB_SPLIT_CHOICE
+            if (k == 2 && !d.big) CU(cudaFuncSetAttribute((const void *)fsb_choice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
+#endif
             int occ = 0;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern[k], blk, L.bytes));
             if (occ < 1) { delete e; return fail(FSB_ERR_CUDA, "step kernel %d cannot be resident (smem %d)", k, L.bytes); }
@@ -359,7 +362,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     A(hand_i, R * d.hi_stride);
     A(hand_p, R * d.Mp);
     if (d.keep_history) A(hand_s, R * d.Mp);
-    A(queue, 6 * kMaxBatches);
+    A(queue, 8 * kMaxBatches);
 #undef A
     {
         DevPoint *pd = nullptr; double *td = nullptr, *rt = nullptr;
@@ -682,7 +685,7 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
         ++e->last_launches;
     }
     if (t_last >= t_first) {
-        CU(cudaMemsetAsync(d.queue, 0, 6 * kMaxBatches * sizeof(int), e->stream));
+        CU(cudaMemsetAsync(d.queue, 0, 8 * kMaxBatches * sizeof(int), e->stream));
         // one simulated day = three kernels per replication batch (events-1, holdings pass, events-2), every
         // batch on its own stream; the engine's stream forks before the first day and joins after the last
         int nb = nb_override > 0 ? nb_override : e->n_batches;
@@ -717,9 +720,12 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                 if (timed) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st)); e->kev_used += 2; }
                 if (ht && ht->nav_open_out)  // the NAVs of :460 are final after the pass: device -> host while events-2 runs
                     CU(cudaMemcpyAsync(ht->nav_open_out + a.r_begin * d.K, d.nav_open + a.r_begin * d.K, rb * d.K * 8, cudaMemcpyDeviceToHost, st));
+#if FSB_SPLIT_CHOICE
+                if (!d.big) fsb_choice_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
+#endif
                 if (d.big) fsb_big_events2_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
                 else fsb_events2_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
-                e->last_launches += 3;
+                e->last_launches += (FSB_SPLIT_CHOICE && !d.big) ? 4 : 3;
             }
             e->launch_parity ^= 1;
         }

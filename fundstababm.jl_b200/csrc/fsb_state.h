@@ -86,7 +86,7 @@ struct DevState {
     // per-replication pointers of the step context: [kRepPtrs] x (base address, stride in bytes); lane i of a
     // CTA computes pointer i of the replication it starts on (order = the pointer block of Ctx, fsb_step.cuh)
     const ulonglong2 *ptr_table;
-    int *queue;       // [3][2] dynamic work counters per kernel kind (double buffered across launches)
+    int *queue;       // [batches][4][2] dynamic work counters per kernel kind (double buffered across launches)
     const DevPoint *points;
     const double *tables;
 };

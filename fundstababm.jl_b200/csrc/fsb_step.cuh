@@ -36,6 +36,9 @@
 #ifndef FSB_BIG
 #define FSB_BIG 0
 #endif
+#ifndef FSB_SPLIT_CHOICE
+#define FSB_SPLIT_CHOICE (!FSB_BIG)  // the day's fund choices as a kernel of their own (default build only)
+#endif
 #if FSB_BIG
 #define fsb_events1_kernel fsb_big_events1_kernel
 #define fsb_pass_kernel fsb_big_pass_kernel
@@ -1894,14 +1897,14 @@ __device__ FSB_FP_INLINE void phase_store_prices(const DevState &s, const int t)
 // through small per-replication handoff arrays in global memory:
 //   hand_p [Mp]      opening prices of the day              (the post-impact prices go into the day's
 //                                                             column of the price history)
-//   hand_i [..]      HI_T step stamp, HI_OPEN, HI_NCOLS, HI_NCASH, fmod bitmap, hcols[], cash[], r_col[]
+//   hand_i [..]      HI_T step stamp, HI_OPEN, HI_NCOLS, HI_NCASH, fmod bitmap, hcols[], cash[], r_col[], choice[]
 //   hand_s [Mp]      the day's net sale per asset (keep_history only: Q3 volume bookkeeping)
 //   keys   [kc][kq]  horizon returns per column (pass -> events-2)
 // ------------------------------------------------------------------------------------------------
 enum { HI_T = 0, HI_OPEN, HI_NCOLS, HI_NCASH, HI_FMOD = 8 };
-__host__ __device__ inline int hand_ints(int K, int cap) { return ((HI_FMOD + (K + 31) / 32 + 3 * cap) + 3) & ~3; }
+__host__ __device__ inline int hand_ints(int K, int cap) { return ((HI_FMOD + (K + 31) / 32 + 4 * cap) + 3) & ~3; }
 
-enum { KIND_EVENTS1 = 0, KIND_PASS = 1, KIND_EVENTS2 = 2 };
+enum { KIND_EVENTS1 = 0, KIND_PASS = 1, KIND_EVENTS2 = 2, KIND_CHOICE = 3 };
 
 // events-1: one time step of one replication up to the cash list
 __device__ __forceinline__ void step_events1(const DevState &s, Ctx &c, const int t, const int flags)
@@ -2016,16 +2019,46 @@ __device__ __forceinline__ void step_events2(const DevState &s, Ctx &c, const in
     for (int n = tid; n < ((N + 7) & ~7); n += NT) c.pos16_()[n] = static_cast<short>((n < N) ? G.pos[n] : -1);
     for (int k = tid; k < K; k += NT) c.stl_()[k] = G.stakeless[k];
     for (int q = tid; q < nf; q += NT) c.fsel_()[q] = 0;
+#if FSB_SPLIT_CHOICE
+    for (int q = tid; q < ncash; q += NT) c.r_choice_()[q] = hi[HI_FMOD + nf + 3 * cap + q];  // (chosen by fsb_choice_kernel)
+    __syncthreads();
+#else
     __syncthreads();
     phase_choice(s, t, ncols, ncash, selector);
     if (c.isc_()[I_ERR]) {
         if (tid == 0) atomicOr(c.err, c.isc_()[I_ERR]);
         return;
     }
+#endif
     phase_reinvest(s, t, ncash, flags);
     phase_store_prices(s, t);
     FSB_MARK(15);
 }
+
+#if FSB_SPLIT_CHOICE
+// The fund choices of the day's cash holders (ranks per horizon column + sampling, T6) as a kernel of their own
+// in front of events-2, which then starts from the choices in hand_i.  Measured: +1.9 % on the whole step --
+// each of the two kernels keeps less hot code in flight than the fused one (instruction fetch).
+__device__ __forceinline__ void step_choice(const DevState &s, Ctx &c, const int t, const int selector)
+{
+    FSB_TH;
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
+    const int K = c.K, cap = c.cap, nf = (K + 31) / 32;
+    int *hi = G.hand_i;
+    if (hi[HI_T] != t || hi[HI_OPEN]) return;
+    const int ncash = hi[HI_NCASH], ncols = hi[HI_NCOLS];
+    if (ncash == 0) return;  // (uniform: nobody reinvests)
+    if (tid < 16) c.isc_()[tid] = 0;
+    for (int q = tid; q < ncash; q += NT) { c.cash_()[q] = hi[HI_FMOD + nf + cap + q]; c.r_col_()[q] = hi[HI_FMOD + nf + 2 * cap + q]; }
+    __syncthreads();
+    phase_choice(s, t, ncols, ncash, selector);
+    if (c.isc_()[I_ERR]) {  // (raises the replication's error flag: events-2 skips a flagged replication)
+        if (tid == 0) atomicOr(c.err, c.isc_()[I_ERR]);
+        return;
+    }
+    for (int q = tid; q < ncash; q += NT) hi[HI_FMOD + nf + 3 * cap + q] = c.r_choice_()[q];
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // kernels: persistent CTAs pull replications from a work counter (one counter pair per kernel kind)
@@ -2092,7 +2125,7 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
 #endif
     __syncthreads();
 
-    int *const queue = s.queue + 2 * (3 * a.batch + KIND);
+    int *const queue = s.queue + 2 * (4 * a.batch + KIND);
     if (blockIdx.x == 0 && threadIdx.x == 0) queue[launch_parity ^ 1] = 0;  // reset the next launch's counter
     for (;;) {
         if (threadIdx.x == 0) r_sh = atomicAdd(&queue[launch_parity], 1);
@@ -2133,6 +2166,9 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         FSB_MARK(0);
         if (KIND == KIND_EVENTS1) step_events1(s, c, a.t_first, a.flags);
         else if (KIND == KIND_PASS) step_pass(s, c, a.t_first, a.selector);
+#if FSB_SPLIT_CHOICE
+        else if (KIND == KIND_CHOICE) step_choice(s, c, a.t_first, a.selector);
+#endif
         else step_events2(s, c, a.t_first, a.selector, a.flags);
         __syncthreads();
     }
@@ -2156,5 +2192,11 @@ __global__ void __launch_bounds__(kE2Threads, FSB_E2_CTAS) fsb_events2_kernel(co
 {
     phase_kernel_body<KIND_EVENTS2>(s, a, launch_parity, nullptr);
 }
+#if FSB_SPLIT_CHOICE
+__global__ void __launch_bounds__(kE2Threads, FSB_E2_CTAS) fsb_choice_kernel(const DevState s, const StepArgs a, const int launch_parity)
+{
+    phase_kernel_body<KIND_CHOICE>(s, a, launch_parity, nullptr);
+}
+#endif
 
 }  // namespace fsb
