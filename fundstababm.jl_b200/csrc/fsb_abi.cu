@@ -99,7 +99,7 @@ struct fsb_engine {
     int64_t device_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // replication batches: each runs its three kernels per step on its own stream, so that the memory-bound
+    // replication batches: each runs its kernels of a step on its own stream, so that the memory-bound
     // holdings pass of one batch overlaps the latency-bound event kernels of another
     int block_e2 = 0;
     int n_batches = 1;
@@ -686,7 +686,7 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
     }
     if (t_last >= t_first) {
         CU(cudaMemsetAsync(d.queue, 0, 8 * kMaxBatches * sizeof(int), e->stream));
-        // one simulated day = three kernels per replication batch (events-1, holdings pass, events-2), every
+        // one simulated day = four kernels per replication batch (events-1, holdings pass, choice, events-2), every
         // batch on its own stream; the engine's stream forks before the first day and joins after the last
         int nb = nb_override > 0 ? nb_override : e->n_batches;
         if (d.big) nb = 1;
