@@ -102,6 +102,7 @@ struct fsb_engine {
     // replication batches: each runs its kernels of a step on its own stream, so that the memory-bound
     // holdings pass of one batch overlaps the latency-bound event kernels of another
     int block_e2 = 0;
+    int sms = 1;
     int n_batches = 1;
     std::vector<cudaStream_t> bstream;
     std::vector<cudaEvent_t> bjoin;
@@ -232,6 +233,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     CU(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     CU(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    e->sms = sms;
     int nw = e->block / 32;
     // events-2 may run wider CTAs than events-1 (one warp per horizon column in its rank phase)
     e->block_e2 = (cfg->block_threads > 0) ? e->block : kE2Threads;
@@ -361,6 +363,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     A(keys, R * d.kc * ((d.K + 3) & ~3));
     A(hand_i, R * d.hi_stride);
     A(hand_p, R * d.Mp);
+    if (FSB_SPLIT_CHOICE && !d.big) A(hand_m, R * 2 * ((d.N + 63) / 64));
     if (d.keep_history) A(hand_s, R * d.Mp);
     A(queue, 8 * kMaxBatches);
 #undef A
@@ -708,6 +711,9 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                 }
                 const unsigned g1 = static_cast<unsigned>(std::min<long long>(rb, e->grid[0])), g2 = static_cast<unsigned>(std::min<long long>(rb, e->grid[1])),
                                g3 = static_cast<unsigned>(std::min<long long>(rb, e->grid[2]));
+#if FSB_SPLIT_CHOICE
+                if (!d.big) fsb_draws_kernel<<<static_cast<unsigned>(std::min<long long>((rb + 7) / 8, static_cast<long long>(e->sms) * 8)), 256, 0, st>>>(d, a);
+#endif
                 if (d.big) fsb_big_events1_kernel<<<g1, e->block, e->smem_bytes[0], st>>>(d, a, e->launch_parity);
                 else fsb_events1_kernel<<<g1, e->block, e->smem_bytes[0], st>>>(d, a, e->launch_parity);
                 const bool timed = e->kev_used + 2 <= 4096;  // (the dominant kernel is timed launch by launch: bench.py's roofline)
@@ -725,7 +731,7 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
 #endif
                 if (d.big) fsb_big_events2_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
                 else fsb_events2_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
-                e->last_launches += (FSB_SPLIT_CHOICE && !d.big) ? 4 : 3;
+                e->last_launches += (FSB_SPLIT_CHOICE && !d.big) ? 5 : 3;
             }
             e->launch_parity ^= 1;
         }

@@ -81,6 +81,7 @@ struct DevState {
     // handoff between the three kernels of a step (fsb_step.cuh)
     int *hand_i;               // [R][hi_stride]
     double *hand_p;            // [R][Mp] opening prices of the day
+    unsigned *hand_m;          // [R][2 * ceil(N / 64)] reviewer flags of the day (fsb_draws_kernel -> events-1), or null
     double *hand_s;            // [R][Mp] net sale per asset of the day (keep_history only, else null)
     const double *ranktab;     // [K] (i + 1) / (K (K + 1) / 2): rank probabilities of the rank rule (Q14)
     // per-replication pointers of the step context: [kRepPtrs] x (base address, stride in bytes); lane i of a

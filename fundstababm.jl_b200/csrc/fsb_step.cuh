@@ -284,6 +284,7 @@ struct Rep {
     unsigned long long *keys;
     int *hand_i;
     double *hand_p, *hand_s;
+    const unsigned *hand_m;
 };
 __device__ __forceinline__ Rep rep_ptrs(const DevState &s, const long long r, const int kq, const int slot)
 {
@@ -305,6 +306,7 @@ __device__ __forceinline__ Rep rep_ptrs(const DevState &s, const long long r, co
     g.hand_i = s.hand_i + r * s.hi_stride;
     g.hand_p = s.hand_p + r * s.Mp;
     g.hand_s = s.hand_s ? s.hand_s + r * s.Mp : nullptr;
+    g.hand_m = s.hand_m ? s.hand_m + r * (2 * ((s.N + 63) >> 6)) : nullptr;
     return g;
 }
 
@@ -1011,6 +1013,17 @@ __device__ FSB_FP_INLINE void phase_shocks(const DevState &s, const int t)
     double *const po = p_open(c), *const pc = p_cur(c);
     // L2 prefetch of the stakes (gathered by the stake sequence)
     if (tid == 0 && (N & 1) == 0) l2_prefetch_bulk(G.stake, static_cast<unsigned>(N * 8));
+#if FSB_SPLIT_CHOICE
+    {   // the day's market move, prices and reviewer flags were drawn by fsb_draws_kernel
+        (void)Pprev; (void)M;
+        const double2 *hp2 = reinterpret_cast<const double2 *>(G.hand_p);
+        for (int m2 = tid; m2 < hp; m2 += NT) {
+            const double2 v = hp2[m2];
+            reinterpret_cast<double2 *>(po)[m2] = v;
+            reinterpret_cast<double2 *>(pc)[m2] = v;
+        }
+    }
+#else
     // marketmove!: every thread evaluates the same draw (no barrier)
     double mret;
     {
@@ -1057,6 +1070,7 @@ __device__ FSB_FP_INLINE void phase_shocks(const DevState &s, const int t)
         reinterpret_cast<double2 *>(po)[m2] = v;
         reinterpret_cast<double2 *>(pc)[m2] = v;
     }
+#endif
     FSB_MARK(19);
     // investor -> fund map, horizons and the fund flags into shared memory
     if (tid < 16) c.isc_()[tid] = 0;
@@ -1085,6 +1099,11 @@ __device__ FSB_FP_INLINE void phase_shocks(const DevState &s, const int t)
 #pragma unroll 1
         for (int b = lo; b < hi; b += 64) {
             const int n0 = b + 2 * lane;
+#if FSB_SPLIT_CHOICE
+            (void)rp;
+            const unsigned m0 = G.hand_m[2 * (b >> 6)], m1 = G.hand_m[2 * (b >> 6) + 1];  // (flags of investors b + 2 lane, b + 2 lane + 1)
+            const bool f0 = (m0 >> lane) & 1u, f1 = (m1 >> lane) & 1u;
+#else
             double u0 = 2.0, u1 = 2.0;
             if (n0 < hi) {
                 if (c.u_review) {
@@ -1099,6 +1118,7 @@ __device__ FSB_FP_INLINE void phase_shocks(const DevState &s, const int t)
             }
             const bool f0 = u0 < rp, f1 = u1 < rp;
             const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
+#endif
             const unsigned lt = (1u << lane) - 1u;
             int k0 = cnt + __popc(m0 & lt) + __popc(m1 & lt);
             if (f0) { if (k0 < cap) c.wl_()[warp * cap + k0] = n0; ++k0; }
@@ -2037,6 +2057,101 @@ __device__ __forceinline__ void step_events2(const DevState &s, Ctx &c, const in
 }
 
 #if FSB_SPLIT_CHOICE
+// The day's exogenous draws as a flat kernel in front of events-1: marketmove! (:13-17), stockmove! (:29-34) and
+// the reviewer flags of drawreviewers (:147-151), one WARP per replication, no shared memory, no barriers.
+// Results: market[t] (+ the drawdown statistics), the day's opening prices in hand_p (pads zero) and, per block
+// of 64 investors, two 32-bit masks in hand_m (bit l of mask 0 / 1: investor 64 b + 2 l / + 1 reviews).
+// Same draws (Philox sites, tapes) and the same arithmetic statements as the fused phase_shocks.
+__global__ void __launch_bounds__(256) fsb_draws_kernel(const DevState s, const StepArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int t = a.t_first, M = s.M, N = s.N, Mp = s.Mp, hp = Mp >> 1;
+#pragma unroll 1
+    for (long long r = a.r_begin + wid; r < a.r_end; r += nw) {
+        if (s.err[r] & ~FSB_REP_TRACE_OVERFLOW) continue;  // frozen replication
+        const long long g = s.rep_offset + r;
+        const DevPoint &pt = s.points[s.reps_per_point > 0 ? static_cast<int>(g / s.reps_per_point) : 0];
+        Rng rng;
+        rng.k0 = static_cast<uint32_t>(s.seed); rng.k1 = static_cast<uint32_t>(s.seed >> 32); rng.rep = static_cast<uint32_t>(g);
+        const double *z_mkt = s.any_tape ? s.z_mkt[r] : nullptr, *z_stock = s.any_tape ? s.z_stock[r] : nullptr;
+        const double *u_review = s.any_tape ? s.u_review[r] : nullptr;
+        int toff = 0;
+        if (s.step_tape) { z_mkt = s.st_zmkt + r; z_stock = s.st_zstock + r * M; u_review = s.st_urev + r * N; toff = t - 1; }
+        // marketmove!
+        double mret;
+        {
+            double z;
+            if (z_mkt) z = z_mkt[t - 1 - toff];
+            else {
+                const uint4 w = draw_block_s(rng, SITE_MKT, static_cast<uint32_t>(t), 0, 0);
+                z = det_norminv(u52(w.x, w.y));
+            }
+            double *market = s.market + r * s.mkt_len;
+            const double mprev = market[s.keep_history ? t - 2 : ((t - 1) & 1)];
+            const double gr = (1.0 + pt.drift) + pt.marketvol * z;
+            const double mnew = mprev * gr;
+            mret = ddiv(mnew - mprev, mprev);
+            if (lane == 0) {
+                market[s.keep_history ? t - 1 : (t & 1)] = mnew;
+                double peak = s.mkt_peak[r];
+                if (mnew > peak) { peak = mnew; s.mkt_peak[r] = peak; }
+                const double dd = ddiv(peak - mnew, peak);
+                if (dd > s.mkt_dd[r]) s.mkt_dd[r] = dd;
+            }
+        }
+        // stockmove!, two assets per lane and trip (one Philox block = two uniforms)
+        const double *Pprev = s.P + r * s.p_stride + static_cast<long long>(pcol(s, t - 1)) * Mp;
+        const double *beta = s.beta + r * Mp, *vol = s.vol + r * Mp;
+        double2 *hp2 = reinterpret_cast<double2 *>(s.hand_p + r * Mp);
+#pragma unroll 1
+        for (int m2 = lane; m2 < hp; m2 += 32) {
+            double2 v = make_double2(0.0, 0.0);
+            const int m = 2 * m2;
+            if (m < M) {
+                const double2 prev = reinterpret_cast<const double2 *>(Pprev)[m2];
+                const double2 be = reinterpret_cast<const double2 *>(beta)[m2];
+                const double2 vo = reinterpret_cast<const double2 *>(vol)[m2];
+                double z0, z1 = 0.0;
+                if (z_stock) {
+                    const double *zs = z_stock + static_cast<long long>(M) * (t - 1 - toff);
+                    z0 = zs[m];
+                    if (m + 1 < M) z1 = zs[m + 1];
+                } else {
+                    const uint4 w = draw_block_s(rng, SITE_STOCK, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(m2));
+                    z0 = det_norminv(u52(w.x, w.y));
+                    z1 = det_norminv(u52(w.z, w.w));
+                }
+                v.x = (1.0 + mret * be.x) * prev.x + (vo.x * z0) * prev.x;
+                if (m + 1 < M) v.y = (1.0 + mret * be.y) * prev.y + (vo.y * z1) * prev.y;
+            }
+            hp2[m2] = v;
+        }
+        // drawreviewers: flags of 64 investors per trip
+        unsigned *hm = s.hand_m + r * (2 * ((N + 63) >> 6));
+        const double rp = pt.reviewprob;
+#pragma unroll 1
+        for (int b = 0; b < N; b += 64) {
+            const int n0 = b + 2 * lane;
+            double u0 = 2.0, u1 = 2.0;
+            if (n0 < N) {
+                if (u_review) {
+                    const double *ur = u_review + static_cast<long long>(N) * (t - 1 - toff);
+                    u0 = ur[n0];
+                    if (n0 + 1 < N) u1 = ur[n0 + 1];
+                } else {
+                    const uint4 w = draw_block_s(rng, SITE_REVIEW, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(n0 >> 1));
+                    u0 = u52(w.x, w.y);
+                    if (n0 + 1 < N) u1 = u52(w.z, w.w);
+                }
+            }
+            const unsigned m0 = __ballot_sync(0xffffffffu, u0 < rp), m1 = __ballot_sync(0xffffffffu, u1 < rp);
+            if (lane == 0) { hm[2 * (b >> 6)] = m0; hm[2 * (b >> 6) + 1] = m1; }
+        }
+    }
+}
+
 // The fund choices of the day's cash holders (ranks per horizon column + sampling, T6) as a kernel of their own
 // in front of events-2, which then starts from the choices in hand_i.  Measured: +1.9 % on the whole step --
 // each of the two kernels keeps less hot code in flight than the fused one (instruction fetch).
