@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            (N=1; N>1 under torch.distributed.run)
     python bench.py --impl reference ...                     (CPU oracle port on the host cores)
 
-A "step" is one simulated day for the whole batch of replications (four kernel launches per GPU and
+A "step" is one simulated day for the whole batch of replications (five kernel launches per GPU and
 replication batch: events-1, holdings pass, events-2).  Workload at N GPUs: the default Params shape (K=M=250, N=1000, W=100;
 BASELINE.json configs[2] at N=1) with --reps-per-gpu replications resident in HBM on every GPU
 (weak scaling: replications are independent, there is no data-path collective), Philox shocks.
@@ -336,7 +336,7 @@ def main():
                "h2d_bytes_per_step": int(8 * Re * (1 + M + N)), "d2h_bytes_per_step": int(8 * Re * K),
                "replications_per_gpu": Re, "ms_per_step": 1e3 * e2e_s / nsteps,
                "what": "fsb_run_step_hosttape: per step H2D of the step's shocks from pinned host buffers, "
-                       "four kernel launches per replication batch (4 batches, transfers overlap kernels), D2H of all NAVs; wall clock"}
+                       "five kernel launches per replication batch (4 batches, transfers overlap kernels), D2H of all NAVs; wall clock"}
         eng2.close()
 
     cpu = None
@@ -359,7 +359,7 @@ def main():
                          "share_of_step_time": pass_ms / dev_ms,
                          "whole_step": {"algorithmic_bytes_per_fund_step": b_alg(K, M, N),
                                         "achieved": value / world * b_alg(K, M, N) / 1e9, "frac": value / world * b_alg(K, M, N) / 1e9 / peak,
-                                        "what": "per GPU: all kernels of a step (events-1, pass, choice, events-2) against SURVEY 8d's bytes"}},
+                                        "what": "per GPU: all kernels of a step (draws, events-1, pass, choice, events-2) against SURVEY 8d's bytes"}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "checks": {"error_replications": status_bad, "replication_steps_counted": int(stats[0][8])},
         }

@@ -689,7 +689,7 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
     }
     if (t_last >= t_first) {
         CU(cudaMemsetAsync(d.queue, 0, 8 * kMaxBatches * sizeof(int), e->stream));
-        // one simulated day = four kernels per replication batch (events-1, holdings pass, choice, events-2), every
+        // one simulated day = five kernels per replication batch (draws, events-1, holdings pass, choice, events-2), every
         // batch on its own stream; the engine's stream forks before the first day and joins after the last
         int nb = nb_override > 0 ? nb_override : e->n_batches;
         if (d.big) nb = 1;

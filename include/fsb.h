@@ -92,7 +92,7 @@ typedef struct fsb_config {
     int32_t log_capacity;   /* liquidation-log rows per replication; 0 = auto (K + 1024)        */
     int32_t trace_capacity; /* trace records per traced replication; 0 = auto                   */
     int32_t steps_per_launch; /* kept for ABI compatibility and ignored: a simulated day is always
-                                 launches events-1, holdings pass, choice, events-2: DESIGN.md 4   */
+                                 launches draws, events-1, pass, choice, events-2: DESIGN.md 4    */
     int32_t block_threads;  /* 0 = auto                                                         */
     int32_t blocks_per_sm;  /* CTAs per SM of the holdings-pass kernel; 0 = auto                */
 } fsb_config;
@@ -200,8 +200,8 @@ int32_t fsb_stats_all(fsb_engine **engines, int32_t n, uint64_t *out);
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------- */
 /* device time of the last fsb_run (CUDA events): total on the engine's stream, and the time summed over
  * the launches of the dominant kernel (the holdings pass, fsb_pass_kernel; events on the stream of every
- * launch); number of kernel launches of the last fsb_run (four per simulated day and replication batch; three for
- * shapes beyond shared memory, where the fund choice stays inside events-2) */
+ * launch); number of kernel launches of the last fsb_run (five per simulated day and replication batch; three for
+ * shapes beyond shared memory, where the draws and the fund choice stay inside the event kernels) */
 int32_t fsb_last_run_timing(fsb_engine *e, double *total_ms, double *step_kernel_ms, int64_t *launches);
 /* how many launches of the dominant kernel step_kernel_ms sums over */
 int64_t fsb_last_pass_launches(const fsb_engine *e);

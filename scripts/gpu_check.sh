@@ -28,7 +28,7 @@ fi
 if has full; then
     # one launch of each of the kernels of a step (the pass kernel is the dominant one)
     $PROF > $OUT/prof_plain_$TAG.log 2>&1 &&
-    for k in events1 pass choice events2; do
+    for k in draws events1 pass choice events2; do
         ncu --set full --clock-control none --import-source on -k regex:fsb_${k}_kernel -s 1 -c 1 -f -o $OUT/prof_${TAG}_$k \
             $PROF > $OUT/ncu_full_${TAG}_$k.log 2>&1
         echo "full $k rc=$?"

@@ -48,7 +48,7 @@ lines = [f"# {tag}: ncu --set full --clock-control none, one launch of each kern
          f"Command: `FSB_BATCHES=1 python scripts/prof_step.py --reps {reps} --steps 3 --t0 300` (default Params shape, "
          "probabilistic selector).  Numbers under a profiler are not bench values.", ""]
 traffic = {}
-for kname in ("events1", "pass", "choice", "events2"):
+for kname in ("draws", "events1", "pass", "choice", "events2"):
     rep = os.path.join(out, f"prof_{tag}_{kname}.ncu-rep")
     if not os.path.exists(rep):
         continue
