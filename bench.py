@@ -336,7 +336,7 @@ def main():
                "h2d_bytes_per_step": int(8 * Re * (1 + M + N)), "d2h_bytes_per_step": int(8 * Re * K),
                "replications_per_gpu": Re, "ms_per_step": 1e3 * e2e_s / nsteps,
                "what": "fsb_run_step_hosttape: per step H2D of the step's shocks from pinned host buffers, "
-                       "five kernel launches per replication batch (4 batches, transfers overlap kernels), D2H of all NAVs; wall clock"}
+                       "five kernel launches per replication batch (8 batches, transfers overlap kernels), D2H of all NAVs; wall clock"}
         eng2.close()
 
     cpu = None
