@@ -27,6 +27,13 @@ __global__ void fsb_big_pass_kernel(const DevState s, const StepArgs a, const in
 __global__ void fsb_big_events2_kernel(const DevState s, const StepArgs a, const int launch_parity);
 }  // namespace fsb
 
+namespace fsb {  // fsb_facts.cu
+int facts_rows();
+int facts_max_lag();
+int facts_max_sel();
+cudaError_t facts_launch(const DevState &d, cudaStream_t st, long long rep_first, int n_reps, int maxlag, double pct, double *out);
+}  // namespace fsb
+
 using namespace fsb;
 
 constexpr int kMaxBatches = 8;  // replication batches (streams) an engine can run concurrently
@@ -118,7 +125,7 @@ struct fsb_engine {
     ncclComm_t comm = nullptr;
     int n_ranks = 1;
     // last-run timing
-    double last_total_ms = 0.0, last_pass_ms = 0.0;
+    double last_total_ms = 0.0, last_pass_ms = 0.0, last_facts_ms = 0.0;
     int64_t last_launches = 0, last_pass_launches = 0;
     std::vector<cudaEvent_t> kev;  // event pairs around the pass-kernel launches of the last run
     size_t kev_used = 0;
@@ -943,6 +950,68 @@ extern "C" int32_t fsb_download_log(fsb_engine *e, int64_t rep, int64_t *n_rows,
     TRY(geti(d.log_ninv, ninvestors)); TRY(geti(d.log_nstocks, nstocks));
     if (initialsize) CU(cudaMemcpy(initialsize, d.log_size + lb, rows * 8, cudaMemcpyDeviceToHost));
     if (liquidity) CU(cudaMemcpy(liquidity, d.log_liquidity + lb, rows * 8, cudaMemcpyDeviceToHost));
+    return FSB_OK;
+}
+
+extern "C" int32_t fsb_stylised_facts(fsb_engine *e, int64_t rep_first, int64_t n_reps, int32_t maxlag, double returnspctile,
+                                      double *stock_pacf, double *market_pacf, double *stock_volacluster,
+                                      double *market_volacluster, double *kurtoses, double *lossgain, double *corrs)
+{
+    if (!e) return fail(FSB_ERR_BAD_PARAMS, "null engine");
+    if (n_reps < 1) return fail(FSB_ERR_RANGE, "n_reps %lld", (long long)n_reps);
+    TRY(check_rep(e, rep_first));
+    TRY(check_rep(e, rep_first + n_reps - 1));
+    const DevState &d = e->d;
+    if (!d.keep_history) return fail(FSB_ERR_NO_HISTORY, "fsb_stylised_facts needs an engine created with keep_history=1");
+    if (!e->state_set) return fail(FSB_ERR_BAD_STATE, "no state");
+    const int M = d.M, n = d.T - d.W - 1, n2 = n - d.W;
+    if (maxlag < 1 || maxlag > facts_max_lag()) return fail(FSB_ERR_BAD_PARAMS, "maxlag %d not in 1..%d", maxlag, facts_max_lag());
+    if (n <= 2 * maxlag + 1) return fail(FSB_ERR_BAD_PARAMS, "%d returns after the burn-in are too few for %d lags", n, maxlag);
+    if (!(returnspctile >= 0.0 && returnspctile <= 100.0)) return fail(FSB_ERR_BAD_PARAMS, "returnspctile %g not in [0,100]", returnspctile);
+    if (n2 >= 1 && static_cast<int>(static_cast<double>(n2 - 1) * (returnspctile / 100.0)) + 2 > facts_max_sel())
+        return fail(FSB_ERR_BAD_PARAMS, "percentile %g of %d returns needs more than the %d order statistics a thread keeps",
+                    returnspctile, n2, facts_max_sel());
+    const int rows = facts_rows(), nser = M + 1, L = facts_max_lag();
+    const size_t per_rep = static_cast<size_t>(rows) * nser;
+    const int64_t chunk = std::min<int64_t>(n_reps, 4096);
+    double *dev = nullptr;
+    CU(cudaMalloc(&dev, per_rep * chunk * 8));
+    std::vector<double> buf(per_rep * chunk);
+    int32_t rc = FSB_OK;
+    e->last_facts_ms = 0.0;
+    for (int64_t c0 = 0; c0 < n_reps && rc == FSB_OK; c0 += chunk) {
+        const int64_t nc = std::min(chunk, n_reps - c0);
+        cudaError_t ce = cudaEventRecord(e->ev0, e->stream);
+        if (ce == cudaSuccess) ce = facts_launch(d, e->stream, rep_first + c0, static_cast<int>(nc), maxlag, returnspctile, dev);
+        if (ce == cudaSuccess) ce = cudaEventRecord(e->ev1, e->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(buf.data(), dev, per_rep * nc * 8, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        float ms = 0.f;
+        if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+        if (ce != cudaSuccess) { rc = fail(FSB_ERR_CUDA, "stylised facts: %s", cudaGetErrorString(ce)); break; }
+        e->last_facts_ms += ms;
+        for (int64_t i = 0; i < nc; ++i) {
+            const double *b = buf.data() + per_rep * i;
+            const int64_t r = c0 + i;
+            for (int l = 0; l < maxlag; ++l) {
+                if (stock_pacf) std::memcpy(stock_pacf + (r * maxlag + l) * M, b + static_cast<size_t>(l) * nser, M * 8);
+                if (stock_volacluster) std::memcpy(stock_volacluster + (r * maxlag + l) * M, b + static_cast<size_t>(L + l) * nser, M * 8);
+                if (market_pacf) market_pacf[r * maxlag + l] = b[static_cast<size_t>(l) * nser + M];
+                if (market_volacluster) market_volacluster[r * maxlag + l] = b[static_cast<size_t>(L + l) * nser + M];
+            }
+            if (kurtoses) std::memcpy(kurtoses + r * M, b + static_cast<size_t>(2 * L) * nser, M * 8);
+            if (lossgain) std::memcpy(lossgain + r * M, b + static_cast<size_t>(2 * L + 1) * nser, M * 8);
+            if (corrs) std::memcpy(corrs + r * M, b + static_cast<size_t>(2 * L + 2) * nser, M * 8);
+        }
+    }
+    cudaFree(dev);
+    return rc;
+}
+
+extern "C" int32_t fsb_last_facts_timing(fsb_engine *e, double *kernel_ms)
+{
+    if (!e || !kernel_ms) return fail(FSB_ERR_BAD_PARAMS, "null argument");
+    *kernel_ms = e->last_facts_ms;
     return FSB_OK;
 }
 

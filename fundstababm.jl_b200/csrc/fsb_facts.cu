@@ -1,0 +1,274 @@
+// fsb_facts.cu -- Func.calc_stylisedfacts (src/functions.jl:604-648) on the device, from the price,
+// volume and market histories a keep_history engine holds in HBM: per stock the partial
+// autocorrelations of the demeaned returns and of their squares (lags 1..10, calc_pacf :588-602), the
+// excess kurtosis (calc_kurtoses :538-545), the loss/gain ratio (lossgainratio :572-586) and the
+// volume-|return| correlation (volavolumecorr :560-570); for the market index the two PACFs.
+// Only M-vectors leave the device instead of the M x T histories (2 x 2.7 MB per replication).
+//
+// One thread per series (stock m, or the market index as series M), 128 series per CTA: thread m
+// walks its series through time, so a warp reads 32 consecutive stocks of one price column -- the
+// histories are [t][asset], asset fastest, and every load is coalesced.  Three passes over the
+// history: (1) means of returns and volume, (2) lagged products, moments and the order statistics
+// the percentile needs, (3) up/down counts and the centred correlation sums.
+//
+// PACF by regression as StatsBase v0.30.0 does it (per lag l: OLS of x[i] on [1, x[i-1..i-l]],
+// i = l+1..n, through the Cholesky factor of X'X) -- but the (l+1)^2 sums of every lag are derived
+// from 11 full-range lagged sums F_d = sum_s x[s] x[s-d] minus the few head / tail products each
+// window leaves out, instead of 10 passes with up to 66 running sums.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "fsb_state.h"
+
+namespace fsb {
+
+constexpr int kFactLags = 10;   // lags carried in registers (the reference's maxlag default, :605)
+constexpr int kFactSel = 128;   // order statistics a thread can keep for the percentile
+constexpr int kFactThreads = 128;  // series per CTA; a replication's M + 1 series spread over gridDim.y CTAs
+constexpr int kFactRows = 2 * kFactLags + 3;  // rows of the output block: pacf[10], volacluster[10], kurtosis, lossgain, corr
+
+struct FactSeries {  // where a thread's series lives
+    const double *p;       // first value (column 1)
+    long long stride;      // doubles between consecutive days
+    const double *vol;     // volume, same stride (null for the market index)
+};
+
+// Window corrections of the lagged sums, built once per series: the regression of lag l runs over rows
+// i = l..n-1 (0-based), so sum_i z[i-a] z[i-b] = F[d] (d = b-a, all s = d..n-1) minus the head products
+// s = d..l-a-1 and the tail products s = n-a..n-1.  hd[d][m] = the first m head products of lag d,
+// td[d][a] = the last a tail products of lag d, hs[m] / ts[a] the same for the plain sums.
+struct FactEdges {
+    double hd[kFactLags + 1][kFactLags + 1], td[kFactLags + 1][kFactLags + 1], hs[kFactLags + 1], ts[kFactLags + 1];
+};
+__device__ __noinline__ void fact_edges(FactEdges &e, const double *head, const double *tail /* tail[k] = z[n-1-k] */)
+{
+    e.hs[0] = e.ts[0] = 0.0;
+    for (int m = 0; m < kFactLags; ++m) { e.hs[m + 1] = e.hs[m] + head[m]; e.ts[m + 1] = e.ts[m] + tail[m]; }
+    for (int d = 0; d <= kFactLags; ++d) {
+        e.hd[d][0] = e.td[d][0] = 0.0;
+        for (int m = 0; m + d < kFactLags; ++m) {
+            e.hd[d][m + 1] = e.hd[d][m] + head[d + m] * head[m];
+            e.td[d][m + 1] = e.td[d][m] + tail[m] * tail[m + d];
+        }
+    }
+}
+
+// last coefficient of the regression of z[i] on [1, z[i-1], ..., z[i-l]], rows i = l..n-1, from the full-range
+// sums F[d] = sum_{s=d..n-1} z[s] z[s-d], S = sum z and the window corrections
+__device__ __noinline__ double fact_pacf_lag(const double *F, double S, const FactEdges &e, int n, int l)
+{
+    double G[kFactLags + 1][kFactLags + 1], rhs[kFactLags + 1];
+    for (int a = 0; a <= l; ++a) {
+        const double sa = S - e.hs[l - a] - e.ts[a];  // sum_{i=l..n-1} z[i-a]
+        for (int b = a; b <= l; ++b) {
+            const int d = b - a;
+            const double c = F[d] - e.hd[d][l - b] - e.td[d][a];
+            if (a == 0) { if (b > 0) rhs[b] = c; }
+            else G[b][a] = c;  // lower triangle, b >= a >= 1
+        }
+        if (a == 0) rhs[0] = sa; else G[a][0] = sa;
+    }
+    G[0][0] = static_cast<double>(n - l);
+    const int dm = l + 1;
+    for (int j = 0; j < dm; ++j) {  // Cholesky, lower triangle in place
+        double s = G[j][j];
+        for (int k = 0; k < j; ++k) s -= G[j][k] * G[j][k];
+        const double ljj = sqrt(s);
+        G[j][j] = ljj;
+        for (int i = j + 1; i < dm; ++i) {
+            double t = G[i][j];
+            for (int k = 0; k < j; ++k) t -= G[i][k] * G[j][k];
+            G[i][j] = t / ljj;
+        }
+    }
+    for (int i = 0; i < dm; ++i) {
+        double t = rhs[i];
+        for (int k = 0; k < i; ++k) t -= G[i][k] * rhs[k];
+        rhs[i] = t / G[i][i];
+    }
+    // back substitution: only the last unknown is needed
+    return rhs[dm - 1] / G[dm - 1][dm - 1];
+}
+
+// Walks a series through time: fn(j, return j, volume j) for j = 0..n-1.  A thread's loads are one per day and
+// each would wait a full HBM round trip if issued where it is used; the loads of kFactAhead days are issued
+// together, ahead of the arithmetic on them.
+constexpr int kFactAhead = 8;
+template <bool kVol, class Fn>
+__device__ __forceinline__ void fact_walk(const double *__restrict__ p0, const double *__restrict__ v0, long long stride, int n, Fn &&fn)
+{
+    double pa = p0[0];
+    for (int j0 = 0; j0 < n; j0 += kFactAhead) {
+        double pb[kFactAhead], vv[kFactAhead];
+#pragma unroll
+        for (int u = 0; u < kFactAhead; ++u) {
+            const bool on = j0 + u < n;
+            pb[u] = on ? p0[static_cast<long long>(j0 + u + 1) * stride] : 1.0;
+            vv[u] = (kVol && on) ? v0[static_cast<long long>(j0 + u) * stride] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kFactAhead; ++u) {
+            if (j0 + u < n) {
+                fn(j0 + u, (pb[u] - pa) / pa, vv[u]);
+                pa = pb[u];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFactThreads, 3)
+fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, const double pct, double *__restrict__ out)
+{
+    const long long r = rep_first + blockIdx.x;
+    const int M = s.M, T = s.T, W = s.W, Mp = s.Mp;
+    const int n = T - W - 1;      // returns per series (assetreturns :500-515)
+    const int n2 = n - W;         // returns the loss/gain ratio looks at (:575,578)
+    const int nser = M + 1;
+    double *o = out + static_cast<long long>(blockIdx.x) * kFactRows * nser;
+    // percentile(v, pct) = quantile(v, pct/100): f0 = (n2-1) p, i = trunc(f0), h = f0 - i (Statistics._quantile)
+    int qi = 0, qcap = 0;
+    double qh = 0.0;
+    if (n2 >= 1) {
+        const double f0 = static_cast<double>(n2 - 1) * (pct / 100.0), t0 = trunc(f0);
+        qh = f0 - t0;
+        qi = static_cast<int>(t0);
+        qcap = min(qi + 2, n2);
+    }
+    for (int ser = blockIdx.y * kFactThreads + threadIdx.x; ser < nser; ser += gridDim.y * kFactThreads) {
+        FactSeries fs;
+        if (ser < M) {
+            fs.p = s.P + r * s.p_stride + ser;
+            fs.stride = Mp;
+            fs.vol = s.volume + r * static_cast<long long>(T) * Mp + ser;
+        } else {
+            fs.p = s.market + r * s.mkt_len;
+            fs.stride = 1;
+            fs.vol = nullptr;
+        }
+        const double *p0 = fs.p + static_cast<long long>(W) * fs.stride;            // column W+1
+        const double *v0 = fs.vol ? fs.vol + static_cast<long long>(W + 1) * fs.stride : nullptr;  // column W+2
+        // pass 1: means
+        double sr = 0.0, sv = 0.0;
+        if (v0) fact_walk<true>(p0, v0, fs.stride, n, [&](int, double ret, double v) { sr += ret; sv += v; });
+        else fact_walk<false>(p0, v0, fs.stride, n, [&](int, double ret, double) { sr += ret; });
+        const double mean = sr / static_cast<double>(n), mv = sv / static_cast<double>(n);
+        // pass 2: lagged products of x and of y = x^2, sums, order statistics of |x|
+        double F[kFactLags + 1], Fy[kFactLags + 1], xw[kFactLags];
+        double head[kFactLags], sel[kFactSel];
+#pragma unroll
+        for (int d = 0; d <= kFactLags; ++d) F[d] = Fy[d] = 0.0;
+#pragma unroll
+        for (int d = 0; d < kFactLags; ++d) xw[d] = 0.0;
+        for (int d = 0; d < kFactLags; ++d) head[d] = 0.0;
+        double sx = 0.0, sabs = 0.0;
+        int nsel = 0;
+        const bool stock = fs.vol != nullptr;
+        fact_walk<false>(p0, v0, fs.stride, n, [&](int j, double ret, double) {
+            const double x = ret - mean;
+            const double y = x * x;
+            sx += x;
+            sabs += fabs(x);
+            F[0] += y;
+            Fy[0] += y * y;
+#pragma unroll
+            for (int d = 1; d <= kFactLags; ++d) {
+                const double xl = xw[d - 1];
+                F[d] += x * xl;
+                Fy[d] += y * (xl * xl);
+            }
+#pragma unroll
+            for (int d = kFactLags - 1; d > 0; --d) xw[d] = xw[d - 1];
+            xw[0] = x;
+            if (j < kFactLags) head[j] = x;
+            if (stock && j >= W && qcap > 0) {  // keep the qcap smallest |x| in a max-heap: the percentile needs its top two
+                const double a = fabs(x);
+                if (nsel < qcap) {  // sift up
+                    int k = nsel++;
+                    while (k > 0) {
+                        const int up = (k - 1) >> 1;
+                        const double pv = sel[up];
+                        if (!(pv < a)) break;
+                        sel[k] = pv;
+                        k = up;
+                    }
+                    sel[k] = a;
+                } else if (a < sel[0]) {  // replaces the largest: sift down
+                    int k = 0;
+                    for (;;) {
+                        int c = 2 * k + 1;
+                        if (c >= nsel) break;
+                        double cv = sel[c];
+                        if (c + 1 < nsel) {
+                            const double c2 = sel[c + 1];
+                            if (c2 > cv) { cv = c2; ++c; }
+                        }
+                        if (!(cv > a)) break;
+                        sel[k] = cv;
+                        k = c;
+                    }
+                    sel[k] = a;
+                }
+            }
+        });
+        // the sums leave their registers for the per-lag solves (local memory from here on)
+        double Fl[kFactLags + 1], Fyl[kFactLags + 1], tail[kFactLags];
+#pragma unroll
+        for (int d = 0; d <= kFactLags; ++d) { Fl[d] = F[d]; Fyl[d] = Fy[d]; }
+#pragma unroll
+        for (int d = 0; d < kFactLags; ++d) tail[d] = xw[d];
+        FactEdges ed;
+        fact_edges(ed, head, tail);
+        for (int l = 1; l <= maxlag; ++l) o[static_cast<long long>(l - 1) * nser + ser] = fact_pacf_lag(Fl, sx, ed, n, l);
+        for (int d = 0; d < kFactLags; ++d) { head[d] *= head[d]; tail[d] *= tail[d]; }
+        fact_edges(ed, head, tail);
+        for (int l = 1; l <= maxlag; ++l) o[static_cast<long long>(kFactLags + l - 1) * nser + ser] = fact_pacf_lag(Fyl, F[0], ed, n, l);
+        if (!fs.vol) continue;
+        // kurtosis (StatsBase: population moments about the sample mean, minus 3).  The series is demeaned already;
+        // its residual mean (~1e-19) moves the moments by less than their last bit and is dropped.
+        {
+            const double nn = static_cast<double>(n), c2 = F[0] / nn, c4 = Fy[0] / nn;
+            o[static_cast<long long>(2 * kFactLags) * nser + ser] = c4 / (c2 * c2) - 3.0;
+        }
+        // pass 3: loss/gain counts and the centred sums of cor(volume, |x|)
+        double q = 0.0;
+        if (n2 >= 1) {  // sorted a[qi], a[qi+1] = the two largest of the qi+2 smallest (the heap's root and its larger child)
+            double hi = sel[0], lo = sel[0];
+            if (qcap == qi + 2) {
+                lo = sel[1];
+                if (qcap > 2 && sel[2] > lo) lo = sel[2];
+            }
+            q = (qh == 0.0) ? lo : lo + qh * (hi - lo);
+        }
+        const double ma = sabs / static_cast<double>(n);
+        int up = 0, down = 0;
+        double xx = 0.0, yy = 0.0, xy = 0.0;
+        fact_walk<true>(p0, v0, fs.stride, n, [&](int j, double ret, double v) {
+            const double x = ret - mean;
+            if (j >= W) { up += x > q; down += x < -q; }
+            const double xi = v - mv, yi = fabs(x) - ma;
+            xx += xi * xi;
+            yy += yi * yi;
+            xy += xi * yi;
+        });
+        o[static_cast<long long>(2 * kFactLags + 1) * nser + ser] =
+            n2 >= 1 ? static_cast<double>(down) / static_cast<double>(up) : __longlong_as_double(0x7ff8000000000000LL);
+        const double mx = xx > yy ? xx : yy, mn = xx > yy ? yy : xx;
+        double c = xy / mx / sqrt(mn / mx);
+        if (c > 1.0) c = 1.0; else if (c < -1.0) c = -1.0;
+        o[static_cast<long long>(2 * kFactLags + 2) * nser + ser] = c;
+    }
+}
+
+// launched by fsb_stylised_facts (fsb_abi.cu); out: device [n_reps][kFactRows][M + 1]
+int facts_rows() { return kFactRows; }
+int facts_max_lag() { return kFactLags; }
+int facts_max_sel() { return kFactSel; }
+cudaError_t facts_launch(const DevState &d, cudaStream_t st, long long rep_first, int n_reps, int maxlag, double pct, double *out)
+{
+    const dim3 grid(static_cast<unsigned>(n_reps), static_cast<unsigned>(std::min((d.M + 1 + kFactThreads - 1) / kFactThreads, 64)));
+    fsb_facts_kernel<<<grid, kFactThreads, 0, st>>>(d, rep_first, maxlag, pct, out);
+    return cudaGetLastError();
+}
+
+}  // namespace fsb

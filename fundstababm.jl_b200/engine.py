@@ -203,6 +203,26 @@ class Engine:
         L.check(L.lib().fsb_download_trace(self._h, rep, None, None, None, recs.ctypes.data, C.byref(n)))
         return dict(nav_open=nav, p_sell=ps, p_resp=pr, events=recs[: n.value])
 
+    def stylised_facts(self, rep_first=0, n_reps=None, maxlag=10, returnspctile=5):
+        """Func.calc_stylisedfacts (functions.jl:604-648) on the device; arrays keyed by the reference's names,
+        leading axis = replication."""
+        n = self.n_reps - rep_first if n_reps is None else n_reps
+        M = self.M
+        o = dict(stockpacf=np.zeros((n, maxlag, M)), marketpacf=np.zeros((n, maxlag)),
+                 stockvolacluster=np.zeros((n, maxlag, M)), marketvolacluster=np.zeros((n, maxlag)),
+                 stockkurtoses=np.zeros((n, M)), lossgainratios=np.zeros((n, M)), corrs=np.zeros((n, M)))
+        L.check(L.lib().fsb_stylised_facts(self._h, rep_first, n, maxlag, float(returnspctile), *[o[k].ctypes.data for k in (
+            "stockpacf", "marketpacf", "stockvolacluster", "marketvolacluster", "stockkurtoses", "lossgainratios",
+            "corrs")]))
+        for k in ("stockpacf", "stockvolacluster"):
+            o[k] = o[k].transpose(0, 2, 1)  # [rep][stock][lag]: the reference's bigm x nlags matrix per replication
+        return o
+
+    def last_facts_ms(self):
+        ms = C.c_double()
+        L.check(L.lib().fsb_last_facts_timing(self._h, C.byref(ms)))
+        return ms.value
+
     # statistics --------------------------------------------------------------------------------
     def comm_init_rank(self, n_ranks, rank, unique_id: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)

@@ -1,9 +1,10 @@
 """runmodel -- mirror of the reference's driver (src/runmodel.jl:6-68) for the hot path.
 
 Allocates the zeroed structs (:13-28), calls ``Func.initialise`` (:30) and ``Func.modelrun``
-(:36) -- both on the GPU -- and returns what the reference only prints.  Post-processing that
-is out of scope (logistic regression :44, stylised facts :47, plots :50-67) is not performed
-here; the returned arrays are exactly what those functions consume.
+(:36) -- both on the GPU -- and returns what the reference only prints, including the stylised
+facts of :47 (computed on the device from the histories the run leaves in HBM).  Post-processing
+that is out of scope (logistic regression :44, plots :50-67) is not performed here; the returned
+arrays are exactly what those functions consume.
 """
 from __future__ import annotations
 
@@ -22,6 +23,7 @@ class RunResult:
     investors: Types.RetailInvestor
     funds: Types.EquityFund
     boundsfailures: list
+    stylefacts: dict
 
 
 def runmodel(params=None, *, fundselector="probabilistic", doplot=False, boundstest=False, seed=0, device=0,
@@ -38,9 +40,11 @@ def runmodel(params=None, *, fundselector="probabilistic", doplot=False, boundst
     failures = []
     if boundstest:
         failures += Func.boundstest(market, stocks, investors, funds)
-    log = Func.modelrun(market, stocks, investors, funds, params, fundselector, seed=seed, device=device)
+    stylefacts = {}
+    log = Func.modelrun(market, stocks, investors, funds, params, fundselector, seed=seed, device=device,
+                        stylefacts=stylefacts)
     if verbose:
         print(log)
     if boundstest:
         failures += Func.boundstest(market, stocks, investors, funds)
-    return RunResult(log, market, stocks, investors, funds, failures)
+    return RunResult(log, market, stocks, investors, funds, failures, stylefacts)

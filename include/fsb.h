@@ -186,6 +186,21 @@ int32_t fsb_download_trace(fsb_engine *e, int64_t rep, double *nav_open, double 
                            fsb_trace_rec *recs, int64_t *n_recs);
 int32_t fsb_rep_status(fsb_engine *e, int32_t *flags /*n_reps*/);
 
+/* ---- stylised facts on the device ----------------------------------------------- */
+/* Func.calc_stylisedfacts (src/functions.jl:604-648; called at src/runmodel.jl:47) for replications
+ * [rep_first, rep_first + n_reps), computed from the price / volume / market histories in HBM
+ * (keep_history=1), so that only M-vectors cross the host link instead of the M x T histories.
+ * Array outputs of the reference function, per replication, column-major as Julia stores them
+ * (any may be NULL): stock_pacf, stock_volacluster [n_reps][maxlag][M] (calc_pacf :588-602 of the
+ * demeaned returns :517-535 / of their squares); market_pacf, market_volacluster [n_reps][maxlag];
+ * kurtoses (:538-545), lossgain (:572-586, percentile `returnspctile` of |x|), corrs (:560-570)
+ * [n_reps][M].  maxlag in 1..10 (reference default 10), returnspctile in [0,100] (default 5).
+ * The z-tests and the KS test of :629-641 are host statistics on these vectors / on downloaded
+ * returns and stay with the caller. */
+int32_t fsb_stylised_facts(fsb_engine *e, int64_t rep_first, int64_t n_reps, int32_t maxlag, double returnspctile,
+                           double *stock_pacf, double *market_pacf, double *stock_volacluster,
+                           double *market_volacluster, double *kurtoses, double *lossgain, double *corrs);
+
 /* ---- ensemble statistics + the single NCCL allreduce ---------------------------------------- */
 /* multi-process: rank 0 calls fsb_comm_unique_id, ships the 128 bytes to the other ranks by any
  * means, then every rank calls fsb_comm_init_rank.  single-process multi-GPU: fsb_comm_init_all. */
@@ -205,6 +220,8 @@ int32_t fsb_stats_all(fsb_engine **engines, int32_t n, uint64_t *out);
 int32_t fsb_last_run_timing(fsb_engine *e, double *total_ms, double *step_kernel_ms, int64_t *launches);
 /* how many launches of the dominant kernel step_kernel_ms sums over */
 int64_t fsb_last_pass_launches(const fsb_engine *e);
+/* device time (CUDA events on the engine's stream) of the kernel launches of the last fsb_stylised_facts */
+int32_t fsb_last_facts_timing(fsb_engine *e, double *kernel_ms);
 /* asynchronous variant used for overlapping several engines in one process */
 int32_t fsb_run_async(fsb_engine *e, int64_t t_first, int64_t t_last, int32_t selector, int32_t flags);
 int32_t fsb_sync(fsb_engine *e);

@@ -951,3 +951,138 @@ void orc_finalise_fund_value(orc_world *w, int64_t t_now)
         V_(w, k, t_now) = w->nav_close[k];
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Func.calc_stylisedfacts, functions.jl:604-648 -- the array-valued outputs.
+ * PARITY UNPINNED: the reference has no tests for these functions (TODOs at functions.jl:547,554,
+ * 560,572) and the statistics come from packages whose sources are not under /root/reference:
+ * StatsBase v0.30.0 (Manifest.toml:506-510) `pacf` (default method :regression = per lag l the
+ * OLS fit of x[i] on [1, x[i-1..i-l]], i = l+1..n, solved as cholesky(X'X) \ X'y, last
+ * coefficient), `kurtosis` (excess, population moments about the sample mean), `percentile`
+ * (= Statistics.quantile(v, p/100): f0 = (n-1)p, i = trunc(f0)+1, h = f0-trunc(f0),
+ * v[i] + h (v[i+1]-v[i]) on the sorted vector) and Statistics.cor (sums of centred products,
+ * clamped to [-1,1]).  Restated from their published algorithms; all sums sequential, ascending.
+ * Quirks kept: lossgainratio skips another perfwindow[end] returns of the already trimmed series
+ * (functions.jl:575,578) and its cutoff is the 5th percentile of |x|.
+ * ---------------------------------------------------------------------------------------------- */
+static void sf_returns(const double *v, int64_t stride, int64_t T, int64_t W, double *x)
+{   /* assetreturns, functions.jl:500-515: (v[i+1]-v[i])/v[i], i = W+1..T-1 (1-based); then demean :517-535 */
+    const int64_t n = T - W - 1;
+    double s = 0.0;
+    for (int64_t j = 0; j < n; ++j) {
+        const double a = v[(W + j) * stride], b = v[(W + j + 1) * stride];
+        x[j] = (b - a) / a;
+        s = s + x[j];
+    }
+    const double mean = s / (double)n;
+    for (int64_t j = 0; j < n; ++j) x[j] = x[j] - mean;
+}
+
+static double sf_pacf_lag(const double *x, int64_t n, int64_t l)
+{   /* StatsBase pacf_regress!: regressors [1, x[i-1], ..., x[i-l]], response x[i], rows i = l+1..n */
+    enum { MAXD = 65 };
+    double G[MAXD][MAXD], rhs[MAXD];
+    const int64_t d = l + 1;
+    for (int64_t a = 0; a < d; ++a) {
+        for (int64_t b = a; b < d; ++b) {
+            double s = 0.0;
+            for (int64_t i = l; i < n; ++i) s = s + (a ? x[i - a] : 1.0) * (b ? x[i - b] : 1.0);
+            G[a][b] = G[b][a] = s;
+        }
+        double s = 0.0;
+        for (int64_t i = l; i < n; ++i) s = s + (a ? x[i - a] : 1.0) * x[i];
+        rhs[a] = s;
+    }
+    /* Cholesky G = L L', in place in the lower triangle */
+    for (int64_t j = 0; j < d; ++j) {
+        double s = G[j][j];
+        for (int64_t k = 0; k < j; ++k) s = s - G[j][k] * G[j][k];
+        const double ljj = sqrt(s);
+        G[j][j] = ljj;
+        for (int64_t i = j + 1; i < d; ++i) {
+            double t = G[i][j];
+            for (int64_t k = 0; k < j; ++k) t = t - G[i][k] * G[j][k];
+            G[i][j] = t / ljj;
+        }
+    }
+    for (int64_t i = 0; i < d; ++i) {          /* L y = rhs */
+        double t = rhs[i];
+        for (int64_t k = 0; k < i; ++k) t = t - G[i][k] * rhs[k];
+        rhs[i] = t / G[i][i];
+    }
+    for (int64_t i = d - 1; i >= 0; --i) {     /* L' b = y */
+        double t = rhs[i];
+        for (int64_t k = i + 1; k < d; ++k) t = t - G[k][i] * rhs[k];
+        rhs[i] = t / G[i][i];
+    }
+    return rhs[d - 1];
+}
+
+static int sf_cmp(const void *a, const void *b)
+{
+    const double x = *(const double *)a, y = *(const double *)b;
+    return (x > y) - (x < y);
+}
+
+int orc_stylisedfacts(const double *marketval, const double *stocksval, const double *stocksvolume,
+                      int64_t M, int64_t T, int64_t W, int64_t maxlag, double pctile,
+                      double *stock_pacf, double *market_pacf, double *stock_volacluster,
+                      double *market_volacluster, double *kurtoses, double *lossgain, double *corrs)
+{
+    const int64_t n = T - W - 1;
+    if (n < 2 || maxlag < 1 || maxlag > 64 || n <= 2 * maxlag + 1) return ORC_ERR_BAD_STATE;
+    double *x = (double *)malloc(sizeof(double) * (size_t)n * 3);
+    double *y = x + n, *a = y + n;
+    for (int64_t s = 0; s <= M; ++s) {          /* s == M: the market index */
+        if (s < M) sf_returns(stocksval + s, M, T, W, x); else sf_returns(marketval, 1, T, W, x);
+        for (int64_t j = 0; j < n; ++j) y[j] = x[j] * x[j];   /* demeaned returns squared, :616-617 */
+        for (int64_t l = 1; l <= maxlag; ++l) {               /* calc_pacf, :588-602 */
+            const double c = sf_pacf_lag(x, n, l), v = sf_pacf_lag(y, n, l);
+            if (s < M) { stock_pacf[s + M * (l - 1)] = c; stock_volacluster[s + M * (l - 1)] = v; }
+            else       { market_pacf[l - 1] = c; market_volacluster[l - 1] = v; }
+        }
+        if (s == M) break;
+        /* calc_kurtoses :538-545 -> StatsBase.kurtosis(v): moments about mean(v), minus 3 */
+        {
+            double sm = 0.0, c2 = 0.0, c4 = 0.0;
+            for (int64_t j = 0; j < n; ++j) sm = sm + x[j];
+            const double mu = sm / (double)n;
+            for (int64_t j = 0; j < n; ++j) { const double z = x[j] - mu, z2 = z * z; c2 = c2 + z2; c4 = c4 + z2 * z2; }
+            c2 = c2 / (double)n; c4 = c4 / (double)n;
+            kurtoses[s] = c4 / (c2 * c2) - 3.0;
+        }
+        /* lossgainratio :572-586 on x[W+1:end] */
+        {
+            const int64_t n2 = n - W;
+            if (n2 < 1) lossgain[s] = NAN;
+            else {
+                for (int64_t j = 0; j < n2; ++j) a[j] = fabs(x[W + j]);
+                qsort(a, (size_t)n2, sizeof(double), sf_cmp);
+                const double f0 = (double)(n2 - 1) * (pctile / 100.0), t0 = trunc(f0), h = f0 - t0;
+                const int64_t i = (int64_t)t0;
+                const double q = (h == 0.0) ? a[i] : a[i] + h * (a[i + 1] - a[i]);
+                int64_t up = 0, down = 0;
+                for (int64_t j = 0; j < n2; ++j) { up += x[W + j] > q; down += x[W + j] < -q; }
+                lossgain[s] = (double)down / (double)up;
+            }
+        }
+        /* volavolumecorr :560-570: cor(volume[s, W+2:end], |x|) */
+        {
+            const double *vol = stocksvolume + s + M * (W + 1);
+            double sv = 0.0, sa = 0.0;
+            for (int64_t j = 0; j < n; ++j) { sv = sv + vol[M * j]; sa = sa + fabs(x[j]); }
+            const double mv = sv / (double)n, ma = sa / (double)n;
+            double xx = 0.0, yy = 0.0, xy = 0.0;
+            for (int64_t j = 0; j < n; ++j) {
+                const double xi = vol[M * j] - mv, yi = fabs(x[j]) - ma;
+                xx = xx + xi * xi; yy = yy + yi * yi; xy = xy + xi * yi;
+            }
+            const double mx = xx > yy ? xx : yy, mn = xx > yy ? yy : xx;
+            double c = xy / mx / sqrt(mn / mx);
+            if (c > 1.0) c = 1.0; else if (c < -1.0) c = -1.0;   /* clampcor; NaN passes through */
+            corrs[s] = c;
+        }
+    }
+    free(x);
+    return ORC_OK;
+}

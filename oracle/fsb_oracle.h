@@ -138,6 +138,15 @@ int orc_respawn(orc_world *w, int64_t t, double *buy_values, int64_t *buy_funds,
 int orc_reinvest(orc_world *w, int64_t t, int selector, double *buy_values, int64_t *buy_funds,
                  int64_t *nbuy);
 
+/* Func.calc_stylisedfacts, functions.jl:604-648 (array outputs; parity unpinned, see fsb_oracle.c).
+ * Inputs column-major as Julia stores them: marketval[T], stocksval[M x T], stocksvolume[M x T].
+ * Outputs: stock_pacf / stock_volacluster [M x maxlag] column-major, market_* [maxlag],
+ * kurtoses / lossgain / corrs [M]. */
+int orc_stylisedfacts(const double *marketval, const double *stocksval, const double *stocksvolume,
+                      int64_t M, int64_t T, int64_t W, int64_t maxlag, double pctile,
+                      double *stock_pacf, double *market_pacf, double *stock_volacluster,
+                      double *market_volacluster, double *kurtoses, double *lossgain, double *corrs);
+
 /* ---- RNG building blocks exposed for cross-checks against the CUDA engine ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double orc_det_log(double x);

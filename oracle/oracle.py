@@ -110,6 +110,7 @@ def lib():
             getattr(L, name).argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_draw_discrete.restype = C.c_uint32
         L.orc_draw_discrete.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.orc_stylisedfacts.argtypes = [C.c_void_p] * 3 + [C.c_int64] * 4 + [C.c_double] + [C.c_void_p] * 7
         L.orc_dotw.restype = C.c_double
         L.orc_dotw.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]
         _LIB = L
@@ -361,3 +362,21 @@ def dotw(x, y):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)
     return lib().orc_dotw(x.ctypes.data, 1, y.ctypes.data, 1, len(x))
+
+
+def stylisedfacts(marketval, stocksval, stocksvolume, perfwindow_end, maxlag=10, returnspctile=5):
+    """Func.calc_stylisedfacts (functions.jl:604-648), array outputs only; dict keyed by the reference's names."""
+    mk = np.ascontiguousarray(marketval, dtype=np.float64)
+    sv = np.asfortranarray(stocksval, dtype=np.float64)
+    vo = np.asfortranarray(stocksvolume, dtype=np.float64)
+    M, T = sv.shape
+    out = dict(stockpacf=np.zeros((M, maxlag), order="F"), marketpacf=np.zeros(maxlag),
+               stockvolacluster=np.zeros((M, maxlag), order="F"), marketvolacluster=np.zeros(maxlag),
+               stockkurtoses=np.zeros(M), lossgainratios=np.zeros(M), corrs=np.zeros(M))
+    rc = lib().orc_stylisedfacts(mk.ctypes.data, sv.ctypes.data, vo.ctypes.data, M, T, perfwindow_end, maxlag,
+                                 float(returnspctile), *(out[k].ctypes.data for k in (
+                                     "stockpacf", "marketpacf", "stockvolacluster", "marketvolacluster",
+                                     "stockkurtoses", "lossgainratios", "corrs")))
+    if rc != 0:
+        raise ValueError(f"orc_stylisedfacts: {rc}")
+    return out

@@ -1,0 +1,54 @@
+"""Times fsb_stylised_facts after a full run at the default Params shape: R replications with
+keep_history=1, wall clock around the blocking ABI call (kernel + D2H of the M-vectors) and the kernel's own device time, against the
+download of the same replications' M x T histories that the reference's host-side calc_stylisedfacts
+would need.  Usage: python scripts/facts_timing.py [--reps 2048] > gpurun_out/facts_<tag>.json"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from __graft_entry__ import load_package  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--reps", type=int, default=2048)
+ap.add_argument("--days", type=int, default=0, help="simulate only this many days (0 = all); the facts read all T columns either way")
+a = ap.parse_args()
+fsb = load_package()
+p = fsb.Params.default()
+with fsb.Engine(p, a.reps, keep_history=True) as eng:
+    eng.init_device(0xFAC75)
+    t0 = time.perf_counter()
+    t_first = p.perfwindow[-1] + 2
+    try:
+        eng.run(t_first, p.bigt if a.days <= 0 else t_first + a.days - 1, selector="probabilistic")
+    except fsb._lib.FsbError as ex:  # a replication that hit Q6 (functions.jl:282 throws) stops; the others are complete
+        if ex.code != fsb._lib.ERR_REPLICATION:
+            raise
+    t_run = time.perf_counter() - t0
+    eng.stylised_facts(0, min(64, a.reps))  # warm-up
+    best, kbest = 1e30, 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        f = eng.stylised_facts()
+        best = min(best, time.perf_counter() - t0)
+        kbest = min(kbest, eng.last_facts_ms() * 1e-3)
+    t0 = time.perf_counter()
+    nd = min(32, a.reps)
+    for r in range(nd):
+        eng.download_state(r)
+    t_dl = (time.perf_counter() - t0) / nd
+    M, T, W = p.bigm, p.bigt, p.perfwindow[-1]
+    n = T - W - 1
+    hist_bytes = a.reps * (2 * M + 1) * n * 8  # price + volume + market columns the facts read, once
+    out = dict(what="fsb_stylised_facts, default Params shape", replications=a.reps, run_s=t_run, facts_ms=best * 1e3, facts_kernel_ms=kbest * 1e3,
+               kernel_gbps_three_passes=3 * hist_bytes / kbest / 1e9,
+               facts_us_per_replication=best / a.reps * 1e6, history_bytes_once=hist_bytes,
+               history_gbps_single_read=hist_bytes / best / 1e9, passes_over_history=3,
+               download_state_ms_per_replication=t_dl * 1e3,
+               error_replications=int((eng.rep_status() != 0).sum()),
+               finite_kurtoses=float((abs(f["stockkurtoses"]) < 1e300).mean()),
+               mean_kurtosis=float(f["stockkurtoses"][abs(f["stockkurtoses"]) < 1e300].mean()),
+               mean_lag1_pacf=float(f["stockpacf"][:, :, 0][abs(f["stockpacf"][:, :, 0]) < 1e300].mean()))
+    print(json.dumps(out))
