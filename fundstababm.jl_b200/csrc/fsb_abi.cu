@@ -28,10 +28,10 @@ __global__ void fsb_big_events2_kernel(const DevState s, const StepArgs a, const
 }  // namespace fsb
 
 namespace fsb {  // fsb_facts.cu
-int facts_rows();
 int facts_max_lag();
 int facts_max_sel();
-cudaError_t facts_launch(const DevState &d, cudaStream_t st, long long rep_first, int n_reps, int maxlag, double pct, double *out);
+long long facts_doubles_per_rep(int M, int maxlag);
+cudaError_t facts_launch(const DevState &d, cudaStream_t st, long long rep_first, int n_reps, int maxlag, double pct, double *base);
 }  // namespace fsb
 
 using namespace fsb;
@@ -971,12 +971,11 @@ extern "C" int32_t fsb_stylised_facts(fsb_engine *e, int64_t rep_first, int64_t 
     if (n2 >= 1 && static_cast<int>(static_cast<double>(n2 - 1) * (returnspctile / 100.0)) + 2 > facts_max_sel())
         return fail(FSB_ERR_BAD_PARAMS, "percentile %g of %d returns needs more than the %d order statistics a thread keeps",
                     returnspctile, n2, facts_max_sel());
-    const int rows = facts_rows(), nser = M + 1, L = facts_max_lag();
-    const size_t per_rep = static_cast<size_t>(rows) * nser;
-    const int64_t chunk = std::min<int64_t>(n_reps, 4096);
+    // the kernel writes the seven arrays in the caller's layouts; each goes straight to the caller's memory
+    const size_t per_rep = static_cast<size_t>(facts_doubles_per_rep(M, maxlag));
+    const int64_t chunk = std::min<int64_t>(n_reps, 16384);
     double *dev = nullptr;
     CU(cudaMalloc(&dev, per_rep * chunk * 8));
-    std::vector<double> buf(per_rep * chunk);
     int32_t rc = FSB_OK;
     e->last_facts_ms = 0.0;
     for (int64_t c0 = 0; c0 < n_reps && rc == FSB_OK; c0 += chunk) {
@@ -984,25 +983,20 @@ extern "C" int32_t fsb_stylised_facts(fsb_engine *e, int64_t rep_first, int64_t 
         cudaError_t ce = cudaEventRecord(e->ev0, e->stream);
         if (ce == cudaSuccess) ce = facts_launch(d, e->stream, rep_first + c0, static_cast<int>(nc), maxlag, returnspctile, dev);
         if (ce == cudaSuccess) ce = cudaEventRecord(e->ev1, e->stream);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(buf.data(), dev, per_rep * nc * 8, cudaMemcpyDeviceToHost, e->stream);
+        const double *src = dev;
+        auto out = [&](double *dst, size_t per) {  // per: doubles per replication of this array
+            if (dst && ce == cudaSuccess)
+                ce = cudaMemcpyAsync(dst + per * c0, src, per * nc * 8, cudaMemcpyDeviceToHost, e->stream);
+            src += per * nc;
+        };
+        const size_t lm = static_cast<size_t>(maxlag) * M;
+        out(stock_pacf, lm); out(stock_volacluster, lm); out(market_pacf, maxlag); out(market_volacluster, maxlag);
+        out(kurtoses, M); out(lossgain, M); out(corrs, M);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
         float ms = 0.f;
         if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e->ev0, e->ev1);
         if (ce != cudaSuccess) { rc = fail(FSB_ERR_CUDA, "stylised facts: %s", cudaGetErrorString(ce)); break; }
         e->last_facts_ms += ms;
-        for (int64_t i = 0; i < nc; ++i) {
-            const double *b = buf.data() + per_rep * i;
-            const int64_t r = c0 + i;
-            for (int l = 0; l < maxlag; ++l) {
-                if (stock_pacf) std::memcpy(stock_pacf + (r * maxlag + l) * M, b + static_cast<size_t>(l) * nser, M * 8);
-                if (stock_volacluster) std::memcpy(stock_volacluster + (r * maxlag + l) * M, b + static_cast<size_t>(L + l) * nser, M * 8);
-                if (market_pacf) market_pacf[r * maxlag + l] = b[static_cast<size_t>(l) * nser + M];
-                if (market_volacluster) market_volacluster[r * maxlag + l] = b[static_cast<size_t>(L + l) * nser + M];
-            }
-            if (kurtoses) std::memcpy(kurtoses + r * M, b + static_cast<size_t>(2 * L) * nser, M * 8);
-            if (lossgain) std::memcpy(lossgain + r * M, b + static_cast<size_t>(2 * L + 1) * nser, M * 8);
-            if (corrs) std::memcpy(corrs + r * M, b + static_cast<size_t>(2 * L + 2) * nser, M * 8);
-        }
     }
     cudaFree(dev);
     return rc;

@@ -26,7 +26,12 @@ namespace fsb {
 constexpr int kFactLags = 10;   // lags carried in registers (the reference's maxlag default, :605)
 constexpr int kFactSel = 128;   // order statistics a thread can keep for the percentile
 constexpr int kFactThreads = 128;  // series per CTA; a replication's M + 1 series spread over gridDim.y CTAs
-constexpr int kFactRows = 2 * kFactLags + 3;  // rows of the output block: pacf[10], volacluster[10], kurtosis, lossgain, corr
+
+struct FactOut {  // device arrays in the layouts of include/fsb.h, indexed from the first replication of the launch
+    double *pacf, *volc;    // [n_reps][maxlag][M]
+    double *mpacf, *mvolc;  // [n_reps][maxlag]
+    double *kurt, *lg, *corr;  // [n_reps][M]
+};
 
 struct FactSeries {  // where a thread's series lives
     const double *p;       // first value (column 1)
@@ -91,6 +96,38 @@ __device__ __noinline__ double fact_pacf_lag(const double *F, double S, const Fa
     return rhs[dm - 1] / G[dm - 1][dm - 1];
 }
 
+// Keeps the qcap smallest values seen so far in a max-heap (the percentile needs its top two).  Out of line: the
+// walk that calls it is unrolled, and most days no value of a lane qualifies.
+__device__ __noinline__ void fact_heap_insert(double *sel, int &nsel, int qcap, double a)
+{
+    if (nsel < qcap) {  // sift up
+        int k = nsel++;
+        while (k > 0) {
+            const int up = (k - 1) >> 1;
+            const double pv = sel[up];
+            if (!(pv < a)) break;
+            sel[k] = pv;
+            k = up;
+        }
+        sel[k] = a;
+    } else {  // replaces the largest: sift down
+        int k = 0;
+        for (;;) {
+            int c = 2 * k + 1;
+            if (c >= nsel) break;
+            double cv = sel[c];
+            if (c + 1 < nsel) {
+                const double c2 = sel[c + 1];
+                if (c2 > cv) { cv = c2; ++c; }
+            }
+            if (!(cv > a)) break;
+            sel[k] = cv;
+            k = c;
+        }
+        sel[k] = a;
+    }
+}
+
 // Walks a series through time: fn(j, return j, volume j) for j = 0..n-1.  A thread's loads are one per day and
 // each would wait a full HBM round trip if issued where it is used; the loads of kFactAhead days are issued
 // together, ahead of the arithmetic on them.
@@ -99,33 +136,37 @@ template <bool kVol, class Fn>
 __device__ __forceinline__ void fact_walk(const double *__restrict__ p0, const double *__restrict__ v0, long long stride, int n, Fn &&fn)
 {
     double pa = p0[0];
-    for (int j0 = 0; j0 < n; j0 += kFactAhead) {
+    int j0 = 0;
+    for (; j0 + kFactAhead <= n; j0 += kFactAhead) {  // whole groups: no guards, so the unrolled window shifts are renames
         double pb[kFactAhead], vv[kFactAhead];
 #pragma unroll
         for (int u = 0; u < kFactAhead; ++u) {
-            const bool on = j0 + u < n;
-            pb[u] = on ? p0[static_cast<long long>(j0 + u + 1) * stride] : 1.0;
-            vv[u] = (kVol && on) ? v0[static_cast<long long>(j0 + u) * stride] : 0.0;
+            pb[u] = p0[static_cast<long long>(j0 + u + 1) * stride];
+            vv[u] = kVol ? v0[static_cast<long long>(j0 + u) * stride] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < kFactAhead; ++u) {
-            if (j0 + u < n) {
-                fn(j0 + u, (pb[u] - pa) / pa, vv[u]);
-                pa = pb[u];
-            }
+            fn(j0 + u, (pb[u] - pa) / pa, vv[u]);
+            pa = pb[u];
         }
+    }
+#pragma unroll 1
+    for (; j0 < n; ++j0) {
+        const double pb = p0[static_cast<long long>(j0 + 1) * stride];
+        fn(j0, (pb - pa) / pa, kVol ? v0[static_cast<long long>(j0) * stride] : 0.0);
+        pa = pb;
     }
 }
 
 __global__ void __launch_bounds__(kFactThreads, 3)
-fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, const double pct, double *__restrict__ out)
+fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, const double pct, const FactOut out)
 {
     const long long r = rep_first + blockIdx.x;
     const int M = s.M, T = s.T, W = s.W, Mp = s.Mp;
     const int n = T - W - 1;      // returns per series (assetreturns :500-515)
     const int n2 = n - W;         // returns the loss/gain ratio looks at (:575,578)
     const int nser = M + 1;
-    double *o = out + static_cast<long long>(blockIdx.x) * kFactRows * nser;
+    const long long rb = blockIdx.x;
     // percentile(v, pct) = quantile(v, pct/100): f0 = (n2-1) p, i = trunc(f0), h = f0 - i (Statistics._quantile)
     int qi = 0, qcap = 0;
     double qh = 0.0;
@@ -181,34 +222,9 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
             for (int d = kFactLags - 1; d > 0; --d) xw[d] = xw[d - 1];
             xw[0] = x;
             if (j < kFactLags) head[j] = x;
-            if (stock && j >= W && qcap > 0) {  // keep the qcap smallest |x| in a max-heap: the percentile needs its top two
+            if (stock && j >= W && qcap > 0) {
                 const double a = fabs(x);
-                if (nsel < qcap) {  // sift up
-                    int k = nsel++;
-                    while (k > 0) {
-                        const int up = (k - 1) >> 1;
-                        const double pv = sel[up];
-                        if (!(pv < a)) break;
-                        sel[k] = pv;
-                        k = up;
-                    }
-                    sel[k] = a;
-                } else if (a < sel[0]) {  // replaces the largest: sift down
-                    int k = 0;
-                    for (;;) {
-                        int c = 2 * k + 1;
-                        if (c >= nsel) break;
-                        double cv = sel[c];
-                        if (c + 1 < nsel) {
-                            const double c2 = sel[c + 1];
-                            if (c2 > cv) { cv = c2; ++c; }
-                        }
-                        if (!(cv > a)) break;
-                        sel[k] = cv;
-                        k = c;
-                    }
-                    sel[k] = a;
-                }
+                if (nsel < qcap || a < sel[0]) fact_heap_insert(sel, nsel, qcap, a);
             }
         });
         // the sums leave their registers for the per-lag solves (local memory from here on)
@@ -219,16 +235,19 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
         for (int d = 0; d < kFactLags; ++d) tail[d] = xw[d];
         FactEdges ed;
         fact_edges(ed, head, tail);
-        for (int l = 1; l <= maxlag; ++l) o[static_cast<long long>(l - 1) * nser + ser] = fact_pacf_lag(Fl, sx, ed, n, l);
+        double *o1 = ser < M ? out.pacf + rb * maxlag * M + ser : out.mpacf + rb * maxlag;
+        double *o2 = ser < M ? out.volc + rb * maxlag * M + ser : out.mvolc + rb * maxlag;
+        const int ostride = ser < M ? M : 1;
+        for (int l = 1; l <= maxlag; ++l) o1[static_cast<long long>(l - 1) * ostride] = fact_pacf_lag(Fl, sx, ed, n, l);
         for (int d = 0; d < kFactLags; ++d) { head[d] *= head[d]; tail[d] *= tail[d]; }
         fact_edges(ed, head, tail);
-        for (int l = 1; l <= maxlag; ++l) o[static_cast<long long>(kFactLags + l - 1) * nser + ser] = fact_pacf_lag(Fyl, F[0], ed, n, l);
+        for (int l = 1; l <= maxlag; ++l) o2[static_cast<long long>(l - 1) * ostride] = fact_pacf_lag(Fyl, F[0], ed, n, l);
         if (!fs.vol) continue;
         // kurtosis (StatsBase: population moments about the sample mean, minus 3).  The series is demeaned already;
         // its residual mean (~1e-19) moves the moments by less than their last bit and is dropped.
         {
             const double nn = static_cast<double>(n), c2 = F[0] / nn, c4 = Fy[0] / nn;
-            o[static_cast<long long>(2 * kFactLags) * nser + ser] = c4 / (c2 * c2) - 3.0;
+            out.kurt[rb * M + ser] = c4 / (c2 * c2) - 3.0;
         }
         // pass 3: loss/gain counts and the centred sums of cor(volume, |x|)
         double q = 0.0;
@@ -251,23 +270,33 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
             yy += yi * yi;
             xy += xi * yi;
         });
-        o[static_cast<long long>(2 * kFactLags + 1) * nser + ser] =
+        out.lg[rb * M + ser] =
             n2 >= 1 ? static_cast<double>(down) / static_cast<double>(up) : __longlong_as_double(0x7ff8000000000000LL);
         const double mx = xx > yy ? xx : yy, mn = xx > yy ? yy : xx;
         double c = xy / mx / sqrt(mn / mx);
         if (c > 1.0) c = 1.0; else if (c < -1.0) c = -1.0;
-        o[static_cast<long long>(2 * kFactLags + 2) * nser + ser] = c;
+        out.corr[rb * M + ser] = c;
     }
 }
 
-// launched by fsb_stylised_facts (fsb_abi.cu); out: device [n_reps][kFactRows][M + 1]
-int facts_rows() { return kFactRows; }
+// launched by fsb_stylised_facts (fsb_abi.cu); out: seven device arrays carved from one allocation of
+// facts_doubles_per_rep(M, maxlag) doubles per replication, in the order of FactOut
 int facts_max_lag() { return kFactLags; }
 int facts_max_sel() { return kFactSel; }
-cudaError_t facts_launch(const DevState &d, cudaStream_t st, long long rep_first, int n_reps, int maxlag, double pct, double *out)
+long long facts_doubles_per_rep(int M, int maxlag) { return 2LL * maxlag * M + 2LL * maxlag + 3LL * M; }
+cudaError_t facts_launch(const DevState &d, cudaStream_t st, long long rep_first, int n_reps, int maxlag, double pct, double *base)
 {
+    const long long M = d.M, nr = n_reps;
+    FactOut o;
+    o.pacf = base;
+    o.volc = o.pacf + nr * maxlag * M;
+    o.mpacf = o.volc + nr * maxlag * M;
+    o.mvolc = o.mpacf + nr * maxlag;
+    o.kurt = o.mvolc + nr * maxlag;
+    o.lg = o.kurt + nr * M;
+    o.corr = o.lg + nr * M;
     const dim3 grid(static_cast<unsigned>(n_reps), static_cast<unsigned>(std::min((d.M + 1 + kFactThreads - 1) / kFactThreads, 64)));
-    fsb_facts_kernel<<<grid, kFactThreads, 0, st>>>(d, rep_first, maxlag, pct, out);
+    fsb_facts_kernel<<<grid, kFactThreads, 0, st>>>(d, rep_first, maxlag, pct, o);
     return cudaGetLastError();
 }
 

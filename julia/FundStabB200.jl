@@ -111,4 +111,24 @@ function modelrun(market, stocks, investors, funds, params, fundselector="bestpe
             failtime=failtime, ninvestors=ninvestors, nstocks=nstocks)
 end
 
+# Func.calc_stylisedfacts (src/functions.jl:604-648; called at src/runmodel.jl:47) from the histories an
+# engine holds on the device after a run: only the per-stock vectors cross the host link.  Returns the
+# array-valued entries of the reference's result tuple; the z-tests / KS test (:629-641) run on them in
+# Julia as before.
+function stylisedfacts(e::Engine, params; rep=0, maxlag=10, returnspctile=5)
+    M = params.bigm
+    stockpacf = zeros(M, maxlag); stockvolacluster = zeros(M, maxlag)
+    marketpacf = zeros(maxlag); marketvolacluster = zeros(maxlag)
+    kurtoses = zeros(M); lossgainratios = zeros(M); corrs = zeros(M)
+    check(ccall((:fsb_stylised_facts, LIB), Int32,
+        (Ptr{Cvoid}, Int64, Int64, Int32, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        e.handle, rep, 1, maxlag, returnspctile, stockpacf, marketpacf, stockvolacluster, marketvolacluster,
+        kurtoses, lossgainratios, corrs))
+    nreturns = params.bigt - last(params.perfwindow) - 1
+    return (stockpacf=(stockpacf, 1.96 / sqrt(M)), marketpacf=(marketpacf, 1.96 / sqrt(nreturns)),
+            stockvolacluster=(stockvolacluster, 1.96 / sqrt(M)), marketvolacluster=(marketvolacluster, 1.96 / sqrt(nreturns)),
+            stockkurtoses=kurtoses, lossgainratios=lossgainratios, corrs=corrs)
+end
+
 end # module
