@@ -5,14 +5,19 @@
 as ONE device-resident batch: every (parameter point, replication) pair is a replication of the
 engine, sharded over the ranks of ``torch.distributed`` (if initialised) by contiguous blocks of
 the flattened index; the per-point integer ensemble statistics are summed with a single NCCL
-allreduce inside the library (fsb_stats).  The surrogate / selector stages of the sketch are
-host-side model fitting and stay out of scope.
+allreduce inside the library (fsb_stats).  The "Evaluation" stage can also be the stylised facts of
+every replication (``evaluation="stylisedfacts"``: Func.calc_stylisedfacts on the device),
+averaged per point.  The surrogate / selector stages of the sketch are host-side model fitting and stay
+out of scope.
 """
 from __future__ import annotations
 
 import itertools
 
+import numpy as np
+
 from . import params as Params
+from . import _lib as L
 from .engine import Engine, comm_unique_id
 
 
@@ -57,10 +62,62 @@ def share_unique_id(dist, device):
     return bytes(buf.cpu().tolist())
 
 
+FACT_SCALARS = ("stockkurtoses", "lossgainratios", "corrs")
+FACT_LAGGED = ("stockpacf", "stockvolacluster", "marketpacf", "marketvolacluster")
+
+
+def facts_moments(facts, point_of_rep, n_points):
+    """Result averaging, step 1 (per rank): per point the sums and counts of the FINITE entries of every
+    stylised fact over this rank's replications (and stocks) -- NaN trajectories (Q12) and stocks that never
+    traded (NaN correlation) are left out, and counted.  Returns [n_points][n_fields][2] float64 where the
+    fields are the three per-stock scalars followed by maxlag entries for each of the four PACF families."""
+    maxlag = facts["marketpacf"].shape[-1]
+    cols = []
+    for k in FACT_SCALARS:                       # [rep][stock]
+        cols.append(facts[k][:, :, None])
+    for k in FACT_LAGGED[:2]:                    # [rep][stock][lag]
+        cols.append(facts[k])
+    for k in FACT_LAGGED[2:]:                    # [rep][lag]
+        cols.append(facts[k][:, None, :])
+    out = np.zeros((n_points, len(FACT_SCALARS) + 4 * maxlag, 2))
+    pt = np.asarray(point_of_rep)
+    f0 = 0
+    for c in cols:
+        ok = np.isfinite(c)
+        v = np.where(ok, c, 0.0)
+        for p in np.unique(pt):
+            m = pt == p
+            out[p, f0:f0 + c.shape[2], 0] += v[m].sum(axis=(0, 1))
+            out[p, f0:f0 + c.shape[2], 1] += ok[m].sum(axis=(0, 1))
+        f0 += c.shape[2]
+    return out
+
+
+def facts_means(moments):
+    """Result averaging, step 2 (after the sum over ranks): one dict per point, keyed like calc_stylisedfacts."""
+    maxlag = (moments.shape[1] - len(FACT_SCALARS)) // 4
+    res = []
+    for m in moments:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mean = m[:, 0] / m[:, 1]
+        d = {k: float(mean[i]) for i, k in enumerate(FACT_SCALARS)}
+        d.update({k + "_n": int(m[i, 1]) for i, k in enumerate(FACT_SCALARS)})
+        for j, k in enumerate(FACT_LAGGED):
+            a = len(FACT_SCALARS) + j * maxlag
+            d[k] = mean[a:a + maxlag].copy()
+        res.append(d)
+    return res
+
+
 def calibrate(points, reps, *, seed=0, fundselector="probabilistic", device=0, t_last=None, steps_per_launch=1,
-              engine_kwargs=None):
+              engine_kwargs=None, evaluation=None, maxlag=10, returnspctile=5):
     """Runs ``reps`` replications of every point and returns one statistics dict per point
-    (identical on every rank)."""
+    (identical on every rank).  ``evaluation="stylisedfacts"`` keeps the histories on the device
+    (5.4 MB per replication at the default shape), computes Func.calc_stylisedfacts of every replication
+    there and adds the per-point means over replications and stocks under ``"stylisedfacts"`` (float sums
+    over ranks: equal across world sizes to rounding, unlike the integer statistics)."""
+    if evaluation not in (None, "stylisedfacts"):
+        raise ValueError(f"unknown evaluation {evaluation!r}")
     dist = _dist()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     total = len(points) * reps
@@ -68,10 +125,29 @@ def calibrate(points, reps, *, seed=0, fundselector="probabilistic", device=0, t
     if hi <= lo:
         raise ValueError("fewer (point, replication) pairs than ranks")
     kw = dict(engine_kwargs or {})
+    if evaluation:
+        kw["keep_history"] = True
     with Engine(points, hi - lo, rep_offset=lo, reps_per_point=reps, device=device,
                 steps_per_launch=steps_per_launch, **kw) as eng:
         if world > 1:
             eng.comm_init_rank(world, rank, share_unique_id(dist, device))
         eng.init_device(seed)
-        eng.run(t_last=t_last, selector=fundselector)
-        return eng.stats()
+        try:
+            eng.run(t_last=t_last, selector=fundselector)
+        except L.FsbError as ex:  # replications that hit Q6 stop and are counted in error_replications
+            if ex.code != L.ERR_REPLICATION:
+                raise
+        stats = eng.stats()
+        if evaluation:
+            facts = eng.stylised_facts(maxlag=maxlag, returnspctile=returnspctile)
+            mom = facts_moments(facts, (lo + np.arange(hi - lo)) // reps, len(points))
+            if world > 1:
+                import torch
+                t = torch.from_numpy(mom)
+                if dist.get_backend() == "nccl":
+                    t = t.cuda(device)
+                dist.all_reduce(t)
+                mom = t.cpu().numpy()
+            for st, f in zip(stats, facts_means(mom)):
+                st["stylisedfacts"] = f
+        return stats

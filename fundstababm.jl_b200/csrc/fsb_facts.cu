@@ -8,8 +8,8 @@
 // One thread per series (stock m, or the market index as series M), 128 series per CTA: thread m
 // walks its series through time, so a warp reads 32 consecutive stocks of one price column -- the
 // histories are [t][asset], asset fastest, and every load is coalesced.  Three passes over the
-// history: (1) means of returns and volume, (2) lagged products, moments and the order statistics
-// the percentile needs, (3) up/down counts and the centred correlation sums.
+// prices, one over the volume: (1) the mean return, (2) lagged products, moments, the volume sums and
+// the order statistics the percentile needs, (3) up/down counts against the percentile.
 //
 // PACF by regression as StatsBase v0.30.0 does it (per lag l: OLS of x[i] on [1, x[i-1..i-l]],
 // i = l+1..n, through the Cholesky factor of X'X) -- but the (l+1)^2 sums of every lag are derived
@@ -131,8 +131,7 @@ __device__ __noinline__ void fact_heap_insert(double *sel, int &nsel, int qcap, 
 // Walks a series through time: fn(j, return j, volume j) for j = 0..n-1.  A thread's loads are one per day and
 // each would wait a full HBM round trip if issued where it is used; the loads of kFactAhead days are issued
 // together, ahead of the arithmetic on them.
-constexpr int kFactAhead = 8;
-template <bool kVol, class Fn>
+template <bool kVol, int kFactAhead, class Fn>
 __device__ __forceinline__ void fact_walk(const double *__restrict__ p0, const double *__restrict__ v0, long long stride, int n, Fn &&fn)
 {
     double pa = p0[0];
@@ -188,12 +187,13 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
             fs.vol = nullptr;
         }
         const double *p0 = fs.p + static_cast<long long>(W) * fs.stride;            // column W+1
-        const double *v0 = fs.vol ? fs.vol + static_cast<long long>(W + 1) * fs.stride : nullptr;  // column W+2
-        // pass 1: means
-        double sr = 0.0, sv = 0.0;
-        if (v0) fact_walk<true>(p0, v0, fs.stride, n, [&](int, double ret, double v) { sr += ret; sv += v; });
-        else fact_walk<false>(p0, v0, fs.stride, n, [&](int, double ret, double) { sr += ret; });
-        const double mean = sr / static_cast<double>(n), mv = sv / static_cast<double>(n);
+        // column W+2 of the volume; the market index has none and reads its own values instead (sums unused), so that
+        // one instantiation of the walk serves every series
+        const double *v0 = fs.vol ? fs.vol + static_cast<long long>(W + 1) * fs.stride : p0;
+        // pass 1: the mean return
+        double sr = 0.0;
+        fact_walk<false, 8>(p0, v0, fs.stride, n, [&](int, double ret, double) { sr += ret; });
+        const double mean = sr / static_cast<double>(n);
         // pass 2: lagged products of x and of y = x^2, sums, order statistics of |x|
         double F[kFactLags + 1], Fy[kFactLags + 1], xw[kFactLags];
         double head[kFactLags], sel[kFactSel];
@@ -202,14 +202,17 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
 #pragma unroll
         for (int d = 0; d < kFactLags; ++d) xw[d] = 0.0;
         for (int d = 0; d < kFactLags; ++d) head[d] = 0.0;
-        double sx = 0.0, sabs = 0.0;
+        double sx = 0.0, sabs = 0.0, sv = 0.0, svv = 0.0, sva = 0.0;
         int nsel = 0;
         const bool stock = fs.vol != nullptr;
-        fact_walk<false>(p0, v0, fs.stride, n, [&](int j, double ret, double) {
+        fact_walk<true, 4>(p0, v0, fs.stride, n, [&](int j, double ret, double v) {
             const double x = ret - mean;
             const double y = x * x;
             sx += x;
             sabs += fabs(x);
+            sv += v;
+            svv += v * v;
+            sva += v * fabs(x);
             F[0] += y;
             Fy[0] += y * y;
 #pragma unroll
@@ -249,7 +252,7 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
             const double nn = static_cast<double>(n), c2 = F[0] / nn, c4 = Fy[0] / nn;
             out.kurt[rb * M + ser] = c4 / (c2 * c2) - 3.0;
         }
-        // pass 3: loss/gain counts and the centred sums of cor(volume, |x|)
+        // pass 3: loss/gain counts
         double q = 0.0;
         if (n2 >= 1) {  // sorted a[qi], a[qi+1] = the two largest of the qi+2 smallest (the heap's root and its larger child)
             double hi = sel[0], lo = sel[0];
@@ -259,17 +262,20 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
             }
             q = (qh == 0.0) ? lo : lo + qh * (hi - lo);
         }
-        const double ma = sabs / static_cast<double>(n);
         int up = 0, down = 0;
-        double xx = 0.0, yy = 0.0, xy = 0.0;
-        fact_walk<true>(p0, v0, fs.stride, n, [&](int j, double ret, double v) {
+        fact_walk<false, 8>(p0, v0, fs.stride, n, [&](int j, double ret, double) {
             const double x = ret - mean;
             if (j >= W) { up += x > q; down += x < -q; }
-            const double xi = v - mv, yi = fabs(x) - ma;
-            xx += xi * xi;
-            yy += yi * yi;
-            xy += xi * yi;
         });
+        // cor(volume, |x|) from the raw sums of pass 2: sum (v - mv)^2 = svv - sv^2 / n, sum (|x| - ma)^2 = F_0 - sabs^2 / n,
+        // sum (v - mv)(|x| - ma) = sva - sv sabs / n.  None of the three cancels badly: volumes are sparse spikes
+        // (mean^2 << mean square), |x| has mean^2 / mean square ~ 2 / pi, and the error of the cross term is
+        // ~1e-16 (mv / sd v)(ma / sd |x|) of the normaliser.  A constant volume series (the reference's NaN: no trade
+        // ever touched the stock) must not turn into rounding noise: below n eps of its raw sum the centred sum is 0.
+        const double nn = static_cast<double>(n);
+        double xx = svv - sv * sv / nn;
+        if (!(xx > svv * nn * 2.3e-16)) xx = (xx != xx) ? xx : 0.0;
+        const double yy = F[0] - sabs * sabs / nn, xy = sva - sv * sabs / nn;
         out.lg[rb * M + ser] =
             n2 >= 1 ? static_cast<double>(down) / static_cast<double>(up) : __longlong_as_double(0x7ff8000000000000LL);
         const double mx = xx > yy ? xx : yy, mn = xx > yy ? yy : xx;

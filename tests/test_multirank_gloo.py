@@ -66,6 +66,23 @@ def _worker(rank, world, port, out_dir):
         st = eng_mod.decode_stats(mine.numpy().astype(np.uint64), T)
         assert st["replications"] == int(per_rep[:, L.ST_REPS].sum())
 
+        # 3b. the float "result averaging" of calibrate(evaluation="stylisedfacts"): per-point sums and counts of
+        #     the finite stylised facts, summed over ranks, equal the unsharded ones to rounding
+        R, M, Lg, reps = 22, 6, 3, 11
+        frng = np.random.default_rng(9)
+        facts = dict(stockpacf=frng.standard_normal((R, M, Lg)), stockvolacluster=frng.standard_normal((R, M, Lg)),
+                     marketpacf=frng.standard_normal((R, Lg)), marketvolacluster=frng.standard_normal((R, Lg)),
+                     stockkurtoses=frng.standard_normal((R, M)), lossgainratios=frng.random((R, M)),
+                     corrs=frng.random((R, M)))
+        facts["corrs"][3, 2] = np.nan
+        pts = np.arange(R) // reps
+        a, b = cal.shard(R, rank, world)
+        mom = torch.from_numpy(cal.facts_moments({k: v[a:b] for k, v in facts.items()}, pts[a:b], 2))
+        dist.all_reduce(mom)
+        np.testing.assert_allclose(mom.numpy(), cal.facts_moments(facts, pts, 2), rtol=1e-13)
+        means = cal.facts_means(mom.numpy())
+        assert means[0]["corrs_n"] == reps * M - 1 and means[1]["corrs_n"] == reps * M
+
         # 4. bench.py's timing reduction: max over ranks
         t = torch.tensor([10.0 + rank], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -62,6 +62,41 @@ def test_oracle_rejects_short_series(orc):
         orc.stylisedfacts(mk, sv, vo, 10, maxlag=10)   # 19 returns for 10 lags
 
 
+def fake_facts(rng, R, M, L, nan_reps=()):
+    f = dict(stockpacf=rng.standard_normal((R, M, L)), stockvolacluster=rng.standard_normal((R, M, L)),
+             marketpacf=rng.standard_normal((R, L)), marketvolacluster=rng.standard_normal((R, L)),
+             stockkurtoses=rng.standard_normal((R, M)) + 3, lossgainratios=rng.random((R, M)) + 0.5,
+             corrs=rng.random((R, M)) - 0.5)
+    for r in nan_reps:
+        for v in f.values():
+            v[r] = np.nan
+    f["corrs"][0, 1] = np.nan          # a stock that never traded
+    f["lossgainratios"][1, 0] = np.inf   # no up-move beyond the cutoff
+    return f
+
+
+def test_calibrate_result_averaging(fsb):
+    """Per-point means over the finite entries; sharding the replications over ranks only reorders a sum."""
+    cal = fsb._calibrate
+    R, M, L, reps = 12, 5, 4, 4
+    f = fake_facts(np.random.default_rng(2), R, M, L, nan_reps=(5,))
+    pts = np.arange(R) // reps
+    whole = cal.facts_moments(f, pts, 3)
+    parts = sum(cal.facts_moments({k: v[a:b] for k, v in f.items()}, pts[a:b], 3) for a, b in ((0, 5), (5, 7), (7, 12)))
+    np.testing.assert_allclose(parts, whole, rtol=1e-13)
+    means = cal.facts_means(whole)
+    assert len(means) == 3
+    k = f["stockkurtoses"]
+    assert abs(means[0]["stockkurtoses"] - k[:4].mean()) < 1e-13 and means[0]["stockkurtoses_n"] == 4 * M
+    assert means[1]["stockkurtoses_n"] == 3 * M                       # replication 5 is a NaN trajectory
+    assert abs(means[1]["stockkurtoses"] - np.nanmean(k[4:8])) < 1e-13
+    assert means[0]["corrs_n"] == 4 * M - 1 and means[0]["lossgainratios_n"] == 4 * M - 1
+    np.testing.assert_allclose(means[2]["marketpacf"], f["marketpacf"][8:].mean(axis=0), rtol=1e-13)
+    np.testing.assert_allclose(means[1]["stockvolacluster"], np.nanmean(f["stockvolacluster"][4:8], axis=(0, 1)), rtol=1e-13)
+    with pytest.raises(ValueError):
+        fsb.calibrate([fsb.Params.default()], 1, evaluation="kurtosis")
+
+
 def assert_facts_close(got, ref):
     for k in ("stockpacf", "stockvolacluster", "marketpacf", "marketvolacluster"):
         g = got[k][0] if isinstance(got[k], tuple) else got[k]
@@ -144,3 +179,25 @@ def test_device_facts_errors(fsb):
         with pytest.raises(fsb._lib.FsbError):
             eng.stylised_facts()
         eng.stylised_facts(maxlag=3)
+
+
+@pytest.mark.gpu
+def test_calibrate_evaluates_stylised_facts(fsb):
+    """configs[4] in miniature with the "Evaluation" stage of src/calibrate.jl:14-16 on the device."""
+    base = H.small_params(fsb, bigt=100)
+    pts = fsb.grid(base, thresholdstd=(0.02, 0.1))
+    reps = 4
+    stats = fsb.calibrate(pts, reps, seed=SEED, evaluation="stylisedfacts", maxlag=5)
+    plain = fsb.calibrate(pts, reps, seed=SEED)
+    for i in range(len(pts)):
+        for k, v in plain[i].items():
+            assert H.eq(stats[i][k], v), k                  # keeping the histories changes no outcome
+        with fsb.Engine(pts, reps, rep_offset=i * reps, reps_per_point=reps, keep_history=True) as eng:
+            eng.init_device(SEED)
+            eng.run()
+            f = eng.stylised_facts(maxlag=5)
+        sf = stats[i]["stylisedfacts"]
+        np.testing.assert_allclose(sf["stockkurtoses"], f["stockkurtoses"][np.isfinite(f["stockkurtoses"])].mean(), rtol=1e-12)
+        np.testing.assert_allclose(sf["marketpacf"], f["marketpacf"].mean(axis=0), rtol=1e-12)
+        np.testing.assert_allclose(sf["stockpacf"], np.nanmean(f["stockpacf"], axis=(0, 1)), rtol=1e-12)
+        assert sf["marketpacf"].shape == (5,)
