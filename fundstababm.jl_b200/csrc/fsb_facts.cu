@@ -7,12 +7,14 @@
 //
 // One thread per series (stock m, or the market index as series M), 128 series per CTA: thread m
 // walks its series through time, so a warp reads 32 consecutive stocks of one price column -- the
-// histories are [t][asset], asset fastest, and every load is coalesced.  Three passes over the
-// prices, one over the volume: (1) the mean return, (2) lagged products, moments, the volume sums and
-// the order statistics the percentile needs, (3) up/down counts against the percentile.
+// histories are [t][asset], asset fastest, and every load is coalesced.  Two launches, one per role:
+// <0> the series' own statistics in three walks over the prices and one over the volume -- (1) the mean
+// return, (2) lagged products of x, moments, the volume sums and the order statistics the percentile
+// needs, (3) up/down counts against the percentile; <1> volatility clustering -- the mean, then the
+// lagged products of x^2.
 //
 // PACF by regression as StatsBase v0.30.0 does it (per lag l: OLS of x[i] on [1, x[i-1..i-l]],
-// i = l+1..n, through the Cholesky factor of X'X) -- but the (l+1)^2 sums of every lag are derived
+// i = l+1..n, through a factorisation of X'X) -- but the (l+1)^2 sums of every lag are derived
 // from 11 full-range lagged sums F_d = sum_s x[s] x[s-d] minus the few head / tail products each
 // window leaves out, instead of 10 passes with up to 66 running sums.
 #include <cuda_runtime.h>
@@ -75,25 +77,31 @@ __device__ __noinline__ double fact_pacf_lag(const double *F, double S, const Fa
         if (a == 0) rhs[0] = sa; else G[a][0] = sa;
     }
     G[0][0] = static_cast<double>(n - l);
+    // X'X = L D L' (unit lower triangular L, no square roots, one reciprocal per column instead of a division per
+    // entry); L y = rhs; the last unknown of L' b = D^-1 y is y_last / D_last
     const int dm = l + 1;
-    for (int j = 0; j < dm; ++j) {  // Cholesky, lower triangle in place
-        double s = G[j][j];
-        for (int k = 0; k < j; ++k) s -= G[j][k] * G[j][k];
-        const double ljj = sqrt(s);
-        G[j][j] = ljj;
+    double v[kFactLags + 1], dlast = 1.0;
+    for (int j = 0; j < dm; ++j) {
+        double dj = G[j][j];
+        for (int k = 0; k < j; ++k) {
+            v[k] = G[j][k] * G[k][k];  // L_jk D_k
+            dj -= G[j][k] * v[k];
+        }
+        G[j][j] = dj;
+        dlast = dj;
+        const double inv = 1.0 / dj;
         for (int i = j + 1; i < dm; ++i) {
             double t = G[i][j];
-            for (int k = 0; k < j; ++k) t -= G[i][k] * G[j][k];
-            G[i][j] = t / ljj;
+            for (int k = 0; k < j; ++k) t -= G[i][k] * v[k];
+            G[i][j] = t * inv;
         }
     }
-    for (int i = 0; i < dm; ++i) {
+    for (int i = 1; i < dm; ++i) {
         double t = rhs[i];
         for (int k = 0; k < i; ++k) t -= G[i][k] * rhs[k];
-        rhs[i] = t / G[i][i];
+        rhs[i] = t;
     }
-    // back substitution: only the last unknown is needed
-    return rhs[dm - 1] / G[dm - 1][dm - 1];
+    return rhs[dm - 1] / dlast;
 }
 
 // Keeps the qcap smallest values seen so far in a max-heap (the percentile needs its top two).  Out of line: the
@@ -130,7 +138,8 @@ __device__ __noinline__ void fact_heap_insert(double *sel, int &nsel, int qcap, 
 
 // Walks a series through time: fn(j, return j, volume j) for j = 0..n-1.  A thread's loads are one per day and
 // each would wait a full HBM round trip if issued where it is used; the loads of kFactAhead days are issued
-// together, ahead of the arithmetic on them.
+// together, ahead of the arithmetic on them.  (An additional prefetch.global.L2 of the lines 24 days ahead
+// measured -5 %: the remaining stalls are not HBM latency.)
 template <bool kVol, int kFactAhead, class Fn>
 __device__ __forceinline__ void fact_walk(const double *__restrict__ p0, const double *__restrict__ v0, long long stride, int n, Fn &&fn)
 {
@@ -157,7 +166,11 @@ __device__ __forceinline__ void fact_walk(const double *__restrict__ p0, const d
     }
 }
 
-__global__ void __launch_bounds__(kFactThreads, 3)
+// kRole 0: the series' own statistics (PACF of x, kurtosis, loss/gain ratio, volume correlation);
+// kRole 1: volatility clustering (PACF of y = x^2).  Two launches: each role carries 11 lagged sums and a 10-deep
+// window in registers instead of both (168 registers, 12 warps per SM), so 4 CTAs fit per SM.
+template <int kRole>
+__global__ void __launch_bounds__(kFactThreads, 4)
 fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, const double pct, const FactOut out)
 {
     const long long r = rep_first + blockIdx.x;
@@ -190,98 +203,100 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
         // column W+2 of the volume; the market index has none and reads its own values instead (sums unused), so that
         // one instantiation of the walk serves every series
         const double *v0 = fs.vol ? fs.vol + static_cast<long long>(W + 1) * fs.stride : p0;
+        const int ostride = ser < M ? M : 1;
         // pass 1: the mean return
         double sr = 0.0;
         fact_walk<false, 8>(p0, v0, fs.stride, n, [&](int, double ret, double) { sr += ret; });
         const double mean = sr / static_cast<double>(n);
-        // pass 2: lagged products of x and of y = x^2, sums, order statistics of |x|
-        double F[kFactLags + 1], Fy[kFactLags + 1], xw[kFactLags];
-        double head[kFactLags], sel[kFactSel];
+        // pass 2: the 11 full-range lagged sums of z (x or y) with a window of the last 10 z, and the first 10 z
+        double F[kFactLags + 1], zw[kFactLags], head[kFactLags];
 #pragma unroll
-        for (int d = 0; d <= kFactLags; ++d) F[d] = Fy[d] = 0.0;
+        for (int d = 0; d <= kFactLags; ++d) F[d] = 0.0;
 #pragma unroll
-        for (int d = 0; d < kFactLags; ++d) xw[d] = 0.0;
+        for (int d = 0; d < kFactLags; ++d) zw[d] = 0.0;
         for (int d = 0; d < kFactLags; ++d) head[d] = 0.0;
-        double sx = 0.0, sabs = 0.0, sv = 0.0, svv = 0.0, sva = 0.0;
-        int nsel = 0;
-        const bool stock = fs.vol != nullptr;
-        fact_walk<true, 4>(p0, v0, fs.stride, n, [&](int j, double ret, double v) {
-            const double x = ret - mean;
-            const double y = x * x;
-            sx += x;
-            sabs += fabs(x);
-            sv += v;
-            svv += v * v;
-            sva += v * fabs(x);
-            F[0] += y;
-            Fy[0] += y * y;
+        double sz = 0.0;
+        auto lagged = [&](int j, double z) {
+            sz += z;
+            F[0] += z * z;
 #pragma unroll
-            for (int d = 1; d <= kFactLags; ++d) {
-                const double xl = xw[d - 1];
-                F[d] += x * xl;
-                Fy[d] += y * (xl * xl);
+            for (int d = 1; d <= kFactLags; ++d) F[d] += z * zw[d - 1];
+#pragma unroll
+            for (int d = kFactLags - 1; d > 0; --d) zw[d] = zw[d - 1];
+            zw[0] = z;
+            if (j < kFactLags) head[j] = z;
+        };
+        auto solve = [&](double *o) {  // the sums leave their registers for the per-lag solves (local memory from here on)
+            double Fl[kFactLags + 1], tail[kFactLags];
+#pragma unroll
+            for (int d = 0; d <= kFactLags; ++d) Fl[d] = F[d];
+#pragma unroll
+            for (int d = 0; d < kFactLags; ++d) tail[d] = zw[d];
+            FactEdges ed;
+            fact_edges(ed, head, tail);
+            for (int l = 1; l <= maxlag; ++l) o[static_cast<long long>(l - 1) * ostride] = fact_pacf_lag(Fl, sz, ed, n, l);
+        };
+        if constexpr (kRole == 1) {
+            fact_walk<false, 8>(p0, v0, fs.stride, n, [&](int j, double ret, double) {
+                const double x = ret - mean;
+                lagged(j, x * x);
+            });
+            solve(ser < M ? out.volc + rb * maxlag * M + ser : out.mvolc + rb * maxlag);
+        } else {
+            // ... plus the fourth moment, sum |x|, the raw volume sums and the order statistics of |x| the percentile needs
+            double sel[kFactSel];
+            double s4 = 0.0, sabs = 0.0, sv = 0.0, svv = 0.0, sva = 0.0;
+            int nsel = 0;
+            const bool stock = fs.vol != nullptr;
+            fact_walk<true, 4>(p0, v0, fs.stride, n, [&](int j, double ret, double v) {
+                const double x = ret - mean, a = fabs(x), y = x * x;
+                s4 += y * y;
+                sabs += a;
+                sv += v;
+                svv += v * v;
+                sva += v * a;
+                lagged(j, x);
+                if (stock && j >= W && qcap > 0 && (nsel < qcap || a < sel[0])) fact_heap_insert(sel, nsel, qcap, a);
+            });
+            solve(ser < M ? out.pacf + rb * maxlag * M + ser : out.mpacf + rb * maxlag);
+            if (!stock) continue;
+            const double nn = static_cast<double>(n);
+            // kurtosis (StatsBase: population moments about the sample mean, minus 3).  The series is demeaned already;
+            // its residual mean (~1e-19) moves the moments by less than their last bit and is dropped.
+            {
+                const double c2 = F[0] / nn, c4 = s4 / nn;
+                out.kurt[rb * M + ser] = c4 / (c2 * c2) - 3.0;
             }
-#pragma unroll
-            for (int d = kFactLags - 1; d > 0; --d) xw[d] = xw[d - 1];
-            xw[0] = x;
-            if (j < kFactLags) head[j] = x;
-            if (stock && j >= W && qcap > 0) {
-                const double a = fabs(x);
-                if (nsel < qcap || a < sel[0]) fact_heap_insert(sel, nsel, qcap, a);
+            // pass 3: loss/gain counts
+            double q = 0.0;
+            if (n2 >= 1) {  // sorted a[qi], a[qi+1] = the two largest of the qi+2 smallest (the heap's root and its larger child)
+                double hi = sel[0], lo = sel[0];
+                if (qcap == qi + 2) {
+                    lo = sel[1];
+                    if (qcap > 2 && sel[2] > lo) lo = sel[2];
+                }
+                q = (qh == 0.0) ? lo : lo + qh * (hi - lo);
             }
-        });
-        // the sums leave their registers for the per-lag solves (local memory from here on)
-        double Fl[kFactLags + 1], Fyl[kFactLags + 1], tail[kFactLags];
-#pragma unroll
-        for (int d = 0; d <= kFactLags; ++d) { Fl[d] = F[d]; Fyl[d] = Fy[d]; }
-#pragma unroll
-        for (int d = 0; d < kFactLags; ++d) tail[d] = xw[d];
-        FactEdges ed;
-        fact_edges(ed, head, tail);
-        double *o1 = ser < M ? out.pacf + rb * maxlag * M + ser : out.mpacf + rb * maxlag;
-        double *o2 = ser < M ? out.volc + rb * maxlag * M + ser : out.mvolc + rb * maxlag;
-        const int ostride = ser < M ? M : 1;
-        for (int l = 1; l <= maxlag; ++l) o1[static_cast<long long>(l - 1) * ostride] = fact_pacf_lag(Fl, sx, ed, n, l);
-        for (int d = 0; d < kFactLags; ++d) { head[d] *= head[d]; tail[d] *= tail[d]; }
-        fact_edges(ed, head, tail);
-        for (int l = 1; l <= maxlag; ++l) o2[static_cast<long long>(l - 1) * ostride] = fact_pacf_lag(Fyl, F[0], ed, n, l);
-        if (!fs.vol) continue;
-        // kurtosis (StatsBase: population moments about the sample mean, minus 3).  The series is demeaned already;
-        // its residual mean (~1e-19) moves the moments by less than their last bit and is dropped.
-        {
-            const double nn = static_cast<double>(n), c2 = F[0] / nn, c4 = Fy[0] / nn;
-            out.kurt[rb * M + ser] = c4 / (c2 * c2) - 3.0;
+            int up = 0, down = 0;
+            fact_walk<false, 8>(p0, v0, fs.stride, n, [&](int j, double ret, double) {
+                const double x = ret - mean;
+                if (j >= W) { up += x > q; down += x < -q; }
+            });
+            out.lg[rb * M + ser] =
+                n2 >= 1 ? static_cast<double>(down) / static_cast<double>(up) : __longlong_as_double(0x7ff8000000000000LL);
+            // cor(volume, |x|) from the raw sums of pass 2: sum (v - mv)^2 = svv - sv^2 / n, sum (|x| - ma)^2 = F_0 - sabs^2 / n,
+            // sum (v - mv)(|x| - ma) = sva - sv sabs / n.  None of the three cancels badly: volumes are sparse spikes
+            // (mean^2 << mean square), |x| has mean^2 / mean square ~ 2 / pi, and the error of the cross term is
+            // ~1e-16 (mv / sd v)(ma / sd |x|) of the normaliser.  A constant volume series (the reference's NaN: no trade
+            // ever touched the stock) must not turn into rounding noise: below n eps of its raw sum the centred sum is 0.
+            double xx = svv - sv * sv / nn;
+            if (!(xx > svv * nn * 2.3e-16)) xx = (xx != xx) ? xx : 0.0;
+            const double yy = F[0] - sabs * sabs / nn, xy = sva - sv * sabs / nn;
+            const double mx = xx > yy ? xx : yy, mn = xx > yy ? yy : xx;
+            double c = xy / mx / sqrt(mn / mx);
+            if (c > 1.0) c = 1.0; else if (c < -1.0) c = -1.0;
+            out.corr[rb * M + ser] = c;
         }
-        // pass 3: loss/gain counts
-        double q = 0.0;
-        if (n2 >= 1) {  // sorted a[qi], a[qi+1] = the two largest of the qi+2 smallest (the heap's root and its larger child)
-            double hi = sel[0], lo = sel[0];
-            if (qcap == qi + 2) {
-                lo = sel[1];
-                if (qcap > 2 && sel[2] > lo) lo = sel[2];
-            }
-            q = (qh == 0.0) ? lo : lo + qh * (hi - lo);
-        }
-        int up = 0, down = 0;
-        fact_walk<false, 8>(p0, v0, fs.stride, n, [&](int j, double ret, double) {
-            const double x = ret - mean;
-            if (j >= W) { up += x > q; down += x < -q; }
-        });
-        // cor(volume, |x|) from the raw sums of pass 2: sum (v - mv)^2 = svv - sv^2 / n, sum (|x| - ma)^2 = F_0 - sabs^2 / n,
-        // sum (v - mv)(|x| - ma) = sva - sv sabs / n.  None of the three cancels badly: volumes are sparse spikes
-        // (mean^2 << mean square), |x| has mean^2 / mean square ~ 2 / pi, and the error of the cross term is
-        // ~1e-16 (mv / sd v)(ma / sd |x|) of the normaliser.  A constant volume series (the reference's NaN: no trade
-        // ever touched the stock) must not turn into rounding noise: below n eps of its raw sum the centred sum is 0.
-        const double nn = static_cast<double>(n);
-        double xx = svv - sv * sv / nn;
-        if (!(xx > svv * nn * 2.3e-16)) xx = (xx != xx) ? xx : 0.0;
-        const double yy = F[0] - sabs * sabs / nn, xy = sva - sv * sabs / nn;
-        out.lg[rb * M + ser] =
-            n2 >= 1 ? static_cast<double>(down) / static_cast<double>(up) : __longlong_as_double(0x7ff8000000000000LL);
-        const double mx = xx > yy ? xx : yy, mn = xx > yy ? yy : xx;
-        double c = xy / mx / sqrt(mn / mx);
-        if (c > 1.0) c = 1.0; else if (c < -1.0) c = -1.0;
-        out.corr[rb * M + ser] = c;
     }
 }
 
@@ -302,7 +317,8 @@ cudaError_t facts_launch(const DevState &d, cudaStream_t st, long long rep_first
     o.lg = o.kurt + nr * M;
     o.corr = o.lg + nr * M;
     const dim3 grid(static_cast<unsigned>(n_reps), static_cast<unsigned>(std::min((d.M + 1 + kFactThreads - 1) / kFactThreads, 64)));
-    fsb_facts_kernel<<<grid, kFactThreads, 0, st>>>(d, rep_first, maxlag, pct, o);
+    fsb_facts_kernel<0><<<grid, kFactThreads, 0, st>>>(d, rep_first, maxlag, pct, o);
+    fsb_facts_kernel<1><<<grid, kFactThreads, 0, st>>>(d, rep_first, maxlag, pct, o);
     return cudaGetLastError();
 }
 

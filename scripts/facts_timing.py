@@ -42,10 +42,11 @@ with fsb.Engine(p, a.reps, keep_history=True) as eng:
     M, T, W = p.bigm, p.bigt, p.perfwindow[-1]
     n = T - W - 1
     hist_bytes = a.reps * (2 * M + 1) * n * 8  # price + volume + market columns the facts read, once
+    read_bytes = a.reps * (5 * (M + 1) + M) * n * 8  # what the two launches read: five walks over prices / market, one over volume
     out = dict(what="fsb_stylised_facts, default Params shape", replications=a.reps, run_s=t_run, facts_ms=best * 1e3, facts_kernel_ms=kbest * 1e3,
-               kernel_gbps_three_passes=3 * hist_bytes / kbest / 1e9,
+               kernel_read_bytes=read_bytes, kernel_gbps=read_bytes / kbest / 1e9,
                facts_us_per_replication=best / a.reps * 1e6, history_bytes_once=hist_bytes,
-               history_gbps_single_read=hist_bytes / best / 1e9, passes_over_history=3,
+               
                download_state_ms_per_replication=t_dl * 1e3,
                error_replications=int((eng.rep_status() != 0).sum()),
                finite_kurtoses=float((abs(f["stockkurtoses"]) < 1e300).mean()),
