@@ -971,35 +971,56 @@ extern "C" int32_t fsb_stylised_facts(fsb_engine *e, int64_t rep_first, int64_t 
     if (n2 >= 1 && static_cast<int>(static_cast<double>(n2 - 1) * (returnspctile / 100.0)) + 2 > facts_max_sel())
         return fail(FSB_ERR_BAD_PARAMS, "percentile %g of %d returns needs more than the %d order statistics a thread keeps",
                     returnspctile, n2, facts_max_sel());
-    // the kernel writes the seven arrays in the caller's layouts; each goes straight to the caller's memory
+    // The kernels write the seven arrays in the caller's layouts and each goes straight to the caller's memory.
+    // Replications go in chunks through two device buffers: a copy into pageable host memory blocks the host, so
+    // the kernels of chunk c+1 are launched (engine stream) before the copies of chunk c start (a batch stream).
     const size_t per_rep = static_cast<size_t>(facts_doubles_per_rep(M, maxlag));
-    const int64_t chunk = std::min<int64_t>(n_reps, 16384);
-    double *dev = nullptr;
-    CU(cudaMalloc(&dev, per_rep * chunk * 8));
-    int32_t rc = FSB_OK;
-    e->last_facts_ms = 0.0;
-    for (int64_t c0 = 0; c0 < n_reps && rc == FSB_OK; c0 += chunk) {
-        const int64_t nc = std::min(chunk, n_reps - c0);
-        cudaError_t ce = cudaEventRecord(e->ev0, e->stream);
-        if (ce == cudaSuccess) ce = facts_launch(d, e->stream, rep_first + c0, static_cast<int>(nc), maxlag, returnspctile, dev);
-        if (ce == cudaSuccess) ce = cudaEventRecord(e->ev1, e->stream);
-        const double *src = dev;
+    // 296 replications = 592 CTAs = one wave of 4 CTAs per SM; measured at 2048 replications (wall / sum of kernel
+    // times, ms): 296: 31.3 / 25.6, 592: 33.3 / 23.9, 1024: 36.2 / 21.5, one chunk: 45.3 / 19.9
+    const char *ck = getenv("FSB_FACTS_CHUNK");  // measurement knob
+    const int64_t chunk = std::min<int64_t>(n_reps, ck && atoll(ck) > 0 ? atoll(ck) : 296);
+    const int64_t n_chunks = (n_reps + chunk - 1) / chunk;
+    cudaStream_t cs = e->bstream.empty() ? e->stream : e->bstream[0];
+    double *dev[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev(static_cast<size_t>(2 * n_chunks), nullptr);
+    cudaError_t ce = cudaMalloc(&dev[0], per_rep * chunk * 8);
+    if (ce == cudaSuccess && n_chunks > 1) ce = cudaMalloc(&dev[1], per_rep * chunk * 8);
+    for (size_t i = 0; i < ev.size() && ce == cudaSuccess; ++i) ce = cudaEventCreate(&ev[i]);
+    auto launch = [&](int64_t c) {
+        const int64_t c0 = c * chunk, nc = std::min(chunk, n_reps - c0);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev[2 * c], e->stream);
+        if (ce == cudaSuccess) ce = facts_launch(d, e->stream, rep_first + c0, static_cast<int>(nc), maxlag, returnspctile, dev[c & 1]);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev[2 * c + 1], e->stream);
+    };
+    if (ce == cudaSuccess) launch(0);
+    for (int64_t c = 0; c < n_chunks && ce == cudaSuccess; ++c) {
+        if (c + 1 < n_chunks) launch(c + 1);  // its buffer was read by the copies of chunk c-1, which have returned
+        const int64_t c0 = c * chunk, nc = std::min(chunk, n_reps - c0);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs, ev[2 * c + 1], 0);
+        const double *src = dev[c & 1];
         auto out = [&](double *dst, size_t per) {  // per: doubles per replication of this array
             if (dst && ce == cudaSuccess)
-                ce = cudaMemcpyAsync(dst + per * c0, src, per * nc * 8, cudaMemcpyDeviceToHost, e->stream);
+                ce = cudaMemcpyAsync(dst + per * c0, src, per * nc * 8, cudaMemcpyDeviceToHost, cs);
             src += per * nc;
         };
         const size_t lm = static_cast<size_t>(maxlag) * M;
         out(stock_pacf, lm); out(stock_volacluster, lm); out(market_pacf, maxlag); out(market_volacluster, maxlag);
         out(kurtoses, M); out(lossgain, M); out(corrs, M);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(cs);  // (pinned destinations would make the copies asynchronous)
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    e->last_facts_ms = 0.0;
+    for (int64_t c = 0; c < n_chunks && ce == cudaSuccess; ++c) {
         float ms = 0.f;
-        if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e->ev0, e->ev1);
-        if (ce != cudaSuccess) { rc = fail(FSB_ERR_CUDA, "stylised facts: %s", cudaGetErrorString(ce)); break; }
+        ce = cudaEventElapsedTime(&ms, ev[2 * c], ev[2 * c + 1]);
         e->last_facts_ms += ms;
     }
-    cudaFree(dev);
-    return rc;
+    if (ce != cudaSuccess) cudaDeviceSynchronize();  // nothing may still use the buffers freed below
+    for (cudaEvent_t x : ev) if (x) cudaEventDestroy(x);
+    cudaFree(dev[0]);
+    cudaFree(dev[1]);
+    if (ce != cudaSuccess) return fail(FSB_ERR_CUDA, "stylised facts: %s", cudaGetErrorString(ce));
+    return FSB_OK;
 }
 
 extern "C" int32_t fsb_last_facts_timing(fsb_engine *e, double *kernel_ms)
