@@ -10,8 +10,8 @@
 // histories are [t][asset], asset fastest, and every load is coalesced.  Two launches, one per role:
 // <0> the series' own statistics in three walks over the prices and one over the volume -- (1) the mean
 // return, (2) lagged products of x, moments, the volume sums and the order statistics the percentile
-// needs, (3) up/down counts against the percentile; <1> volatility clustering -- the mean, then the
-// lagged products of x^2.
+// needs, (3) up/down counts against the percentile; <1> volatility clustering -- the lagged
+// products of x^2 (the mean return comes from <0>).
 //
 // PACF by regression as StatsBase v0.30.0 does it (per lag l: OLS of x[i] on [1, x[i-1..i-l]],
 // i = l+1..n, through a factorisation of X'X) -- but the (l+1)^2 sums of every lag are derived
@@ -33,6 +33,7 @@ struct FactOut {  // device arrays in the layouts of include/fsb.h, indexed from
     double *pacf, *volc;    // [n_reps][maxlag][M]
     double *mpacf, *mvolc;  // [n_reps][maxlag]
     double *kurt, *lg, *corr;  // [n_reps][M]
+    double *mean;              // [n_reps][M + 1] scratch: the mean returns, launch <0> -> launch <1>
 };
 
 struct FactSeries {  // where a thread's series lives
@@ -104,9 +105,8 @@ __device__ __noinline__ double fact_pacf_lag(const double *F, double S, const Fa
     return rhs[dm - 1] / dlast;
 }
 
-// Keeps the qcap smallest values seen so far in a max-heap (the percentile needs its top two).  Out of line: the
-// walk that calls it is unrolled, and most days no value of a lane qualifies.
-__device__ __noinline__ void fact_heap_insert(double *sel, int &nsel, int qcap, double a)
+// Keeps the qcap smallest values seen so far in a max-heap (the percentile needs its top two).
+__device__ __forceinline__ void fact_heap_insert(double *sel, int &nsel, int qcap, double a)
 {
     if (nsel < qcap) {  // sift up
         int k = nsel++;
@@ -134,6 +134,17 @@ __device__ __noinline__ void fact_heap_insert(double *sel, int &nsel, int qcap, 
         }
         sel[k] = a;
     }
+}
+
+// Empties a lane's candidate buffer into its heap; a candidate may have been overtaken since it was staged.
+constexpr int kFactStage = 8;
+__device__ __noinline__ void fact_heap_flush(double *sel, int &nsel, int qcap, const double *stg, int &nstg)
+{
+    for (int i = 0; i < nstg; ++i) {
+        const double a = stg[i];
+        if (nsel < qcap || a < sel[0]) fact_heap_insert(sel, nsel, qcap, a);
+    }
+    nstg = 0;
 }
 
 // Walks a series through time: fn(j, return j, volume j) for j = 0..n-1.  A thread's loads are one per day and
@@ -204,10 +215,16 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
         // one instantiation of the walk serves every series
         const double *v0 = fs.vol ? fs.vol + static_cast<long long>(W + 1) * fs.stride : p0;
         const int ostride = ser < M ? M : 1;
-        // pass 1: the mean return
-        double sr = 0.0;
-        fact_walk<false, 8>(p0, v0, fs.stride, n, [&](int, double ret, double) { sr += ret; });
-        const double mean = sr / static_cast<double>(n);
+        // pass 1: the mean return (launch <0> walks for it and leaves it for launch <1>, which follows on the same stream)
+        double mean;
+        if constexpr (kRole == 0) {
+            double sr = 0.0;
+            fact_walk<false, 8>(p0, v0, fs.stride, n, [&](int, double ret, double) { sr += ret; });
+            mean = sr / static_cast<double>(n);
+            out.mean[rb * nser + ser] = mean;
+        } else {
+            mean = out.mean[rb * nser + ser];
+        }
         // pass 2: the 11 full-range lagged sums of z (x or y) with a window of the last 10 z, and the first 10 z
         double F[kFactLags + 1], zw[kFactLags], head[kFactLags];
 #pragma unroll
@@ -244,7 +261,8 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
             solve(ser < M ? out.volc + rb * maxlag * M + ser : out.mvolc + rb * maxlag);
         } else {
             // ... plus the fourth moment, sum |x|, the raw volume sums and the order statistics of |x| the percentile needs
-            double sel[kFactSel];
+            double sel[kFactSel], stg[kFactStage];
+            int nstg = 0;
             double s4 = 0.0, sabs = 0.0, sv = 0.0, svv = 0.0, sva = 0.0;
             int nsel = 0;
             const bool stock = fs.vol != nullptr;
@@ -256,8 +274,15 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
                 svv += v * v;
                 sva += v * a;
                 lagged(j, x);
-                if (stock && j >= W && qcap > 0 && (nsel < qcap || a < sel[0])) fact_heap_insert(sel, nsel, qcap, a);
+                // Candidates wait in a small per-lane buffer and all lanes of the warp empty theirs together, when the first
+                // one is full: inserted one by one the 32 lanes qualify on different days, and the warp would run the sift
+                // for one or two of them nearly every day.
+                if (stock && j >= W && qcap > 0) {
+                    if (nsel < qcap || a < sel[0]) stg[nstg++] = a;
+                    if (__any_sync(__activemask(), nstg == kFactStage)) fact_heap_flush(sel, nsel, qcap, stg, nstg);
+                }
             });
+            fact_heap_flush(sel, nsel, qcap, stg, nstg);
             solve(ser < M ? out.pacf + rb * maxlag * M + ser : out.mpacf + rb * maxlag);
             if (!stock) continue;
             const double nn = static_cast<double>(n);
@@ -304,7 +329,7 @@ fsb_facts_kernel(const DevState s, const long long rep_first, const int maxlag, 
 // facts_doubles_per_rep(M, maxlag) doubles per replication, in the order of FactOut
 int facts_max_lag() { return kFactLags; }
 int facts_max_sel() { return kFactSel; }
-long long facts_doubles_per_rep(int M, int maxlag) { return 2LL * maxlag * M + 2LL * maxlag + 3LL * M; }
+long long facts_doubles_per_rep(int M, int maxlag) { return 2LL * maxlag * M + 2LL * maxlag + 3LL * M + (M + 1); }
 cudaError_t facts_launch(const DevState &d, cudaStream_t st, long long rep_first, int n_reps, int maxlag, double pct, double *base)
 {
     const long long M = d.M, nr = n_reps;
@@ -316,6 +341,7 @@ cudaError_t facts_launch(const DevState &d, cudaStream_t st, long long rep_first
     o.kurt = o.mvolc + nr * maxlag;
     o.lg = o.kurt + nr * M;
     o.corr = o.lg + nr * M;
+    o.mean = o.corr + nr * M;
     const dim3 grid(static_cast<unsigned>(n_reps), static_cast<unsigned>(std::min((d.M + 1 + kFactThreads - 1) / kFactThreads, 64)));
     fsb_facts_kernel<0><<<grid, kFactThreads, 0, st>>>(d, rep_first, maxlag, pct, o);
     fsb_facts_kernel<1><<<grid, kFactThreads, 0, st>>>(d, rep_first, maxlag, pct, o);
