@@ -976,7 +976,8 @@ extern "C" int32_t fsb_stylised_facts(fsb_engine *e, int64_t rep_first, int64_t 
     // the kernels of chunk c+1 are launched (engine stream) before the copies of chunk c start (a batch stream).
     const size_t per_rep = static_cast<size_t>(facts_doubles_per_rep(M, maxlag));
     // 296 replications = 592 CTAs = one wave of 4 CTAs per SM; measured at 2048 replications (wall / sum of kernel
-    // times, ms): 296: 31.3 / 25.6, 592: 33.3 / 23.9, 1024: 36.2 / 21.5, one chunk: 45.3 / 19.9
+    // times, ms; before the batched heap insertions): 296: 31.3 / 25.6, 592: 33.3 / 23.9, 1024: 36.2 / 21.5, one chunk:
+    // 45.3 / 19.9; with them 296: 29.2 / 17.6, one chunk: 41.1 / 15.5
     const char *ck = getenv("FSB_FACTS_CHUNK");  // measurement knob
     const int64_t chunk = std::min<int64_t>(n_reps, ck && atoll(ck) > 0 ? atoll(ck) : 296);
     const int64_t n_chunks = (n_reps + chunk - 1) / chunk;
