@@ -108,7 +108,7 @@ def assert_facts_close(got, ref):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("M,T,W,pct,maxlag", [(7, 200, 20, 5, 10), (300, 160, 5, 50, 3), (5, 90, 1, 0, 10),
-                                                (4, 120, 10, 100, 7)])
+                                                (4, 120, 10, 100, 7), (1100, 70, 3, 30, 2)])
 def test_device_facts_of_uploaded_histories(fsb, orc, M, T, W, pct, maxlag):
     """Func.calc_stylisedfacts on arrays: heavy-tailed synthetic histories, every stock trades."""
     mk, sv, vo = synthetic_history(np.random.default_rng(M + T), M, T)
