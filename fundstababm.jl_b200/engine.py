@@ -203,14 +203,22 @@ class Engine:
         L.check(L.lib().fsb_download_trace(self._h, rep, None, None, None, recs.ctypes.data, C.byref(n)))
         return dict(nav_open=nav, p_sell=ps, p_resp=pr, events=recs[: n.value])
 
-    def stylised_facts(self, rep_first=0, n_reps=None, maxlag=10, returnspctile=5):
+    def stylised_facts(self, rep_first=0, n_reps=None, maxlag=10, returnspctile=5, out=None):
         """Func.calc_stylisedfacts (functions.jl:604-648) on the device; arrays keyed by the reference's names,
-        leading axis = replication."""
+        leading axis = replication.  ``out``: the dict a previous call with the same shape returned -- its arrays
+        are filled again (a sweep loop saves the page faults of 46 KB of fresh result memory per replication)."""
         n = self.n_reps - rep_first if n_reps is None else n_reps
         M = self.M
-        o = dict(stockpacf=np.zeros((n, maxlag, M)), marketpacf=np.zeros((n, maxlag)),
-                 stockvolacluster=np.zeros((n, maxlag, M)), marketvolacluster=np.zeros((n, maxlag)),
-                 stockkurtoses=np.zeros((n, M)), lossgainratios=np.zeros((n, M)), corrs=np.zeros((n, M)))
+        if out is None:
+            o = dict(stockpacf=np.zeros((n, maxlag, M)), marketpacf=np.zeros((n, maxlag)),
+                     stockvolacluster=np.zeros((n, maxlag, M)), marketvolacluster=np.zeros((n, maxlag)),
+                     stockkurtoses=np.zeros((n, M)), lossgainratios=np.zeros((n, M)), corrs=np.zeros((n, M)))
+        else:
+            o = dict(out)
+            for k in ("stockpacf", "stockvolacluster"):
+                o[k] = o[k].transpose(0, 2, 1)  # back to the ABI's [rep][lag][stock]
+            if o["stockpacf"].shape != (n, maxlag, M) or not all(v.flags["C_CONTIGUOUS"] for v in o.values()):
+                raise ValueError("out does not come from a stylised_facts call of the same shape")
         L.check(L.lib().fsb_stylised_facts(self._h, rep_first, n, maxlag, float(returnspctile), *[o[k].ctypes.data for k in (
             "stockpacf", "marketpacf", "stockvolacluster", "marketvolacluster", "stockkurtoses", "lossgainratios",
             "corrs")]))

@@ -137,6 +137,10 @@ def test_device_facts_after_a_run(fsb, orc):
         eng.run(selector="probabilistic")
         got = eng.stylised_facts(maxlag=10, returnspctile=5)
         sub = eng.stylised_facts(3, 2, maxlag=4, returnspctile=20)
+        again = eng.stylised_facts(maxlag=10, returnspctile=5, out={k: np.full_like(v, 7.0) for k, v in got.items()})
+        assert all(H.eq(again[k], got[k]) for k in got)            # result arrays of a previous call can be reused
+        with pytest.raises(ValueError):
+            eng.stylised_facts(maxlag=9, out=got)
         for r in range(R):
             w = H.oracle_world(orc, params, SEED, r, trace=False)
             w.modelrun(selector="probabilistic")
