@@ -32,6 +32,18 @@ def test_library_exports_every_declared_symbol(fsb):
     assert os.path.dirname(fsb._lib.so_path()).endswith(os.path.join("fundstababm.jl_b200", "csrc"))
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/fsb.h compiles as C99 (no C++ or CUDA types in the signatures) and a C
+    translation unit can name every declared entry point."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    calls = "\n".join(f"    p[{i}] = (void *){n};" for i, n in enumerate(_declared_functions()))
+    src.write_text('#include "fsb.h"\nint main(void) {\n    void *p[64];\n' + calls + "\n    return p[0] == 0;\n}\n")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Wno-pedantic", "-fsyntax-only",
+                          "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
 def test_tape_key_layout(fsb):
     lib = fsb._lib.lib()
     assert lib.fsb_tape_key(3, 1234, 17, 5) == (3 << 56) | (1234 << 32) | (17 << 16) | 5
