@@ -86,7 +86,8 @@ function initialise(market, stocks, investors, funds, params; seed=0, rep=0, dev
 end
 
 "Replacement for Func.modelrun (src/functions.jl:446-491); returns the log as a NamedTuple of columns (:452-456)."
-function modelrun(market, stocks, investors, funds, params, fundselector="bestperformer"; seed=0, rep=0, device=0)
+function modelrun(market, stocks, investors, funds, params, fundselector="bestperformer"; seed=0, rep=0, device=0,
+                  stylefacts=nothing)
     haskey(SELECTORS, fundselector) || error("Please specify a valid fund selection method in reinvest!")  # Q9
     e = Engine(params; repoffset=rep, device=device)
     upload!(e, market, stocks, investors, funds)
@@ -104,6 +105,9 @@ function modelrun(market, stocks, investors, funds, params, fundselector="bestpe
     check(ccall((:fsb_download_log, LIB), Int32,
         (Ptr{Cvoid}, Int64, Ref{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
         e.handle, 0, n, liquidated, replacedby, initialsize, liquidity, failtime, ninvestors, nstocks))
+    # `stylefacts = Ref{Any}()`: receives calc_stylisedfacts of the finished run, computed from the histories
+    # still on the device (src/runmodel.jl:47), before the engine is released
+    stylefacts === nothing || (stylefacts[] = stylisedfacts(e, params))
     finalize(e)
     # wrap with DataFrame(...) where DataFrames is loaded: logisticregression (:846-856) and
     # plot_liquidationcounts (:832) read exactly these column names
@@ -112,7 +116,8 @@ function modelrun(market, stocks, investors, funds, params, fundselector="bestpe
 end
 
 # Func.calc_stylisedfacts (src/functions.jl:604-648; called at src/runmodel.jl:47) from the histories an
-# engine holds on the device after a run: only the per-stock vectors cross the host link.  Returns the
+# engine holds on the device after a run (modelrun's `stylefacts` keyword calls it before releasing its
+# engine): only the per-stock vectors cross the host link.  Returns the
 # array-valued entries of the reference's result tuple; the z-tests / KS test (:629-641) run on them in
 # Julia as before.
 function stylisedfacts(e::Engine, params; rep=0, maxlag=10, returnspctile=5)
