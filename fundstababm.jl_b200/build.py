@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libfsb_b200.so")
 SOURCES = ["fsb_abi.cu", "fsb_step_big.cu", "fsb_facts.cu"]  # (the second one: the same step kernels built for big shapes)
-HEADERS = ["fsb_device.cuh", "fsb_state.h", "fsb_step.cuh", "fsb_aux.cuh", "../../include/fsb.h"]
+HEADERS = ["fsb_device.cuh", "fsb_state.h", "fsb_step.cuh", "fsb_passx.cuh", "fsb_aux.cuh", "../../include/fsb.h"]
 
 # -fmad=false: no implicit FMA contraction -- every fused operation in the kernels is an explicit
 # fma(), which is what makes results bit-identical to the CPU oracle.
@@ -40,14 +40,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
         outs = [p.communicate()[0] for p in procs]
         ok = all(p.returncode == 0 for p in procs)
-        cmd = [nvcc, "-shared", "-o", SO] + objs + ["-ldl"]
+        # link to a temporary name and move it over SO only on success: a failed build must never leave (or
+        # silently keep) a stale library that tests and benches would then load
+        tmp = SO + ".tmp"
+        cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-ldl"]
         res = subprocess.run(cmd, capture_output=True, text=True) if ok else subprocess.CompletedProcess(cmd, 1, "", "compile failed")
-        res.stdout = "\n".join(outs) + res.stdout
+        log = " ".join(cmd) + "\n" + "\n".join(outs) + (res.stdout or "") + (res.stderr or "")
         for obj in objs:
             if os.path.exists(obj):
                 os.remove(obj)
         with open(os.path.join(CSRC, "build.log"), "w") as f:
-            f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+            f.write(log)
+        if res.returncode != 0 or not os.path.exists(tmp):
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            tail = "\n".join(l for l in log.splitlines() if "error" in l.lower() or "fatal" in l.lower())[-4000:] or log[-4000:]
+            raise RuntimeError(f"building {SO} failed (full log: {os.path.join(CSRC, 'build.log')}):\n{tail}")
+        os.replace(tmp, SO)
+        if verbose:
+            print(log)
     return SO
 
 

@@ -20,6 +20,7 @@
 #include "fsb_aux.cuh"
 #include "fsb_state.h"
 #include "fsb_step.cuh"
+#include "fsb_passx.cuh"
 
 namespace fsb {  // the FSB_BIG build of the step kernels (fsb_step_big.cu)
 __global__ void fsb_big_events1_kernel(const DevState s, const StepArgs a, const int launch_parity);
@@ -118,6 +119,8 @@ struct fsb_engine {
     int grid[3] = {0, 0, 0}, block = 256, block_pass = 256, smem_bytes[3] = {0, 0, 0}, init_smem = 0;
     int launch_parity = 0;
     bool fast = false;
+    bool usex = false;  // the pass reads the packed mirror (fsb_passx_kernel)
+    int grid_x = 0;
     bool log_built = false, state_set = false;
     int64_t t_done = 0;  // last simulated t (0 = none since init/upload)
     int64_t words_per_point = 0;
@@ -347,6 +350,22 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
                                                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return cleanup(fail(FSB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(cr)));
     }
+    // the packed mirror of the holdings (fsb_passx.cuh), default shape only.  OPT-IN (FSB_PASS_PACKED=1): measured on a B200 it is
+    // bit-identical to the dense TMA-fed pass and moves 0.4x its bytes, but runs at 0.77x its speed -- both are bound by
+    // shared-memory wavefronts, not by HBM -- so the dense pass stays the default.
+    e->usex = (d.K <= 256 && d.Mp == 256 && !d.big && d.kc <= kXKc && d.ring_stages > 0 && getenv("FSB_PASS_PACKED") && atoi(getenv("FSB_PASS_PACKED")) > 0);
+    d.xcols = kXCols;
+    if (const char *ev = getenv("FSB_XCOLS")) d.xcols = std::min(kXCols, std::max(4, (atoi(ev) / 4) * 4));
+    if (e->usex) {
+        A(X, R * ((d.K + 3) & ~3) * kXRowBytes); A(Xhdr, R * 256); A(xdirty, R * 8);
+        if (cudaMemset(d.xdirty, 0xff, R * 8 * sizeof(unsigned)) != cudaSuccess) return cleanup(fail(FSB_ERR_CUDA, "cannot mark the packed rows"));
+        int occx = 0;
+        if (cudaFuncSetAttribute(fsb_passx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(XShared))) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occx, fsb_passx_kernel, kXThreads, sizeof(XShared)) != cudaSuccess || occx < 1)
+            return cleanup(fail(FSB_ERR_CUDA, "fsb_passx_kernel cannot be resident"));
+        if (const char *ev = getenv("FSB_PASS_CTAS")) occx = std::min(occx, std::max(1, atoi(ev)));
+        e->grid_x = sms * occx;
+    }
     A(beta, R * d.Mp); A(vol, R * d.Mp); A(impact, R * d.Mp);
     if (d.keep_history) A(volume, R * d.T * d.Mp);
     A(market, R * d.mkt_len);
@@ -460,6 +479,7 @@ extern "C" int32_t fsb_init_device(fsb_engine *e, uint64_t seed)
     e->d.seed = seed;
     fsb_init_kernel<<<static_cast<unsigned>(e->d.R), 256, e->init_smem, e->stream>>>(e->d);
     CU(cudaGetLastError());
+    if (e->d.xdirty) CU(cudaMemsetAsync(e->d.xdirty, 0xff, static_cast<size_t>(e->d.R) * 8 * sizeof(unsigned), e->stream));  // every packed row is stale
     CU(cudaStreamSynchronize(e->stream));
     e->log_built = false;
     e->state_set = true;
@@ -578,6 +598,7 @@ extern "C" int32_t fsb_upload_state(fsb_engine *e, int64_t rep, const double *ma
 #undef UP
     CU(cudaMemset(d.nav_open + rep * K, 0, K * 8));
     CU(cudaMemset(d.nav_close + rep * K, 0, K * 8));
+    if (d.xdirty) CU(cudaMemset(d.xdirty + rep * 8, 0xff, 8 * sizeof(unsigned)));  // every packed row of this replication is stale
     (void)peak;
     e->log_built = false;
     e->state_set = true;
@@ -729,6 +750,7 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                     CU(cudaEventRecord(e->kev[e->kev_used], st));
                 }
                 if (d.big) fsb_big_pass_kernel<<<g2, e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity, e->tm_h);
+                else if (e->usex) fsb_passx_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid_x)), kXThreads, sizeof(XShared), st>>>(d, a, e->launch_parity);
                 else fsb_pass_kernel<<<g2, e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity, e->tm_h);
                 if (timed) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st)); e->kev_used += 2; }
                 if (ht && ht->nav_open_out)  // the NAVs of :460 are final after the pass: device -> host while events-2 runs

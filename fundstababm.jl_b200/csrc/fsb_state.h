@@ -39,6 +39,11 @@ struct DevState {
     unsigned long long seed;
     // fund x asset
     double *H;  // [R][K4][Mp] holdings, asset fastest; K4 = K rounded up to 4 (zero rows, never written)
+    // packed mirror of the holdings rows, read by fsb_passx_kernel (fsb_passx.cuh); null: the dense pass is used
+    unsigned char *X;     // [R][K4][kXRowBytes]
+    unsigned char *Xhdr;  // [R][256] chain length L of every packed row (255: row is read densely)
+    int xcols;            // staged columns per chunk of that kernel (kXCols; FSB_XCOLS=4..16 for tests)
+    unsigned *xdirty;     // [R][8] funds whose row changed after the day's pass (events-2); the next pass re-packs them
     // asset
     double *P;       // [R][hist_cols][Mp] price history (burn-in 1..W+1, then ring or full)
     double *beta, *vol, *impact;  // [R][Mp]

@@ -2054,6 +2054,10 @@ __device__ __forceinline__ void step_events2(const DevState &s, Ctx &c, const in
     }
 #endif
     phase_reinvest(s, t, ncash, flags);
+    if (s.xdirty) {  // the funds that received shares: their packed rows are stale (fsb_passx.cuh)
+        unsigned *xd = s.xdirty + c.r * 8;
+        for (int q = tid; q < nf; q += NT) xd[q] = static_cast<unsigned>(c.fsel_()[q]);
+    }
     phase_store_prices(s, t);
     FSB_MARK(15);
 }

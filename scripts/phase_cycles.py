@@ -17,7 +17,7 @@ NAMES = {0: "queue/idle between steps", 19: "T0a prefetch + market + stock move"
          7: "T3 respawn block", 8: "T4 cash list + horizons (to B7)", 9: "T4b column staging wait (to B8)",
          10: "T5 full pass (to B9)", 23: "T6a rank sort of own columns", 11: "T6b choice scans",
          12: "T6c wait for the other warps' choices", 13: "T7a injections (to B13)", 24: "T7b stakes loop",
-         25: "T8 buy orders + impact", 14: "T8b wait at B14", 15: "T9 final revalue + price store (to end)"}
+         25: "T8 buy orders + impact", 26: "X set-up (queue, hand_i, hdr)", 27: "X re-pack marked rows", 28: "X stage columns + row order", 29: "X rows: fill + dense + packed loop", 30: "X rows: wait for the stage", 31: "X rows: epilogue", 14: "T8b wait at B14", 15: "T9 final revalue + price store (to end)"}
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=8)
@@ -37,10 +37,10 @@ with fsb.Engine(p, a.reps, blocks_per_sm=a.blocks_per_sm) as eng:
     eng.sync()
     lib.fsb_debug_phase_cycles(eng.handle, out.ctypes.data, 1)
     ms, _, n = eng.last_run_timing()
-tot = float(out[:26].sum())
+tot = float(out[:32].sum())
 print(f"reps={a.reps} steps={a.steps} ms={ms:.3f} fund_steps_per_s={a.reps * p.bigk * a.steps / (ms * 1e-3):.4e}")
 per = a.reps * a.steps
-for i in range(26):
+for i in range(32):
     if out[i]:
         print(f"{100 * out[i] / tot:5.1f}%  {out[i] / per:9.0f} cycles/rep-step  [{i:2d}] {NAMES.get(i, '')}")
 print(f"total {tot / per:.0f} cycles per replication-step (thread 0 of the CTA)")

@@ -376,6 +376,8 @@ def test_error_behaviour(fsb):
 
 @pytest.mark.parametrize("env", [
     {"FSB_CMAX": "6"},                          # small column chunks: several holdings passes per day
+    {"FSB_PASS_PACKED": "1"},                   # the pass over the packed mirror of the holdings (fsb_passx.cuh, opt-in)
+    {"FSB_PASS_PACKED": "1", "FSB_XCOLS": "4"},  # ... with small column chunks: several passes over the packed rows per day
     {"FSB_NO_TMA": "1"},                        # register-ring pass (the path of non-default shapes) on the default shape
     {"FSB_NO_TMA": "1", "FSB_CMAX": "6"},
     {"FSB_BATCHES": "3"},                       # replication batches on separate streams
@@ -408,6 +410,26 @@ def test_schedule_variants_are_invisible(fsb, orc, env, monkeypatch):
     assert w.modelrun(t_last=t_last) == 0
     assert H.eq(want[0]["holdings"], w.holdings) and H.eq(want[0]["nav_close"], w.nav_close)
     w.close()
+
+
+@pytest.mark.parametrize("psize", [(1, 250), (120, 250), (1, 3)], ids=["mixed", "dense", "tiny"])
+def test_packed_mirror_dense_rows_and_repacking(fsb, orc, psize, monkeypatch):
+    """The opt-in pass over the packed mirror of the holdings (fsb_passx.cuh) at portfolio sizes the default Params never
+    produce: rows whose longest chain exceeds the packed capacity are read densely, respawned and reinvested rows are
+    re-packed.  Default K / M / N (the shape the packed pass supports), every array against the oracle."""
+    monkeypatch.setenv("FSB_PASS_PACKED", "1")
+    p = fsb.Params.default(bigt=150, portfsizerange=psize)
+    R = 3
+    with fsb.Engine(p, R, rep_offset=11, keep_history=True) as eng:
+        eng.init_device(SEED)
+        eng.run()
+        for r in range(R):
+            w = H.oracle_world(orc, p, SEED, 11 + r, trace=False)
+            assert w.modelrun() == 0
+            w.finalise_fund_value(p.bigt)
+            H.assert_state_equal(eng.download_state(r), w)
+            H.assert_log_equal(eng.download_log(r), w.log())
+            w.close()
 
 
 @pytest.mark.parametrize("shape", [
