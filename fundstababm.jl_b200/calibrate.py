@@ -109,7 +109,7 @@ def facts_means(moments):
     return res
 
 
-def calibrate(points, reps, *, seed=0, fundselector="probabilistic", device=0, t_last=None, steps_per_launch=1,
+def calibrate(points, reps, *, seed=0, fundselector="probabilistic", device=0, t_last=None,
               engine_kwargs=None, evaluation=None, maxlag=10, returnspctile=5):
     """Runs ``reps`` replications of every point and returns one statistics dict per point
     (identical on every rank).  ``evaluation="stylisedfacts"`` keeps the histories on the device
@@ -121,22 +121,40 @@ def calibrate(points, reps, *, seed=0, fundselector="probabilistic", device=0, t
     dist = _dist()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     total = len(points) * reps
+    if total < world:  # (decided identically on every rank, before any collective: no rank is left waiting in NCCL)
+        raise ValueError(f"{total} (point, replication) pairs cannot be sharded over {world} ranks")
     lo, hi = shard(total, rank, world)
-    if hi <= lo:
-        raise ValueError("fewer (point, replication) pairs than ranks")
     kw = dict(engine_kwargs or {})
     if evaluation:
         kw["keep_history"] = True
     with Engine(points, hi - lo, rep_offset=lo, reps_per_point=reps, device=device,
-                steps_per_launch=steps_per_launch, **kw) as eng:
+                **kw) as eng:
         if world > 1:
             eng.comm_init_rank(world, rank, share_unique_id(dist, device))
         eng.init_device(seed)
         try:
             eng.run(t_last=t_last, selector=fundselector)
-        except L.FsbError as ex:  # replications that hit Q6 stop and are counted in error_replications
+        except L.FsbError as ex:
             if ex.code != L.ERR_REPLICATION:
                 raise
+        # Replications the MODEL stops (Q6: functions.jl:282 would throw) are frozen and counted in
+        # error_replications.  Anything else is a capacity artefact of this engine (event / log rows) or a tape
+        # problem: it would bias the point's statistics silently, so it is an error (raise the capacities).
+        flags = eng.rep_status()
+        bad = flags & ~(L.REP_Q6_NO_ANCHOR | L.REP_TRACE_OVERFLOW)
+        nbad = np.array([int((bad != 0).sum())], dtype=np.int64)
+        if world > 1:
+            import torch
+            tb = torch.from_numpy(nbad)
+            if dist.get_backend() == "nccl":
+                tb = tb.cuda(device)
+            dist.all_reduce(tb)
+            nbad = tb.cpu().numpy()
+        if int(nbad[0]):
+            first = int(np.flatnonzero(bad)[0]) if bad.any() else -1
+            raise L.FsbError(L.ERR_REPLICATION, f"{int(nbad[0])} replications stopped on engine capacity / tape flags "
+                             f"(this rank: first local replication {first}, flags 0x{int(bad[first]) if first >= 0 else 0:x}); "
+                             "raise event_capacity / log_capacity in engine_kwargs")
         stats = eng.stats()
         if evaluation:
             facts = eng.stylised_facts(maxlag=maxlag, returnspctile=returnspctile)

@@ -172,6 +172,7 @@ extern "C" int64_t fsb_stats_words_per_point(const fsb_engine *e)
     return e ? e->words_per_point : 0;
 }
 extern "C" int64_t fsb_device_bytes(const fsb_engine *e) { return e ? e->device_bytes : 0; }
+extern "C" int64_t fsb_next_day(const fsb_engine *e) { return e ? (e->t_done > 0 ? e->t_done + 1 : e->d.W + 2) : 0; }
 
 extern "C" uint64_t fsb_tape_key(int32_t site, int64_t t, int64_t a, int64_t b)
 {
@@ -468,6 +469,10 @@ static int32_t check_rep(fsb_engine *e, int64_t rep)
     if (!e) return fail(FSB_ERR_BAD_PARAMS, "null engine");
     if (rep < 0 || rep >= e->d.R) return fail(FSB_ERR_RANGE, "replication %lld out of range [0,%lld)", (long long)rep, e->d.R);
     CU(cudaSetDevice(e->cfg.device));
+    // The engine's streams are non-blocking: the blocking copies of the upload / download / tape entry points (legacy
+    // default stream) do not wait for them.  Every such entry point starts here, so work enqueued by fsb_run_async has
+    // finished before state is read or overwritten (the batch streams are joined into e->stream by run_enqueue).
+    CU(cudaStreamSynchronize(e->stream));
     return FSB_OK;
 }
 
@@ -602,7 +607,7 @@ extern "C" int32_t fsb_upload_state(fsb_engine *e, int64_t rep, const double *ma
     (void)peak;
     e->log_built = false;
     e->state_set = true;
-    e->t_done = 0;
+    e->t_done = (t_last > d.W + 1) ? t_last : 0;  // (a state uploaded mid-run resumes after its last produced column)
     return FSB_OK;
 }
 
@@ -705,6 +710,11 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
     if (selector < 0 || selector > 3) return fail(FSB_ERR_BAD_SELECTOR, "Please specify a valid fund selection method (best, goodenough, probabilistic, random)");
     if (!e->state_set) return fail(FSB_ERR_BAD_STATE, "no state: call fsb_upload_state or fsb_init_device first");
     if (t_first < d.W + 2 || t_last > d.T) return fail(FSB_ERR_RANGE, "time range [%lld,%lld] outside [%d,%d]", (long long)t_first, (long long)t_last, d.W + 2, d.T);
+    {   // days are simulated once and in order: the price ring, the market slots and the log all assume it
+        const int64_t t_next = e->t_done > 0 ? e->t_done + 1 : d.W + 2;
+        if (t_last >= t_first && t_first != t_next)
+            return fail(FSB_ERR_RANGE, "the next day to simulate is %lld, not %lld (re-running or skipping days would corrupt the price ring)", (long long)t_next, (long long)t_first);
+    }
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaEventRecord(e->ev0, e->stream));
     e->last_launches = 0;
@@ -849,6 +859,7 @@ extern "C" int32_t fsb_rep_status(fsb_engine *e, int32_t *flags)
 {
     if (!e || !flags) return fail(FSB_ERR_BAD_PARAMS, "null argument");
     CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));  // (see check_rep)
     CU(cudaMemcpy(flags, e->d.err, e->d.R * 4, cudaMemcpyDeviceToHost));
     return FSB_OK;
 }

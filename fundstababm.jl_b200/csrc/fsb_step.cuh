@@ -1446,7 +1446,13 @@ static __device__ __noinline__ int phase_respawn(const int t, const int nd, cons
     {
         int eg = 0;
         for (int k = tid; k < K; k += NT) eg |= c.hz_()[k];
-        if (!__syncthreads_or(eg)) return 0;
+        if (!__syncthreads_or(eg)) {
+            // no fund to respawn, but the branch of :471-476 was entered (a fund's stakes sum to zero while its holdings
+            // are not all zero): the reference still calls trackvolume! with the sell orders once more (:474, Q3)
+            if (c.volume && !(flags & FSB_RUN_NO_VOLUME_QUIRK))
+                for (int m = tid; m < M; m += NT) c.volume[static_cast<long long>(t - 1) * Mp + m] -= c.sellsum_()[m];
+            return 0;
+        }
     }
     const int idle_cash = c.isc_()[I_IDLE];
     if (warp == 0) {

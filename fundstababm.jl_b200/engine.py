@@ -24,7 +24,7 @@ def _f(a, shape=None):
 
 class Engine:
     def __init__(self, points, n_reps=1, *, rep_offset=0, reps_per_point=0, device=0, keep_history=False,
-                 event_capacity=0, log_capacity=0, trace_capacity=0, steps_per_launch=1, block_threads=0,
+                 event_capacity=0, log_capacity=0, trace_capacity=0, block_threads=0,
                  blocks_per_sm=0):
         if not isinstance(points, (list, tuple)):
             points = [points]
@@ -36,7 +36,7 @@ class Engine:
         arr = (L.FsbParams * len(points))(*[L.make_params(p, self._keep) for p in points])
         cfg = L.FsbConfig(n_reps=n_reps, rep_offset=rep_offset, reps_per_point=reps_per_point, device=device,
                           keep_history=int(keep_history), event_capacity=event_capacity, log_capacity=log_capacity,
-                          trace_capacity=trace_capacity, steps_per_launch=steps_per_launch,
+                          trace_capacity=trace_capacity,
                           block_threads=block_threads, blocks_per_sm=blocks_per_sm)
         self._h = C.c_void_p()
         L.check(L.lib().fsb_create(arr, len(points), C.byref(cfg), C.byref(self._h)))
@@ -66,6 +66,10 @@ class Engine:
     @property
     def handle(self):
         return self._h
+
+    def next_day(self):
+        """The day the next run must start with (days are simulated once and in order)."""
+        return int(L.lib().fsb_next_day(self._h))
 
     def device_bytes(self):
         return L.lib().fsb_device_bytes(self._h)
@@ -119,12 +123,12 @@ class Engine:
     def run(self, t_first=None, t_last=None, selector="probabilistic", flags=0):
         if selector not in L.SEL:
             raise ValueError("Please specify a valid fund selection method in reinvest!")
-        t_first = self.t_first_default if t_first is None else t_first
+        t_first = self.next_day() if t_first is None else t_first
         t_last = self.T if t_last is None else t_last
         L.check(L.lib().fsb_run(self._h, t_first, t_last, L.SEL[selector], flags))
 
     def run_async(self, t_first=None, t_last=None, selector="probabilistic", flags=0):
-        t_first = self.t_first_default if t_first is None else t_first
+        t_first = self.next_day() if t_first is None else t_first
         t_last = self.T if t_last is None else t_last
         L.check(L.lib().fsb_run_async(self._h, t_first, t_last, L.SEL[selector], flags))
 

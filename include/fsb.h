@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FSB_VERSION 100 /* 0.1.0 */
+#define FSB_VERSION 200 /* 0.2.0: fsb_config lost steps_per_launch; days must be run in order */
 
 /* ---- status codes ---------------------------------------------------------------------- */
 enum {
@@ -91,8 +91,6 @@ typedef struct fsb_config {
     int32_t event_capacity; /* max reviewers / orders per replication-step; 0 = auto            */
     int32_t log_capacity;   /* liquidation-log rows per replication; 0 = auto (K + 1024)        */
     int32_t trace_capacity; /* trace records per traced replication; 0 = auto                   */
-    int32_t steps_per_launch; /* kept for ABI compatibility and ignored: a simulated day is always
-                                 launches draws, events-1, pass, choice, events-2: DESIGN.md 4    */
     int32_t block_threads;  /* 0 = auto                                                         */
     int32_t blocks_per_sm;  /* CTAs per SM of the holdings-pass kernel; 0 = auto                */
 } fsb_config;
@@ -155,13 +153,18 @@ int32_t fsb_set_trace(fsb_engine *e, int64_t rep, int32_t on);
 /* ---- the hot path: replaces the time loop of Func.modelrun, src/functions.jl:457-489 --------
  * runs t = t_first..t_last (inclusive, 1-based; first valid t is perf_hi+2) on every
  * replication; blocking (returns after the stream is synchronised).  Builds the liquidation log
- * (functions.jl:448-456) on the first call. */
+ * (functions.jl:448-456) on the first call.  Days are simulated once and in order: t_first must be
+ * the day after the last simulated one (perf_hi+2 after fsb_init_device / fsb_upload_state of an
+ * initialised state), else FSB_ERR_RANGE.  Returns FSB_ERR_REPLICATION when a replication raised
+ * an error flag (the run itself completed; the flagged replications are frozen). */
 int32_t fsb_run(fsb_engine *e, int64_t t_first, int64_t t_last, int32_t selector, int32_t flags);
 
 /* batched equivalence mode, one step per call: this step's shocks for ALL replications come from
  * host buffers (z_mkt[R], z_stock[R][M] stock-fastest, u_review[R][N] investor-fastest; pinned
  * memory makes the copies asynchronous), are copied to the device, the step runs, and the NAVs
- * V[:,t] of every fund (:460) are copied back into nav_open_out[R][K] (may be NULL).  Blocking. */
+ * V[:,t] of every fund (:460) are copied back into nav_open_out[R][K] (may be NULL).  Blocking.
+ * Like fsb_run_async + fsb_sync it does NOT scan the replication error flags (that would add a
+ * device-to-host copy per step): callers check fsb_rep_status when the sequence of steps is done. */
 int32_t fsb_run_step_hosttape(fsb_engine *e, int64_t t, int32_t selector, int32_t flags,
                               const double *z_mkt, const double *z_stock, const double *u_review,
                               double *nav_open_out);
@@ -222,10 +225,15 @@ int32_t fsb_last_run_timing(fsb_engine *e, double *total_ms, double *step_kernel
 int64_t fsb_last_pass_launches(const fsb_engine *e);
 /* device time (CUDA events on the engine's stream) of the kernel launches of the last fsb_stylised_facts */
 int32_t fsb_last_facts_timing(fsb_engine *e, double *kernel_ms);
-/* asynchronous variant used for overlapping several engines in one process */
+/* asynchronous variant used for overlapping several engines in one process.  Ordering contract: the
+ * engine's streams are non-blocking; every upload / download / tape / status entry point first waits for
+ * the work enqueued here, so it is safe to call them after fsb_run_async without fsb_sync.  fsb_sync
+ * does not scan the replication error flags (fsb_rep_status does). */
 int32_t fsb_run_async(fsb_engine *e, int64_t t_first, int64_t t_last, int32_t selector, int32_t flags);
 int32_t fsb_sync(fsb_engine *e);
 int64_t fsb_device_bytes(const fsb_engine *e);
+/* the day fsb_run / fsb_run_async / fsb_run_step_hosttape must start with next (perf_hi+2 on a fresh state) */
+int64_t fsb_next_day(const fsb_engine *e);
 /* RNG building blocks evaluated ON THE DEVICE, for cross-checks against the oracle */
 int32_t fsb_debug_draws(fsb_engine *e, uint64_t seed, uint32_t rep, uint32_t site, uint32_t a, uint32_t b,
                         uint32_t idx0, int32_t n, int32_t kind /*0 normal 1 uniform 2 discrete*/,

@@ -27,7 +27,7 @@ end
 struct FsbConfig
     n_reps::Int64; rep_offset::Int64; reps_per_point::Int64
     device::Int32; keep_history::Int32; event_capacity::Int32; log_capacity::Int32
-    trace_capacity::Int32; steps_per_launch::Int32; block_threads::Int32; blocks_per_sm::Int32
+    trace_capacity::Int32; block_threads::Int32; blocks_per_sm::Int32
 end
 
 const SELECTORS = Dict("best" => 0, "goodenough" => 1, "probabilistic" => 2, "random" => 3)
@@ -49,7 +49,7 @@ mutable struct Engine
                       params.invcaprange[1], params.invcaprange[2],
                       params.thresholdmean, params.thresholdstd,
                       first(params.portfsizerange), last(params.portfsizerange))
-        cfg = FsbConfig(nreps, repoffset, 0, device, keephistory ? 1 : 0, 0, 0, 0, 1, 0, 0)
+        cfg = FsbConfig(nreps, repoffset, 0, device, keephistory ? 1 : 0, 0, 0, 0, 0, 0)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         GC.@preserve imp vol check(ccall((:fsb_create, LIB), Int32,
             (Ref{FsbParams}, Int32, Ref{FsbConfig}, Ref{Ptr{Cvoid}}), p, 1, cfg, h))

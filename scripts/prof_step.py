@@ -10,7 +10,6 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=8)
 ap.add_argument("--t0", type=int, default=102)
-ap.add_argument("--steps-per-launch", type=int, default=1)
 ap.add_argument("--blocks-per-sm", type=int, default=0)
 ap.add_argument("--block-threads", type=int, default=0)
 ap.add_argument("--config4", action="store_true", help="BASELINE.json configs[3]: 2000 funds x 5000 assets, N = 8000, dense portfolios")
@@ -19,7 +18,7 @@ fsb = load_package()
 p = fsb.Params.default()
 if a.config4:
     p = fsb.Params.default(bigk=2000, bigm=5000, bign=8000, bigt=1101, portfsizerange=(2500, 5000))
-with fsb.Engine(p, a.reps, steps_per_launch=a.steps_per_launch, blocks_per_sm=a.blocks_per_sm,
+with fsb.Engine(p, a.reps, blocks_per_sm=a.blocks_per_sm,
                 block_threads=a.block_threads) as eng:
     eng.init_device(7)
     if a.t0 > 102:

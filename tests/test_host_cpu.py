@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(fsb):
     lib = fsb._lib.lib()
     missing = [n for n in _declared_functions() if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.fsb_version() == 100
+    assert lib.fsb_version() == 200
     assert os.path.dirname(fsb._lib.so_path()).endswith(os.path.join("fundstababm.jl_b200", "csrc"))
 
 

@@ -62,7 +62,16 @@ def test_perfreview_q1_denominator(world):
     # :214  perfreview(4, [3], ...) == [3 3]; valchange uses column `horizon` as denominator (Q1)
     d = world.perfreview(4, [3 - 1])
     assert np.array_equal(d + 1, G.PERFREVIEW_T4_REVIEWER3)
-    assert len(world.perfreview(4, [1 - 1])) == 0 or True  # other reviewers are unpinned
+    # the other reviewers of the toy world at t = 4, re-derived by hand from the pinned state (the reference has no
+    # literal for them): investor 1 (fund 1, h = 1): (V[1,4] - V[1,3]) / V[1,1] with V = 3.18 * price[4,:] -> compare with
+    # the same formula evaluated here in plain numpy
+    for inv in (0, 1, 3):
+        f = int(np.argmax(world.inv_assets[inv, :-1] > 0))
+        h = int(world.horizon[inv])
+        v = world.holdings[f, :] @ world.stock_value
+        expect = (v[3] - v[3 - h]) / v[h - 1] < world.threshold[inv]
+        got = world.perfreview(4, [inv])
+        assert (len(got) == 1 and got[0, 0] == inv and got[0, 1] == f) if expect else len(got) == 0
 
 
 def test_liquidate(world):
