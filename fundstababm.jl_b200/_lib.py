@@ -31,7 +31,7 @@ EXPORTS = (
     "fsb_version", "fsb_last_error", "fsb_create", "fsb_destroy", "fsb_upload_state", "fsb_init_device", "fsb_set_seed",
     "fsb_set_dense_tape", "fsb_set_event_tape", "fsb_tape_key", "fsb_set_trace", "fsb_run", "fsb_run_async", "fsb_run_step_hosttape",
     "fsb_sync", "fsb_download_state", "fsb_download_compact", "fsb_download_log", "fsb_download_trace",
-    "fsb_rep_status", "fsb_stylised_facts", "fsb_comm_unique_id", "fsb_comm_init_rank", "fsb_comm_init_all", "fsb_stats", "fsb_stats_all",
+    "fsb_rep_status", "fsb_stylised_facts", "fsb_comm_unique_id", "fsb_comm_init_rank", "fsb_comm_init_all", "fsb_stats", "fsb_stats_local", "fsb_stats_all",
     "fsb_stats_words_per_point", "fsb_last_run_timing", "fsb_last_pass_launches", "fsb_last_facts_timing", "fsb_device_bytes", "fsb_next_day", "fsb_debug_draws", "fsb_debug_dot",
     "fsb_debug_phase_cycles",
 )
@@ -109,6 +109,7 @@ def lib():
         L.fsb_comm_init_rank.argtypes = [vp, i32, i32, vp]
         L.fsb_comm_init_all.argtypes = [P(vp), i32]
         L.fsb_stats.argtypes = [vp, vp]
+        L.fsb_stats_local.argtypes = [vp, vp]
         L.fsb_stats_all.argtypes = [P(vp), i32, vp]
         L.fsb_stats_words_per_point.restype = i64
         L.fsb_stats_words_per_point.argtypes = [vp]

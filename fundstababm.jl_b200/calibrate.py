@@ -109,13 +109,62 @@ def facts_means(moments):
     return res
 
 
+def calibrate_single_process(points, reps, devices, *, seed=0, fundselector="probabilistic", t_last=None, engine_kwargs=None):
+    """The sweep driven by ONE process over several devices -- the form a Julia caller uses (src/runmodel.jl is one task;
+    julia/FundStabB200.jl `calibrate`): one engine per device on a contiguous shard of the flattened (point, replication)
+    index, the days enqueued asynchronously on every device, one grouped allreduce of the statistics (fsb_comm_init_all +
+    fsb_stats_all).  Same statistics as calibrate() under torch.distributed with len(devices) ranks."""
+    from .engine import comm_init_all, stats_all, decode_stats
+    total, world = len(points) * reps, len(devices)
+    if total < world:
+        raise ValueError(f"{total} (point, replication) pairs cannot be sharded over {world} devices")
+    engines = []
+    try:
+        for g, dev in enumerate(devices):
+            lo, hi = shard(total, g, world)
+            engines.append(Engine(points, hi - lo, rep_offset=lo, reps_per_point=reps, device=dev, **dict(engine_kwargs or {})))
+        if world > 1:
+            comm_init_all(engines)
+        for e in engines:
+            e.init_device(seed)
+        for e in engines:
+            e.run_async(t_last=t_last, selector=fundselector)
+        for e in engines:
+            e.sync()
+        for e in engines:  # capacity / tape flags are errors, the model's own Q6 stops are counted (see calibrate)
+            bad = e.rep_status() & ~(L.REP_Q6_NO_ANCHOR | L.REP_TRACE_OVERFLOW)
+            if bad.any():
+                raise L.FsbError(L.ERR_REPLICATION, f"device {e.device}: {int((bad != 0).sum())} replications stopped on engine capacity / tape flags")
+        raw = stats_all(engines)
+        return [decode_stats(row, engines[0].T) for row in raw]
+    finally:
+        for e in engines:
+            e.close()
+
+
+def history_bytes_per_replication(p):
+    """Device bytes a replication needs on top of the ring state when the engine keeps the price and volume histories
+    (what the stylised-facts kernels read): 2 x T x Mp doubles."""
+    mp = (p.bigm + 127) // 128 * 128
+    return 2 * 8 * p.bigt * mp
+
+
 def calibrate(points, reps, *, seed=0, fundselector="probabilistic", device=0, t_last=None,
-              engine_kwargs=None, evaluation=None, maxlag=10, returnspctile=5):
+              engine_kwargs=None, evaluation=None, maxlag=10, returnspctile=5, history_batch=None,
+              history_budget_bytes=32 << 30):
     """Runs ``reps`` replications of every point and returns one statistics dict per point
-    (identical on every rank).  ``evaluation="stylisedfacts"`` keeps the histories on the device
-    (5.4 MB per replication at the default shape), computes Func.calc_stylisedfacts of every replication
-    there and adds the per-point means over replications and stocks under ``"stylisedfacts"`` (float sums
-    over ranks: equal across world sizes to rounding, unlike the integer statistics)."""
+    (identical on every rank).
+
+    ``evaluation="stylisedfacts"`` adds the per-point means (over replications and stocks) of Func.calc_stylisedfacts
+    under ``"stylisedfacts"`` (float sums over ranks: equal across world sizes to rounding, unlike the integer
+    statistics).  The facts need every return of a series three times over (their mean, then the percentile of the
+    demeaned |returns|, then the counts against it: functions.jl:517-586), so they are computed by the history-based
+    device kernels (fsb_stylised_facts) -- but the histories (5.4 MB per replication at the default shape) never have to
+    exist for the whole ensemble at once: the rank's replications run in HISTORY BATCHES of ``history_batch``
+    replications (default: what fits ``history_budget_bytes`` of device memory), each a history-keeping engine that is
+    simulated, evaluated and released, while the integer statistics accumulate.  Replications are independent and the
+    Philox counters use global replication ids, so the results do not depend on the batch size: a 10^5-replication sweep
+    that only fits as a ring engine gets the same facts as ``keep_history`` would give."""
     if evaluation not in (None, "stylisedfacts"):
         raise ValueError(f"unknown evaluation {evaluation!r}")
     dist = _dist()
@@ -125,47 +174,70 @@ def calibrate(points, reps, *, seed=0, fundselector="probabilistic", device=0, t
         raise ValueError(f"{total} (point, replication) pairs cannot be sharded over {world} ranks")
     lo, hi = shard(total, rank, world)
     kw = dict(engine_kwargs or {})
-    if evaluation:
-        kw["keep_history"] = True
-    with Engine(points, hi - lo, rep_offset=lo, reps_per_point=reps, device=device,
-                **kw) as eng:
-        if world > 1:
-            eng.comm_init_rank(world, rank, share_unique_id(dist, device))
-        eng.init_device(seed)
+
+    def check_flags(eng):
+        # Replications the MODEL stops (Q6: functions.jl:282 would throw) are frozen and counted in
+        # error_replications.  Anything else is a capacity artefact of this engine (event / log rows) or a tape
+        # problem: it would bias the point's statistics silently, so it is an error (raise the capacities).
+        bad = eng.rep_status() & ~(L.REP_Q6_NO_ANCHOR | L.REP_TRACE_OVERFLOW)
+        return int((bad != 0).sum()), (int(np.flatnonzero(bad)[0]), int(bad[np.flatnonzero(bad)[0]])) if bad.any() else None
+
+    def allreduce(a):
+        if world == 1:
+            return a
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if dist.get_backend() == "nccl":
+            t = t.cuda(device)
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def run(eng):
         try:
             eng.run(t_last=t_last, selector=fundselector)
         except L.FsbError as ex:
             if ex.code != L.ERR_REPLICATION:
                 raise
-        # Replications the MODEL stops (Q6: functions.jl:282 would throw) are frozen and counted in
-        # error_replications.  Anything else is a capacity artefact of this engine (event / log rows) or a tape
-        # problem: it would bias the point's statistics silently, so it is an error (raise the capacities).
-        flags = eng.rep_status()
-        bad = flags & ~(L.REP_Q6_NO_ANCHOR | L.REP_TRACE_OVERFLOW)
-        nbad = np.array([int((bad != 0).sum())], dtype=np.int64)
-        if world > 1:
-            import torch
-            tb = torch.from_numpy(nbad)
-            if dist.get_backend() == "nccl":
-                tb = tb.cuda(device)
-            dist.all_reduce(tb)
-            nbad = tb.cpu().numpy()
-        if int(nbad[0]):
-            first = int(np.flatnonzero(bad)[0]) if bad.any() else -1
-            raise L.FsbError(L.ERR_REPLICATION, f"{int(nbad[0])} replications stopped on engine capacity / tape flags "
-                             f"(this rank: first local replication {first}, flags 0x{int(bad[first]) if first >= 0 else 0:x}); "
-                             "raise event_capacity / log_capacity in engine_kwargs")
-        stats = eng.stats()
-        if evaluation:
-            facts = eng.stylised_facts(maxlag=maxlag, returnspctile=returnspctile)
-            mom = facts_moments(facts, (lo + np.arange(hi - lo)) // reps, len(points))
+
+    def fail_on(nbad, first):
+        nbad = int(allreduce(np.array([nbad], dtype=np.int64))[0])
+        if nbad:
+            raise L.FsbError(L.ERR_REPLICATION, f"{nbad} replications stopped on engine capacity / tape flags"
+                             + (f" (this rank: first local replication {first[0]}, flags 0x{first[1]:x})" if first else "")
+                             + "; raise event_capacity / log_capacity in engine_kwargs")
+
+    if not evaluation:
+        with Engine(points, hi - lo, rep_offset=lo, reps_per_point=reps, device=device, **kw) as eng:
             if world > 1:
-                import torch
-                t = torch.from_numpy(mom)
-                if dist.get_backend() == "nccl":
-                    t = t.cuda(device)
-                dist.all_reduce(t)
-                mom = t.cpu().numpy()
-            for st, f in zip(stats, facts_means(mom)):
-                st["stylisedfacts"] = f
-        return stats
+                eng.comm_init_rank(world, rank, share_unique_id(dist, device))
+            eng.init_device(seed)
+            run(eng)
+            fail_on(*check_flags(eng))
+            return eng.stats()   # the single NCCL allreduce, inside the library
+
+    # ---- evaluation on the device, history batch by history batch ------------------------------------------------------
+    kw["keep_history"] = True
+    if history_batch is None:
+        history_batch = max(1, int(history_budget_bytes // (history_bytes_per_replication(points[0]) + (1 << 20))))
+    raw = mom = None
+    nbad, first, T = 0, None, points[0].bigt
+    for b_lo in range(lo, hi, history_batch):
+        b_hi = min(hi, b_lo + history_batch)
+        with Engine(points, b_hi - b_lo, rep_offset=b_lo, reps_per_point=reps, device=device, **kw) as eng:
+            eng.init_device(seed)
+            run(eng)
+            nb, fb = check_flags(eng)
+            nbad, first = nbad + nb, first or fb
+            r = eng.stats_raw(local=True).astype(np.int64)
+            facts = eng.stylised_facts(maxlag=maxlag, returnspctile=returnspctile)
+            m = facts_moments(facts, (b_lo + np.arange(b_hi - b_lo)) // reps, len(points))
+        raw = r if raw is None else raw + r
+        mom = m if mom is None else mom + m
+    fail_on(nbad, first)
+    raw = allreduce(raw)   # (the same words fsb_stats would have summed with its own allreduce)
+    mom = allreduce(mom)
+    from .engine import decode_stats
+    stats = [decode_stats(row.astype(np.uint64), T) for row in raw]
+    for st, f in zip(stats, facts_means(mom)):
+        st["stylisedfacts"] = f
+    return stats

@@ -1143,6 +1143,15 @@ extern "C" int32_t fsb_stats(fsb_engine *e, uint64_t *out)
     return FSB_OK;
 }
 
+extern "C" int32_t fsb_stats_local(fsb_engine *e, uint64_t *out)
+{
+    if (!e || !out) return fail(FSB_ERR_BAD_PARAMS, "null argument");
+    TRY(stats_local(e));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(out, e->stats_dev, static_cast<size_t>(e->d.n_points) * e->words_per_point * 8, cudaMemcpyDeviceToHost));
+    return FSB_OK;
+}
+
 extern "C" int32_t fsb_stats_all(fsb_engine **engines, int32_t n, uint64_t *out)
 {
     if (!engines || n < 1 || !out) return fail(FSB_ERR_BAD_PARAMS, "null argument");

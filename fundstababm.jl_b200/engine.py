@@ -42,7 +42,7 @@ class Engine:
         L.check(L.lib().fsb_create(arr, len(points), C.byref(cfg), C.byref(self._h)))
         p = self.params
         self.K, self.M, self.N, self.T, self.W = p.bigk, p.bigm, p.bign, p.bigt, p.perfwindow[-1]
-        self.n_reps, self.keep_history = n_reps, bool(keep_history)
+        self.n_reps, self.keep_history, self.device = n_reps, bool(keep_history), device
         self.t_first_default = self.W + 2
 
     # lifecycle ---------------------------------------------------------------------------------
@@ -240,10 +240,12 @@ class Engine:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         L.check(L.lib().fsb_comm_init_rank(self._h, n_ranks, rank, buf))
 
-    def stats_raw(self):
+    def stats_raw(self, local=False):
+        """Integer ensemble statistics per sweep point: summed over the ranks of the communicator (one ncclAllReduce), or
+        this engine's replications only (``local=True``, no collective)."""
         wpp = L.lib().fsb_stats_words_per_point(self._h)
         out = np.zeros((len(self.points), wpp), dtype=np.uint64)
-        L.check(L.lib().fsb_stats(self._h, out.ctypes.data))
+        L.check((L.lib().fsb_stats_local if local else L.lib().fsb_stats)(self._h, out.ctypes.data))
         return out
 
     def stats(self):
@@ -261,6 +263,24 @@ class Engine:
         out = C.c_double()
         L.check(L.lib().fsb_debug_dot(self._h, x.ctypes.data, y.ctypes.data, len(x), C.byref(out)))
         return out.value
+
+
+def comm_init_all(engines):
+    """ONE process driving several devices (what a Julia task calling the library does): one NCCL communicator over the
+    engines' devices (ncclCommInitAll)."""
+    arr = (C.c_void_p * len(engines))(*[e.handle for e in engines])
+    L.check(L.lib().fsb_comm_init_all(arr, len(engines)))
+
+
+def stats_all(engines):
+    """The per-point ensemble statistics summed over the engines of one process: a grouped ncclAllReduce, one call per
+    device (fsb_stats_all).  Returns the decoded statistics, one dict per sweep point."""
+    e0 = engines[0]
+    wpp = L.lib().fsb_stats_words_per_point(e0.handle)
+    out = np.zeros((len(e0.points), wpp), dtype=np.uint64)
+    arr = (C.c_void_p * len(engines))(*[e.handle for e in engines])
+    L.check(L.lib().fsb_stats_all(arr, len(engines), out.ctypes.data))
+    return out
 
 
 def comm_unique_id() -> bytes:

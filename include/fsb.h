@@ -213,6 +213,8 @@ int32_t fsb_comm_init_all(fsb_engine **engines, int32_t n);
 /* computes this engine's statistics on the device, sums them across the communicator (if any;
  * ncclAllReduce(sum, uint64) on the engine's stream) and copies n_points*words_per_point words */
 int32_t fsb_stats(fsb_engine *e, uint64_t *out);
+/* the same words for THIS engine's replications only: no collective (what fsb_stats sums over the ranks) */
+int32_t fsb_stats_local(fsb_engine *e, uint64_t *out);
 int32_t fsb_stats_all(fsb_engine **engines, int32_t n, uint64_t *out);
 
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------- */

@@ -136,4 +136,49 @@ function stylisedfacts(e::Engine, params; rep=0, maxlag=10, returnspctile=5)
             stockkurtoses=kurtoses, lossgainratios=lossgainratios, corrs=corrs)
 end
 
+# The sweep of src/calibrate.jl:1-30 from ONE Julia task over several devices: every (point, replication) pair is a
+# replication of an engine, engines hold contiguous shards of the flattened index (one per device), the days are enqueued
+# asynchronously on every device, and the integer ensemble statistics are summed by one grouped allreduce
+# (fsb_comm_init_all + fsb_stats_all).  Returns a (points x words) Matrix{UInt64}; layout: include/fsb.h "statistics".
+function calibrate(points::AbstractVector, reps::Integer; devices=[0], seed=0, fundselector="probabilistic")
+    haskey(SELECTORS, fundselector) || error("Please specify a valid fund selection method in reinvest!")
+    keep = Any[]
+    pods = map(points) do params
+        imp = collect(Float64, params.impactrange); vol = collect(Float64, params.stockvolrange)
+        push!(keep, imp, vol)
+        FsbParams(params.bigm, params.bign, params.bigt, params.bigk, params.marketstartval, params.drift, params.marketvol,
+                  pointer(imp), length(imp), params.betamean, params.betastd, params.stockstartval,
+                  pointer(vol), length(vol), params.reviewprobability, first(params.perfwindow), last(params.perfwindow),
+                  params.invcaprange[1], params.invcaprange[2], params.thresholdmean, params.thresholdstd,
+                  first(params.portfsizerange), last(params.portfsizerange))
+    end
+    total = length(points) * reps
+    ndev = length(devices)
+    total >= ndev || error("$total (point, replication) pairs cannot be sharded over $ndev devices")
+    handles = Ptr{Cvoid}[]
+    GC.@preserve keep pods try
+        for (g, dev) in enumerate(devices)
+            lo, hi = div(total * (g - 1), ndev), div(total * g, ndev)
+            cfg = FsbConfig(hi - lo, lo, reps, dev, 0, 0, 0, 0, 0, 0)
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:fsb_create, LIB), Int32, (Ptr{FsbParams}, Int32, Ref{FsbConfig}, Ref{Ptr{Cvoid}}), pods, length(pods), cfg, h))
+            push!(handles, h[])
+        end
+        ndev > 1 && check(ccall((:fsb_comm_init_all, LIB), Int32, (Ptr{Ptr{Cvoid}}, Int32), handles, ndev))
+        p1 = first(points)
+        for h in handles
+            check(ccall((:fsb_init_device, LIB), Int32, (Ptr{Cvoid}, UInt64), h, seed))
+            check(ccall((:fsb_run_async, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32, Int32),
+                        h, last(p1.perfwindow) + 2, p1.bigt, SELECTORS[fundselector], 0))
+        end
+        foreach(h -> check(ccall((:fsb_sync, LIB), Int32, (Ptr{Cvoid},), h)), handles)
+        words = ccall((:fsb_stats_words_per_point, LIB), Int64, (Ptr{Cvoid},), handles[1])
+        out = zeros(UInt64, words, length(points))
+        check(ccall((:fsb_stats_all, LIB), Int32, (Ptr{Ptr{Cvoid}}, Int32, Ptr{UInt64}), handles, ndev, out))
+        return permutedims(out)
+    finally
+        foreach(h -> ccall((:fsb_destroy, LIB), Int32, (Ptr{Cvoid},), h), handles)
+    end
+end
+
 end # module

@@ -391,6 +391,20 @@ static double draw_u_review(orc_world *w, int64_t t, int64_t n)
     return orc_draw_uniform(w->seed, w->rep, SITE_REVIEW, (uint32_t)t, 0, (uint32_t)n);
 }
 
+/* One day's exogenous draws of a batch of replications as the dense "host tape" of the engine's batched equivalence mode
+ * (fsb_run_step_hosttape): z_mkt[nreps], z_stock[nreps][M], u_review[nreps][N] -- exactly the values the draw helpers above
+ * produce for (seed, rep0 + i, t), i.e. what a recorder wrapped around functions.jl:15, :32, :149 would capture. */
+void orc_fill_step_tape(uint64_t seed, uint32_t rep0, int64_t nreps, int64_t t, int64_t M, int64_t N,
+                        double *z_mkt, double *z_stock, double *u_review)
+{
+    for (int64_t i = 0; i < nreps; ++i) {
+        const uint32_t rep = rep0 + (uint32_t)i;
+        z_mkt[i] = orc_draw_normal(seed, rep, SITE_MKT, (uint32_t)t, 0, 0);
+        for (int64_t m = 0; m < M; ++m) z_stock[i * M + m] = orc_draw_normal(seed, rep, SITE_STOCK, (uint32_t)t, 0, (uint32_t)m);
+        for (int64_t n = 0; n < N; ++n) u_review[i * N + n] = orc_draw_uniform(seed, rep, SITE_REVIEW, (uint32_t)t, 0, (uint32_t)n);
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * price functions
  * ---------------------------------------------------------------------------------------- */

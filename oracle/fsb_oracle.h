@@ -98,6 +98,9 @@ void orc_set_dense_tape(orc_world *w, const double *z_mkt, const double *z_stock
 /* ... and by a sparse event tape sorted by key = orc_tape_key(site,t,a,b) */
 void orc_set_event_tape(orc_world *w, const orc_tape_rec *recs, int64_t n);
 uint64_t orc_tape_key(int site, int64_t t, int64_t a, int64_t b);
+/* one day's exogenous draws of replications rep0 .. rep0+nreps-1 in the engine's host-tape layout */
+void orc_fill_step_tape(uint64_t seed, uint32_t rep0, int64_t nreps, int64_t t, int64_t M, int64_t N,
+                        double *z_mkt, double *z_stock, double *u_review);
 
 void orc_enable_trace(orc_world *w, int on);
 int64_t orc_trace_count(orc_world *w);

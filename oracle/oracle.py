@@ -70,6 +70,7 @@ def lib():
         L.orc_set_rng.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
         L.orc_set_dense_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_event_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.orc_fill_step_tape.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_tape_key.restype = C.c_uint64
         L.orc_tape_key.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64]
         L.orc_enable_trace.argtypes = [C.c_void_p, C.c_int]
@@ -327,6 +328,28 @@ class World:
         """Builds the initial liquidation log (functions.jl:448-456) without stepping."""
         t = self.params.perfwindow[-1] + 2
         lib().orc_modelrun(self._h, t, t - 1, 0, 0)
+
+
+def fill_step_tape(seed, rep0, t, z_mkt, z_stock, u_review, threads=1):
+    """One day's exogenous draws of replications rep0.. in the engine's host-tape layout (z_mkt[R], z_stock[R, M],
+    u_review[R, N], C-contiguous float64, filled in place); `threads` host threads share the replications."""
+    import threading
+    R, M = z_stock.shape
+    N = u_review.shape[1]
+    f = lib().orc_fill_step_tape
+
+    def work(lo, hi):
+        if hi > lo:
+            f(seed, rep0 + lo, hi - lo, t, M, N, z_mkt[lo:].ctypes.data, z_stock[lo:].ctypes.data, u_review[lo:].ctypes.data)
+
+    if threads <= 1:
+        work(0, R)
+        return
+    ths = [threading.Thread(target=work, args=((R * i) // threads, (R * (i + 1)) // threads)) for i in range(threads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
 
 
 # RNG building blocks -------------------------------------------------------------------------

@@ -368,6 +368,45 @@ def test_error_behaviour(fsb):
         assert ei.value.code == L.ERR_BAD_STATE
 
 
+def test_single_process_multi_gpu_statistics(fsb):
+    """fsb_comm_init_all + fsb_stats_all: ONE process, one engine per device (the path a Julia caller uses), against the
+    per-engine statistics and against a single engine holding all replications."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    cal = importlib.import_module(fsb.__name__ + ".calibrate")
+    eng_mod = importlib.import_module(fsb.__name__ + ".engine")
+    p = fsb.Params.default(bigt=130)
+    pts = cal.grid(p, thresholdstd=(0.02, 0.08))
+    reps, devices = 24, [0, 1]
+    got = cal.calibrate_single_process(pts, reps, devices, seed=SEED)
+    with fsb.Engine(pts, len(pts) * reps, reps_per_point=reps) as one:
+        one.init_device(SEED)
+        try:
+            one.run()
+        except fsb._lib.FsbError as ex:
+            assert ex.code == fsb._lib.ERR_REPLICATION
+        want = one.stats()
+    for a, b in zip(got, want):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    # and the collective against the sum of the engines' local statistics
+    total = len(pts) * reps
+    engines = [fsb.Engine(pts, total // 2, rep_offset=g * (total // 2), reps_per_point=reps, device=d) for g, d in enumerate(devices)]
+    try:
+        eng_mod.comm_init_all(engines)
+        for e in engines:
+            e.init_device(SEED)
+            e.run_async(t_last=120)
+        for e in engines:
+            e.sync()
+        local = sum(e.stats_raw(local=True).astype(np.int64) for e in engines)
+        assert np.array_equal(eng_mod.stats_all(engines).astype(np.int64), local)
+    finally:
+        for e in engines:
+            e.close()
+
+
 def test_stakeless_fund_with_holdings_keeps_the_volume_quirk(fsb, orc):
     """functions.jl:471-476 is entered whenever a fund's stakes sum to zero, also when respawn! then finds no all-zero
     holdings row (Q5): trackvolume! still subtracts the sell orders once more (:474, Q3).  Reached through an uploaded

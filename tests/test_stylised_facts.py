@@ -205,3 +205,27 @@ def test_calibrate_evaluates_stylised_facts(fsb):
         np.testing.assert_allclose(sf["marketpacf"], f["marketpacf"].mean(axis=0), rtol=1e-12)
         np.testing.assert_allclose(sf["stockpacf"], np.nanmean(f["stockpacf"], axis=(0, 1)), rtol=1e-12)
         assert sf["marketpacf"].shape == (5,)
+
+
+@pytest.mark.gpu
+def test_calibrate_history_batches_are_invisible(fsb):
+    """Stylised facts for ensembles that only fit as ring engines: calibrate evaluates the rank's
+    replications in history-keeping batches; the batch size changes neither the integer statistics nor (beyond the order
+    of a float sum) the facts, and both equal one history-keeping engine over all replications."""
+    base = fsb.Params.default(bigt=260)
+    pts = fsb.grid(base, thresholdstd=(0.03, 0.08))
+    reps = 10
+    one = fsb.calibrate(pts, reps, seed=SEED, evaluation="stylisedfacts", history_batch=2 * reps)   # a single batch
+    for hb in (3, 7):
+        got = fsb.calibrate(pts, reps, seed=SEED, evaluation="stylisedfacts", history_batch=hb)
+        for a, b in zip(got, one):
+            for k in a:
+                if k == "stylisedfacts":
+                    for kk in a[k]:
+                        np.testing.assert_allclose(a[k][kk], b[k][kk], rtol=1e-12, atol=1e-15, equal_nan=True, err_msg=kk)
+                else:
+                    assert H.eq(a[k], b[k]), k
+    plain = fsb.calibrate(pts, reps, seed=SEED)   # ring engine, the library's own allreduce path
+    for a, b in zip(one, plain):
+        for k in b:
+            assert H.eq(a[k], b[k]), k
