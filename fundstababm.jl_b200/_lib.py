@@ -32,7 +32,7 @@ EXPORTS = (
     "fsb_set_dense_tape", "fsb_set_event_tape", "fsb_tape_key", "fsb_set_trace", "fsb_run", "fsb_run_async", "fsb_run_step_hosttape",
     "fsb_sync", "fsb_download_state", "fsb_download_compact", "fsb_download_log", "fsb_download_trace",
     "fsb_rep_status", "fsb_stylised_facts", "fsb_comm_unique_id", "fsb_comm_init_rank", "fsb_comm_init_all", "fsb_stats", "fsb_stats_local", "fsb_stats_all",
-    "fsb_stats_words_per_point", "fsb_last_run_timing", "fsb_last_pass_launches", "fsb_last_facts_timing", "fsb_device_bytes", "fsb_next_day", "fsb_debug_draws", "fsb_debug_dot",
+    "fsb_stats_words_per_point", "fsb_last_run_timing", "fsb_last_pass_launches", "fsb_last_facts_timing", "fsb_device_bytes", "fsb_debug_redzones", "fsb_next_day", "fsb_debug_draws", "fsb_debug_dot",
     "fsb_debug_phase_cycles",
 )
 
@@ -119,6 +119,7 @@ def lib():
         L.fsb_last_pass_launches.argtypes = [vp]
         L.fsb_device_bytes.restype = i64
         L.fsb_device_bytes.argtypes = [vp]
+        L.fsb_debug_redzones.argtypes = [vp, P(i64), P(i64)]
         L.fsb_next_day.restype = i64
         L.fsb_next_day.argtypes = [vp]
         L.fsb_debug_draws.argtypes = [vp, u64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, i32, i32,

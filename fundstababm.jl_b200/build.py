@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libfsb_b200.so")
-SOURCES = ["fsb_abi.cu", "fsb_step_big.cu", "fsb_facts.cu"]  # (the second one: the same step kernels built for big shapes)
+SOURCES = ["fsb_abi.cu", "fsb_step_big.cu", "fsb_step_fixed.cu", "fsb_facts.cu"]  # (the second one: the same step kernels built for big shapes)
 HEADERS = ["fsb_device.cuh", "fsb_state.h", "fsb_step.cuh", "fsb_passx.cuh", "fsb_aux.cuh", "../../include/fsb.h"]
 
 # -fmad=false: no implicit FMA contraction -- every fused operation in the kernels is an explicit

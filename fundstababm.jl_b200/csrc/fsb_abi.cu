@@ -28,6 +28,13 @@ __global__ void fsb_big_pass_kernel(const DevState s, const StepArgs a, const in
 __global__ void fsb_big_events2_kernel(const DevState s, const StepArgs a, const int launch_parity);
 }  // namespace fsb
 
+namespace fsb {  // the FSB_FIXED build of the event kernels (fsb_step_fixed.cu): exactly the default Params shape
+__global__ void fsb_fix_events1_kernel(const DevState s, const StepArgs a, const int launch_parity);
+__global__ void fsb_fix_choice_kernel(const DevState s, const StepArgs a, const int launch_parity);
+__global__ void fsb_fix_events2_kernel(const DevState s, const StepArgs a, const int launch_parity);
+constexpr int kFixedK = 250, kFixedM = 250, kFixedN = 1000, kFixedCap = 80, kFixedSlots = 8, kFixedW = 100;  // == fsb_step.cuh under FSB_FIXED
+}  // namespace fsb
+
 namespace fsb {  // fsb_facts.cu
 int facts_max_lag();
 int facts_max_sel();
@@ -104,6 +111,10 @@ struct fsb_engine {
     fsb_config cfg{};
     std::vector<DevPoint> points;
     std::vector<void *> allocs;
+    // FSB_REDZONE=1 (debug): every device buffer sits between two guard bands filled with a pattern; fsb_debug_redzones
+    // counts the buffers whose bands were overwritten (compute-sanitizer is not available on every pool)
+    bool redzone = false;
+    std::vector<std::pair<unsigned char *, size_t>> zones;  // (user pointer, user bytes)
     int64_t device_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -120,6 +131,7 @@ struct fsb_engine {
     int launch_parity = 0;
     bool fast = false;
     bool usex = false;  // the pass reads the packed mirror (fsb_passx_kernel)
+    bool fixed = false; // the event / choice kernels come from the fixed-shape build (fsb_step_fixed.cu)
     int grid_x = 0;
     bool log_built = false, state_set = false;
     int64_t t_done = 0;  // last simulated t (0 = none since init/upload)
@@ -151,6 +163,19 @@ static int32_t dalloc(fsb_engine *e, T **out, size_t count, bool zero = true)
 {
     void *p = nullptr;
     const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    if (e->redzone) {
+        constexpr size_t kBand = 256;
+        const size_t padded = (bytes + 255) & ~static_cast<size_t>(255);
+        CU(cudaMalloc(&p, padded + 2 * kBand));
+        CU(cudaMemset(p, 0xA5, padded + 2 * kBand));
+        unsigned char *u = static_cast<unsigned char *>(p) + kBand;
+        if (zero) CU(cudaMemset(u, 0, bytes));
+        e->allocs.push_back(p);
+        e->zones.emplace_back(u, bytes);
+        e->device_bytes += static_cast<int64_t>(padded + 2 * kBand);
+        *out = reinterpret_cast<T *>(u);
+        return FSB_OK;
+    }
     CU(cudaMalloc(&p, bytes));
     if (zero) CU(cudaMemset(p, 0, bytes));
     e->allocs.push_back(p);
@@ -213,6 +238,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     CU(cudaSetDevice(cfg->device));
     fsb_engine *e = new fsb_engine();
     e->cfg = *cfg;
+    e->redzone = getenv("FSB_REDZONE") && atoi(getenv("FSB_REDZONE")) > 0;
     DevState &d = e->d;
     const fsb_params &p0 = pts[0];
     d.K = static_cast<int>(p0.bigk); d.M = static_cast<int>(p0.bigm); d.N = static_cast<int>(p0.bign);
@@ -301,6 +327,21 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
         }
     }
     e->fast = (d.K <= 256);
+    // the default Params shape exactly: the event and choice kernels of the fixed-shape build (FSB_NO_FIXED=1: generic build)
+    e->fixed = (!d.big && d.K == kFixedK && d.M == kFixedM && d.N == kFixedN && d.W == kFixedW && d.cap_ev == kFixedCap && d.slots_a == kFixedSlots &&
+                d.slots_c == kFixedSlots && e->block == kStepThreads && e->block_e2 == kE2Threads && kE2Threads == kStepThreads && !getenv("FSB_NO_FIXED"));
+    if (e->fixed) {
+        const void *kf[3] = {(const void *)fsb_fix_events1_kernel, (const void *)fsb_fix_choice_kernel, (const void *)fsb_fix_events2_kernel};
+        const int sm[3] = {e->smem_bytes[0], e->smem_bytes[2], e->smem_bytes[2]};
+        for (int k = 0; k < 3; ++k) {
+            int occ = 0;
+            if (cudaFuncSetAttribute(kf[k], cudaFuncAttributeMaxDynamicSharedMemorySize, sm[k]) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf[k], e->block, sm[k]) != cudaSuccess || occ < e->occ[k == 0 ? 0 : 2]) {
+                (void)cudaGetLastError();
+                e->fixed = false;  // (cannot be as resident as the generic build: keep that one)
+            }
+        }
+    }
     // batches: with more than one, every kernel takes only a share of each SM so that kernels of different
     // batches are co-resident (pass: 2 CTAs per SM, events: 3)
     e->n_batches = 1;  // (FSB_BATCHES > 1: kernels of different batches overlap; measured gain 3 % at most)
@@ -753,6 +794,7 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                 if (!d.big) fsb_draws_kernel<<<static_cast<unsigned>(std::min<long long>((rb + 7) / 8, static_cast<long long>(e->sms) * 8)), 256, 0, st>>>(d, a);
 #endif
                 if (d.big) fsb_big_events1_kernel<<<g1, e->block, e->smem_bytes[0], st>>>(d, a, e->launch_parity);
+                else if (e->fixed) fsb_fix_events1_kernel<<<g1, e->block, e->smem_bytes[0], st>>>(d, a, e->launch_parity);
                 else fsb_events1_kernel<<<g1, e->block, e->smem_bytes[0], st>>>(d, a, e->launch_parity);
                 const bool timed = e->kev_used + 2 <= 4096;  // (the dominant kernel is timed launch by launch: bench.py's roofline)
                 if (timed) {
@@ -766,9 +808,11 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                 if (ht && ht->nav_open_out)  // the NAVs of :460 are final after the pass: device -> host while events-2 runs
                     CU(cudaMemcpyAsync(ht->nav_open_out + a.r_begin * d.K, d.nav_open + a.r_begin * d.K, rb * d.K * 8, cudaMemcpyDeviceToHost, st));
 #if FSB_SPLIT_CHOICE
-                if (!d.big) fsb_choice_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
+                if (e->fixed) fsb_fix_choice_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
+                else if (!d.big) fsb_choice_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
 #endif
                 if (d.big) fsb_big_events2_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
+                else if (e->fixed) fsb_fix_events2_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
                 else fsb_events2_kernel<<<g3, e->block_e2, e->smem_bytes[2], st>>>(d, a, e->launch_parity);
                 e->last_launches += (FSB_SPLIT_CHOICE && !d.big) ? 5 : 3;
             }
@@ -1176,6 +1220,29 @@ extern "C" int32_t fsb_stats_all(fsb_engine **engines, int32_t n, uint64_t *out)
 }
 
 // ---- debug --------------------------------------------------------------------------------------
+// FSB_REDZONE=1 engines: number of device buffers whose guard bands (256 bytes before, >= 256 after) no longer hold
+// the fill pattern, i.e. that some kernel wrote outside of; -1 in *n_buffers when the engine was created without red zones
+extern "C" int32_t fsb_debug_redzones(fsb_engine *e, int64_t *n_buffers, int64_t *n_damaged)
+{
+    if (!e || !n_buffers || !n_damaged) return fail(FSB_ERR_BAD_PARAMS, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    *n_buffers = e->redzone ? static_cast<int64_t>(e->zones.size()) : -1;
+    *n_damaged = 0;
+    std::vector<unsigned char> band(512);
+    for (const auto &z : e->zones) {
+        const size_t padded = (z.second + 255) & ~static_cast<size_t>(255);
+        bool bad = false;
+        CU(cudaMemcpy(band.data(), z.first - 256, 256, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 256; ++i) bad = bad || band[i] != 0xA5;
+        const size_t tail = padded - z.second + 256;  // the slack up to the 256-byte boundary belongs to the band
+        CU(cudaMemcpy(band.data(), z.first + z.second, tail, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tail; ++i) bad = bad || band[i] != 0xA5;
+        *n_damaged += bad ? 1 : 0;
+    }
+    return FSB_OK;
+}
+
 // per-phase cycle counters of the step kernel (all zero unless built with -DFSB_PHASE_TIMING); reset = 1 clears them
 extern "C" int32_t fsb_debug_phase_cycles(fsb_engine *e, uint64_t out[32], int32_t reset)
 {

@@ -47,6 +47,21 @@
 #define fsb_pass_kernel fsb_big_pass_kernel
 #define fsb_events2_kernel fsb_big_events2_kernel
 #endif
+// FSB_FIXED (fsb_step_fixed.cu): a third build of the same code for exactly the default Params shape (K = M = 250,
+// N = 1000, event capacity 80, 8 column slots, 128-thread CTAs).  Shapes, pitches and every shared-memory offset of the
+// step context are compile-time constants there, so the accessors below cost no instructions (in the generic build they
+// are a shared-memory load and an add each: 14 % / 15 % of the warp instructions of events-1 / events-2) and the
+// per-asset / per-investor loops have constant trip counts.  Only the event and choice kernels are launched from it.
+#ifndef FSB_FIXED
+#define FSB_FIXED 0
+#endif
+#if FSB_FIXED
+#define fsb_events1_kernel fsb_fix_events1_kernel
+#define fsb_pass_kernel fsb_fix_pass_kernel
+#define fsb_events2_kernel fsb_fix_events2_kernel
+#define fsb_choice_kernel fsb_fix_choice_kernel
+#define fsb_draws_kernel fsb_fix_draws_kernel
+#endif
 
 #include "fsb_device.cuh"
 #include "fsb_state.h"
@@ -108,11 +123,11 @@ struct SmemLayout {
 
 // nslots: column slots of `cols` (slot 0: opening prices, 1: current prices, 2..: staged history columns /
 // order rows / probability rows, depending on the kernel)
-__host__ __device__ inline SmemLayout make_layout(int K, int Mp, int N, int cap, int nslots, int nwarps, int ring_stages = 0, bool big = false)
+__host__ __device__ constexpr inline SmemLayout make_layout(int K, int Mp, int N, int cap, int nslots, int nwarps, int ring_stages = 0, bool big = false)
 {
     // ring_stages > 0 marks the pass kernel, which needs none of the per-asset / per-investor event arrays
     const bool lean = ring_stages > 0;
-    SmemLayout L;
+    SmemLayout L{};
     L.cp = (Mp + 127) & ~127;  // == Mp: the engine rounds Mp up to 128 itself
     L.kq = (K + 3) & ~3;
     const int kp = (L.kq + 127) & ~127;
@@ -173,7 +188,31 @@ constexpr int kCtxBytes = 1024;
 
 // The step's context: ONE instance per CTA in shared memory, filled by thread 0 per replication.
 // Phase functions receive a reference to it; thread-private ids are recomputed from threadIdx.
+#if FSB_FIXED
+constexpr int kFixK = 250, kFixM = 250, kFixN = 1000, kFixMp = 256, kFixCap = 80, kFixSlots = 8, kFixW = 100;
+constexpr SmemLayout kFixL = make_layout(kFixK, kFixMp, kFixN, kFixCap, kFixSlots, FSB_STEP_THREADS / 32);
+constexpr int kFixBd = 1024 /* kCtxBytes */, kFixBi = kFixBd + 8 * kFixL.ndoubles, kFixBs = kFixBi + 4 * kFixL.nints;
+#endif
 struct Ctx {
+#if FSB_FIXED
+    // shapes, pitches and shared-memory offsets of the default Params shape as constants (see FSB_FIXED above)
+    static constexpr int K = kFixK, M = kFixM, N = kFixN, Mp = kFixMp, cap = kFixCap, fast = 1, rank256 = 1, W = kFixW;
+    static constexpr int cp = kFixL.cp, cpk = kFixL.cpk, kq = kFixL.kq, srows = kFixL.srows, wsd = kFixL.wsd;
+    static constexpr int o_cols = kFixBd + 8 * kFixL.off_cols, o_ratio = kFixBd + 8 * kFixL.off_ratio, o_sellsum = kFixBd + 8 * kFixL.off_sellsum,
+                         o_nav = kFixBd + 8 * kFixL.off_nav, o_d_stake = kFixBd + 8 * kFixL.off_dstake, o_d_cash = kFixBd + 8 * kFixL.off_dcash,
+                         o_r_inj = kFixBd + 8 * kFixL.off_rinj, o_r_fval = kFixBd + 8 * kFixL.off_rfval, o_r_ncap = kFixBd + 8 * kFixL.off_rncap,
+                         o_scal = kFixBd + 8 * kFixL.off_scal;
+    static constexpr int o_rev = kFixBi + 4 * kFixL.off_rev, o_rfund = kFixBi + 4 * kFixL.off_rfund, o_d_inv = kFixBi + 4 * kFixL.off_dinv,
+                         o_d_fund = kFixBi + 4 * kFixL.off_dfund, o_cash = kFixBi + 4 * kFixL.off_cash, o_r_choice = kFixBi + 4 * kFixL.off_rchoice,
+                         o_r_col = kFixBi + 4 * kFixL.off_rcol, o_hcols = kFixBi + 4 * kFixL.off_hcols, o_eggs = kFixBi + 4 * kFixL.off_eggs,
+                         o_wl = kFixBi + 4 * kFixL.off_wl, o_wcnt = kFixBi + 4 * kFixL.off_wcnt, o_flags = kFixBi + 4 * kFixL.off_flags,
+                         o_nzf = kFixBi + 4 * kFixL.off_nzf, o_pick = kFixBi + 4 * kFixL.off_pick, o_fmod = kFixBi + 4 * kFixL.off_fmod,
+                         o_fsel = kFixBi + 4 * kFixL.off_fsel, o_isc = kFixBi + 4 * kFixL.off_isc;
+    static constexpr int o_pos16 = kFixBs + 2 * kFixL.off_pos16, o_hor16 = kFixBs + 2 * kFixL.off_hor16, o_stl = kFixBs + 2 * kFixL.nshorts,
+                         o_hz = o_stl + ((kFixK + 15) & ~15);
+    int T, cmax, keep_history, cap_log, cap_trace, kc, slot, ring_stages;
+    int o_ring, o_bars;
+#else
     // shapes / configuration (copies of DevState fields)
     int K, M, N, Mp, T, W, cap, cmax, keep_history, cap_log, cap_trace, fast, rank256, kc, slot, ring_stages;
     int cp, cpk, kq, srows, wsd;
@@ -181,6 +220,7 @@ struct Ctx {
     int o_cols, o_ratio, o_sellsum, o_nav, o_d_stake, o_d_cash, o_r_inj, o_r_fval, o_r_ncap, o_scal;
     int o_rev, o_rfund, o_d_inv, o_d_fund, o_cash, o_r_choice, o_r_col, o_hcols, o_eggs, o_wl, o_wcnt, o_flags, o_nzf, o_pick, o_fmod, o_fsel, o_isc;
     int o_pos16, o_hor16, o_stl, o_hz, o_ring, o_bars;
+#endif
     unsigned long long *mbar;
     unsigned mbar_phase;
     unsigned char *big;       // FSB_BIG: this CTA's global buffer for the per-asset arrays
@@ -290,25 +330,32 @@ struct Rep {
 };
 __device__ __forceinline__ Rep rep_ptrs(const DevState &s, const long long r, const int kq, const int slot)
 {
+#if FSB_FIXED  // the shape-dependent strides as constants
+    constexpr int K = kFixK, N = kFixN, Mp = kFixMp, cap_ev = kFixCap;
+    constexpr long long h_stride = static_cast<long long>((kFixK + 3) & ~3) * kFixMp;
+#else
+    const int K = s.K, N = s.N, Mp = s.Mp, cap_ev = s.cap_ev;
+    const long long h_stride = s.h_stride;
+#endif
     Rep g;
-    g.H = s.H + r * s.h_stride;
+    g.H = s.H + r * h_stride;
     g.P = s.P + r * s.p_stride;
-    g.beta = s.beta + r * s.Mp; g.vol = s.vol + r * s.Mp; g.impact = s.impact + r * s.Mp;
-    g.volume = s.volume ? s.volume + r * static_cast<long long>(s.T) * s.Mp : nullptr;
+    g.beta = s.beta + r * Mp; g.vol = s.vol + r * Mp; g.impact = s.impact + r * Mp;
+    g.volume = s.volume ? s.volume + r * static_cast<long long>(s.T) * Mp : nullptr;
     g.market = s.market + r * s.mkt_len;
-    g.pos = s.pos + r * s.N; g.horizon = s.horizon + r * s.N;
-    g.stake = s.stake + r * s.N; g.amount = s.amount + r * s.N; g.threshold = s.threshold + r * s.N;
-    g.nav_open = s.nav_open + r * s.K; g.nav_close = s.nav_close + r * s.K;
-    g.hzero = s.hzero + r * s.K; g.stakeless = s.stakeless + r * s.K;
+    g.pos = s.pos + r * N; g.horizon = s.horizon + r * N;
+    g.stake = s.stake + r * N; g.amount = s.amount + r * N; g.threshold = s.threshold + r * N;
+    g.nav_open = s.nav_open + r * K; g.nav_close = s.nav_close + r * K;
+    g.hzero = s.hzero + r * K; g.stakeless = s.stakeless + r * K;
     g.cnt = s.cnt + r * kCnt;
     g.mkt_peak = s.mkt_peak + r; g.mkt_dd = s.mkt_dd + r;
     g.flow_hist = s.flow_hist + r * kFlowBins;
-    g.scratch = s.scratch + (static_cast<long long>(slot) * s.scratch_ctas + blockIdx.x) * (static_cast<long long>(s.cap_ev) * s.Mp);
+    g.scratch = s.scratch + (static_cast<long long>(slot) * s.scratch_ctas + blockIdx.x) * (static_cast<long long>(cap_ev) * Mp);
     g.keys = s.keys + r * (static_cast<long long>(s.kc) * kq);
     g.hand_i = s.hand_i + r * s.hi_stride;
-    g.hand_p = s.hand_p + r * s.Mp;
-    g.hand_s = s.hand_s ? s.hand_s + r * s.Mp : nullptr;
-    g.hand_m = s.hand_m ? s.hand_m + r * (2 * ((s.N + 63) >> 6)) : nullptr;
+    g.hand_p = s.hand_p + r * Mp;
+    g.hand_s = s.hand_s ? s.hand_s + r * Mp : nullptr;
+    g.hand_m = s.hand_m ? s.hand_m + r * (2 * ((N + 63) >> 6)) : nullptr;
     return g;
 }
 
@@ -342,7 +389,11 @@ static __device__ __noinline__ double ddiv(double x, double y) { return x / y; }
 // 0 < y < inf the IEEE quotient of a zero is that same signed zero
 __device__ __forceinline__ double qdiv(double x, double y)
 {
+#ifdef FSB_QDIV_PLAIN  // (experiment: the shortcut only pays when a whole warp's numerators are zero)
+    return ddiv(x, y);
+#else
     return (x == 0.0 && y > 0.0 && y < 1.7976931348623157e308) ? x : ddiv(x, y);
+#endif
 }
 static __device__ __noinline__ uint4 philox_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
@@ -2203,13 +2254,16 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
     const SmemLayout L = make_layout(s.K, s.Mp, s.N, s.cap_ev, nslots, nwarps, (KIND == KIND_PASS) ? s.ring_stages : 0, FSB_BIG != 0);
     double *sd = reinterpret_cast<double *>(fsb_smem + kCtxBytes);
     if (threadIdx.x == 0) {
-        c.K = s.K; c.M = s.M; c.N = s.N; c.Mp = s.Mp; c.T = s.T; c.W = s.W; c.cap = s.cap_ev; c.cmax = s.cmax;
+        c.T = s.T; c.cmax = s.cmax;
         c.keep_history = s.keep_history; c.cap_log = s.cap_log; c.cap_trace = s.cap_trace;
+        c.kc = s.kc;
+        c.ring_stages = (KIND == KIND_PASS) ? s.ring_stages : 0;
+        c.o_ring = L.off_ring; c.o_bars = L.off_bars;
+#if !FSB_FIXED
+        c.K = s.K; c.M = s.M; c.N = s.N; c.Mp = s.Mp; c.cap = s.cap_ev; c.W = s.W;
         c.cp = L.cp; c.cpk = L.cpk; c.kq = L.kq; c.srows = L.srows; c.wsd = L.wsd;
         c.rank256 = (s.K <= 256) ? 1 : 0;  // the in-register rank sort holds 256 keys
         c.fast = (s.K <= 256 && s.Mp == 256) ? 1 : 0;
-        c.kc = s.kc;
-        c.ring_stages = (KIND == KIND_PASS) ? s.ring_stages : 0;
         const int bd = kCtxBytes, bi = bd + 8 * L.ndoubles, bs = bi + 4 * L.nints;  // byte offsets of the double / int / 16-bit regions
         c.o_cols = bd + 8 * L.off_cols; c.o_ratio = bd + 8 * L.off_ratio; c.o_sellsum = bd + 8 * L.off_sellsum;
         c.o_nav = bd + 8 * L.off_nav; c.o_d_stake = bd + 8 * L.off_dstake; c.o_d_cash = bd + 8 * L.off_dcash;
@@ -2222,7 +2276,7 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         c.o_pos16 = bs + 2 * L.off_pos16; c.o_hor16 = bs + 2 * L.off_hor16;
         c.o_stl = bs + 2 * L.nshorts;
         c.o_hz = c.o_stl + ((s.K + 15) & ~15);
-        c.o_ring = L.off_ring; c.o_bars = L.off_bars;
+#endif
         c.big = nullptr;
 #if FSB_BIG
         c.o_cols = static_cast<int>(L.big_cols); c.o_ratio = static_cast<int>(L.big_ratio); c.o_sellsum = static_cast<int>(L.big_sellsum);

@@ -71,6 +71,12 @@ class Engine:
         """The day the next run must start with (days are simulated once and in order)."""
         return int(L.lib().fsb_next_day(self._h))
 
+    def redzones(self):
+        """(buffers, damaged) of an engine created under FSB_REDZONE=1; buffers == -1 without red zones."""
+        n, bad = C.c_int64(), C.c_int64()
+        L.check(L.lib().fsb_debug_redzones(self._h, C.byref(n), C.byref(bad)))
+        return n.value, bad.value
+
     def device_bytes(self):
         return L.lib().fsb_device_bytes(self._h)
 

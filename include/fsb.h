@@ -234,6 +234,9 @@ int32_t fsb_last_facts_timing(fsb_engine *e, double *kernel_ms);
 int32_t fsb_run_async(fsb_engine *e, int64_t t_first, int64_t t_last, int32_t selector, int32_t flags);
 int32_t fsb_sync(fsb_engine *e);
 int64_t fsb_device_bytes(const fsb_engine *e);
+/* engines created under FSB_REDZONE=1 keep guard bands around every device buffer: counts the buffers some kernel
+ * wrote outside of (n_buffers = -1 without red zones) */
+int32_t fsb_debug_redzones(fsb_engine *e, int64_t *n_buffers, int64_t *n_damaged);
 /* the day fsb_run / fsb_run_async / fsb_run_step_hosttape must start with next (perf_hi+2 on a fresh state) */
 int64_t fsb_next_day(const fsb_engine *e);
 /* RNG building blocks evaluated ON THE DEVICE, for cross-checks against the oracle */

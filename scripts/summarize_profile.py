@@ -20,7 +20,7 @@ src = os.path.join(out, f"launches_{tag}.csv")
 if os.path.exists(src):
     rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit()]
     with open(os.path.join(prof, f"{tag}_launches.csv"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 6 --warmup 3 --no-cpu-baseline\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 6 --warmup 3 --no-cpu-baseline --full-horizon-reps 0\n")
         f.write("# per-launch times are cold-cache and serialised: compare shares, not absolutes\n")
         f.write("id,kernel,grid,block,duration_ms\n")
         tot, by = 0.0, {}
@@ -50,12 +50,17 @@ lines = [f"# {tag}: ncu --set full --clock-control none, one launch of each kern
 traffic = {}
 for kname in ("draws", "events1", "pass", "choice", "events2"):
     rep = os.path.join(out, f"prof_{tag}_{kname}.ncu-rep")
-    if not os.path.exists(rep):
-        continue
+    if not os.path.exists(rep):  # the fixed-shape build of the event kernels (fsb_step_fixed.cu)
+        rep = os.path.join(out, f"prof_{tag}_fix_{kname}.ncu-rep")
+        if not os.path.exists(rep):
+            continue
+        kname_shown = "fix_" + kname
+    else:
+        kname_shown = kname
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, r = rows[0], rows[1], rows[2]
-    lines += [f"## fsb_{kname}_kernel", "", "| metric | value | unit |", "|---|---|---|"]
+    lines += [f"## fsb_{kname_shown}_kernel", "", "| metric | value | unit |", "|---|---|---|"]
     for w in want:
         if w in hdr:
             lines.append(f"| {w} | {r[hdr.index(w)]} | {units[hdr.index(w)]} |")

@@ -407,6 +407,67 @@ def test_single_process_multi_gpu_statistics(fsb):
             e.close()
 
 
+@pytest.mark.parametrize("env", [{}, {"FSB_PASS_PACKED": "1"}, {"FSB_FORCE_BIG": "1"}, {"FSB_BATCHES": "3"}, {"FSB_NO_TMA": "1"}],
+                         ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()) or "default")
+def test_no_kernel_writes_outside_its_buffers(fsb, env, monkeypatch):
+    """compute-sanitizer is closed on this GPU pool (profiles/r2_sanitizer.md), so out-of-bounds WRITES are hunted with the
+    library's own guard bands: under FSB_REDZONE=1 every device buffer sits between two 256-byte bands of a fill pattern;
+    after init, a run with traces, the host-tape step, statistics, stylised facts and every download, no band may have changed."""
+    monkeypatch.setenv("FSB_REDZONE", "1")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for p, R, days in ((fsb.Params.default(), 24, 70), (H.small_params(fsb), 5, 50),
+                       (H.small_params(fsb, bigk=11, bign=90, bigm=17, bigt=140, perfwindow=(1, 12), portfsizerange=(1, 9)), 7, 120)):
+        with fsb.Engine(p, R, keep_history=True, rep_offset=3) as eng:
+            eng.init_device(SEED)
+            eng.set_trace(1)
+            t0 = p.perfwindow[-1] + 2
+            eng.run(t_last=t0 + days - 2)
+            rng = np.random.default_rng(5)
+            nav = np.zeros((R, p.bigk))
+            eng.run_step_hosttape(t0 + days - 1, rng.standard_normal(R), rng.standard_normal((R, p.bigm)), rng.random((R, p.bign)), nav)
+            eng.stats()
+            eng.stylised_facts(maxlag=3)
+            for r in range(R):
+                eng.download_state(r)
+                eng.download_log(r)
+            eng.download_trace(1)
+            n, bad = eng.redzones()
+            assert n > 30 and bad == 0, (n, bad)
+    monkeypatch.delenv("FSB_REDZONE")
+    with fsb.Engine(H.small_params(fsb), 2) as eng:   # (without the guard bands the call says so)
+        assert eng.redzones()[0] == -1
+
+
+def test_repeated_runs_are_bit_identical(fsb):
+    """A data race (the pass kernel reuses its TMA ring slots, kernels hand lists over through global memory, batches run on
+    separate streams) would show up as run-to-run differences: the same 1536 default-shape replications three times, with
+    one and with four replication batches, every replication's holdings / NAVs / prices compared through checksums."""
+    import hashlib
+    import os
+    p = fsb.Params.default()
+    R, t_last = 1536, 101 + 48
+
+    def run():
+        with fsb.Engine(p, R, rep_offset=40_000) as eng:
+            eng.init_device(SEED)
+            eng.run(t_last=t_last)
+            h = hashlib.blake2b(digest_size=16)
+            for r in range(0, R, 3):
+                c = eng.download_compact(r)
+                for k in ("holdings", "nav_close", "nav_open", "price_now", "inv_stake", "inv_amount"):
+                    h.update(np.ascontiguousarray(c[k]).tobytes())
+            return h.hexdigest(), eng.stats_raw().tolist()
+
+    first = run()
+    assert run() == first
+    os.environ["FSB_BATCHES"] = "4"
+    try:
+        assert run() == first
+    finally:
+        del os.environ["FSB_BATCHES"]
+
+
 def test_stakeless_fund_with_holdings_keeps_the_volume_quirk(fsb, orc):
     """functions.jl:471-476 is entered whenever a fund's stakes sum to zero, also when respawn! then finds no all-zero
     holdings row (Q5): trackvolume! still subtracts the sell orders once more (:474, Q3).  Reached through an uploaded
@@ -434,6 +495,7 @@ def test_stakeless_fund_with_holdings_keeps_the_volume_quirk(fsb, orc):
 
 @pytest.mark.parametrize("env", [
     {"FSB_CMAX": "6"},                          # small column chunks: several holdings passes per day
+    {"FSB_NO_FIXED": "1"},                      # the generic build of the event kernels instead of the fixed-shape one
     {"FSB_PASS_PACKED": "1"},                   # the pass over the packed mirror of the holdings (fsb_passx.cuh, opt-in)
     {"FSB_PASS_PACKED": "1", "FSB_XCOLS": "4"},  # ... with small column chunks: several passes over the packed rows per day
     {"FSB_NO_TMA": "1"},                        # register-ring pass (the path of non-default shapes) on the default shape
