@@ -474,6 +474,7 @@ def bench_config5(args, fsb, dist, rank, world, local, barrier):
     import hashlib
     import numpy as np
     from fundstababm_jl_b200.calibrate import calibrate, grid
+    cal_mod = sys.modules["fundstababm_jl_b200.calibrate"]  # (the package exports the function under the module's name)
     base = fsb.Params.default()
     points = grid(base, thresholdstd=(0.01, 0.025, 0.05, 0.1), reviewprobability=(1 / 126, 1 / 63, 1 / 21),
                   impactscale=(0.5, 1.0, 2.0, 4.0))
@@ -498,7 +499,8 @@ def bench_config5(args, fsb, dist, rank, world, local, barrier):
             "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "BASELINE.json configs[4]: calibrate sweep, thresholdstd x reviewprobability x impact scale",
                        "points": len(points), "replications_per_point": reps, "days": days, "K_funds": base.bigk,
-                       "timing": "wall clock of calibrate(): engine creation, device initialisation, 1249 days, statistics allreduce"},
+                       "timing": "wall clock of calibrate(): engine creation, device initialisation, 1249 days, statistics allreduce",
+                       "rank0_split_of_the_last_sweep_s": {k: round(v, 3) for k, v in cal_mod.last_timing.items()}},
             "checks": {"statistics_sha256": h.hexdigest(), "replications": int(sum(st["replications"] for st in stats)),
                        "error_replications_q6": int(sum(st["error_replications"] for st in stats)),
                        "nan_replications": int(sum(st["nan_replications"] for st in stats)),

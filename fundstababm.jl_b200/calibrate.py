@@ -142,6 +142,9 @@ def calibrate_single_process(points, reps, devices, *, seed=0, fundselector="pro
             e.close()
 
 
+last_timing = {}  # wall-clock split of the last plain calibrate() call on this rank (bench.py --config 5 reports it)
+
+
 def history_bytes_per_replication(p):
     """Device bytes a replication needs on top of the ring state when the engine keeps the price and volume histories
     (what the stylised-facts kernels read): 2 x T x Mp doubles."""
@@ -151,7 +154,7 @@ def history_bytes_per_replication(p):
 
 def calibrate(points, reps, *, seed=0, fundselector="probabilistic", device=0, t_last=None,
               engine_kwargs=None, evaluation=None, maxlag=10, returnspctile=5, history_batch=None,
-              history_budget_bytes=32 << 30):
+              history_budget_bytes=32 << 30, library_collective=False):
     """Runs ``reps`` replications of every point and returns one statistics dict per point
     (identical on every rank).
 
@@ -164,7 +167,12 @@ def calibrate(points, reps, *, seed=0, fundselector="probabilistic", device=0, t
     replications (default: what fits ``history_budget_bytes`` of device memory), each a history-keeping engine that is
     simulated, evaluated and released, while the integer statistics accumulate.  Replications are independent and the
     Philox counters use global replication ids, so the results do not depend on the batch size: a 10^5-replication sweep
-    that only fits as a ring engine gets the same facts as ``keep_history`` would give."""
+    that only fits as a ring engine gets the same facts as ``keep_history`` would give.
+
+    The one collective of a sweep -- the sum of the per-point integer statistics over the ranks -- goes through the
+    process group the caller already has (torch.distributed, NCCL over NVLink on GPUs); ``library_collective=True`` uses the
+    library's own communicator instead (fsb_comm_init_rank + fsb_stats, the path bench.py and the Julia glue exercise),
+    which costs a communicator creation and its first-use connection set-up per call (about 1.5 s at 2 ranks)."""
     if evaluation not in (None, "stylisedfacts"):
         raise ValueError(f"unknown evaluation {evaluation!r}")
     dist = _dist()
@@ -207,13 +215,33 @@ def calibrate(points, reps, *, seed=0, fundselector="probabilistic", device=0, t
                              + "; raise event_capacity / log_capacity in engine_kwargs")
 
     if not evaluation:
+        import time as _time
+        tm = {}
+        t0 = _time.perf_counter()
         with Engine(points, hi - lo, rep_offset=lo, reps_per_point=reps, device=device, **kw) as eng:
-            if world > 1:
+            tm["create_s"] = _time.perf_counter() - t0
+            t0 = _time.perf_counter()
+            if world > 1 and library_collective:
                 eng.comm_init_rank(world, rank, share_unique_id(dist, device))
+            tm["comm_init_s"] = _time.perf_counter() - t0
+            t0 = _time.perf_counter()
             eng.init_device(seed)
+            tm["init_device_s"] = _time.perf_counter() - t0
+            t0 = _time.perf_counter()
             run(eng)
+            tm["run_s"] = _time.perf_counter() - t0
+            t0 = _time.perf_counter()
             fail_on(*check_flags(eng))
-            return eng.stats()   # the single NCCL allreduce, inside the library
+            if library_collective or world == 1:
+                out = eng.stats()   # the single NCCL allreduce, inside the library
+            else:
+                from .engine import decode_stats
+                raw = allreduce(eng.stats_raw(local=True).astype(np.int64))   # the single allreduce, on the caller's process group
+                out = [decode_stats(row.astype(np.uint64), points[0].bigt) for row in raw]
+            tm["flags_and_stats_s"] = _time.perf_counter() - t0
+        last_timing.clear()
+        last_timing.update(tm)
+        return out
 
     # ---- evaluation on the device, history batch by history batch ------------------------------------------------------
     kw["keep_history"] = True
