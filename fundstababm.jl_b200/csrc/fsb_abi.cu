@@ -326,6 +326,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
             e->grid[k] = static_cast<int>(std::min<long long>(d.R, static_cast<long long>(sms) * occ));
         }
     }
+    d.scan_choice = (getenv("FSB_SCAN_CHOICE") && atoi(getenv("FSB_SCAN_CHOICE")) > 0) ? 1 : 0;
     e->fast = (d.K <= 256);
     // the default Params shape exactly: the event and choice kernels of the fixed-shape build (FSB_NO_FIXED=1: generic build)
     e->fixed = (!d.big && d.K == kFixedK && d.M == kFixedM && d.N == kFixedN && d.W == kFixedW && d.cap_ev == kFixedCap && d.slots_a == kFixedSlots &&

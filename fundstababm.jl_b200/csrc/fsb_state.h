@@ -31,6 +31,7 @@ struct DevState {
     int big;               // shapes whose per-asset arrays do not fit in shared memory: the FSB_BIG build of the step kernels
     long long big_stride;  // bytes of a CTA's global buffer for those arrays
     unsigned char *bigbuf; // [2 * batches][scratch_ctas][big_stride]
+    int scan_choice;       // FSB_SCAN_CHOICE=1: the rank rule is sampled by the floating-point scan only (no integer shortcut; tests)
     int ring_stages;       // per-warp holdings ring of the pass kernel (kRingStages on the default shape, else 0)
     int n_points;
     long long R, rep_offset, reps_per_point;

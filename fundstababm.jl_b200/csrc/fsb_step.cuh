@@ -603,7 +603,11 @@ static __device__ __noinline__ int select_fund_warp(int t, int inv, const unsign
 // One THREAD samples the rank-proportional choice (functions.jl:400-410, Q14) for reinvestor `inv`:
 // pk[k] = rank_k / (K(K+1)/2) is already in shared memory; Distributions v0.20 sampler:
 // cp = 0, i = 0; while cp < u && i < K: cp += p[++i].
-__device__ __forceinline__ int select_fund_prob(Ctx &c, int t, int inv, const double *pk)
+// cum (optional): the exact integer prefix sums C_i = rank_0 + .. + rank_{i-1} of the column (cum[q] = C_{q+1}).  The scan's
+// partial sums satisfy |cp_i - C_i / S| <= (K + 1) 2^-53 (S = K (K + 1) / 2; every term and every addition rounds once), i.e.
+// < 1e-9 in units of C, so whenever u S is farther than 1e-6 from an integer the scan stops at the smallest i with
+// C_i >= u S -- found by bisection instead of ~150 dependent additions; the 2e-6 of the draws that are closer take the scan.
+__device__ __forceinline__ int select_fund_prob(Ctx &c, int t, int inv, const double *pk, const int *cum = nullptr)
 {
     double forced;
     if (c.tape && tape_lookup(c, FSB_TAPE_CHOICE_IDX, t, inv, 0, &forced)) return static_cast<int>(forced);
@@ -614,9 +618,21 @@ __device__ __forceinline__ int select_fund_prob(Ctx &c, int t, int inv, const do
         const uint4 w = draw_block_s(c.rng, SITE_CHOICE, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(inv));
         u = u52(w.x, w.y);
     }
+    const int K = c.K;
+    if (cum) {
+        const double x = u * (0.5 * static_cast<double>(K) * static_cast<double>(K + 1));
+        if (fabs(x - rint(x)) > 1e-6) {
+            int lo = 0, hi = K - 1;
+#pragma unroll 1
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (static_cast<double>(cum[mid]) >= x) hi = mid; else lo = mid + 1;
+            }
+            return lo;
+        }
+    }
     double cp = 0.0;
     int i = 0;
-    const int K = c.K;
 #pragma unroll 1
     while (i + 4 <= K) {  // 4 probabilities per trip (the adds stay sequential: same cp sequence)
         const double p0 = pk[i], p1 = pk[i + 1], p2 = pk[i + 2], p3 = pk[i + 3];
@@ -1806,10 +1822,36 @@ __device__ FSB_FP_INLINE void phase_choice(const DevState &s, const int t, const
             else warp_rank_count(keys, K, prob_k, c.ranktab);
             __syncwarp();
             FSB_MARK(23);
+            // exact integer prefix sums of the ranks (see select_fund_prob), when the warp has room for them behind the
+            // probability rows: lane l owns funds 8 l .. 8 l + 7
+            const int *cum = nullptr;
+            if (c.rank256 && !s.scan_choice && c.srows * c.cp >= nwarps * c.cpk + nwarps * 128) {
+                int *cw = reinterpret_cast<int *>(c.cols_() + (2 + nwarps) * c.cpk) + warp * 256;
+                const double snorm = 0.5 * static_cast<double>(K) * static_cast<double>(K + 1);
+                int rk[8], tot = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = 8 * lane + q;
+                    rk[q] = (k < K) ? __double2int_rn(prob_k[k] * snorm) : 0;  // rank_k: prob_k = fl(rank_k / S)
+                    tot += rk[q];
+                    rk[q] = tot;
+                }
+                int excl = tot;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int x = __shfl_up_sync(0xffffffffu, excl, d);
+                    if (lane >= d) excl += x;
+                }
+                excl -= tot;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) cw[8 * lane + q] = excl + rk[q];
+                __syncwarp();
+                cum = cw;
+            }
             // the same warp samples the choice of every cash holder whose horizon is this column
             for (int i = lane; i < ncash; i += 32) {
                 if (c.r_col_()[i] != jc) continue;
-                c.r_choice_()[i] = select_fund_prob(c, t, c.cash_()[i], prob_k);
+                c.r_choice_()[i] = select_fund_prob(c, t, c.cash_()[i], prob_k, cum);
             }
             __syncwarp();
         }

@@ -496,6 +496,7 @@ def test_stakeless_fund_with_holdings_keeps_the_volume_quirk(fsb, orc):
 @pytest.mark.parametrize("env", [
     {"FSB_CMAX": "6"},                          # small column chunks: several holdings passes per day
     {"FSB_NO_FIXED": "1"},                      # the generic build of the event kernels instead of the fixed-shape one
+    {"FSB_SCAN_CHOICE": "1"},                   # the rank rule sampled by the floating-point scan alone (no integer shortcut)
     {"FSB_PASS_PACKED": "1"},                   # the pass over the packed mirror of the holdings (fsb_passx.cuh, opt-in)
     {"FSB_PASS_PACKED": "1", "FSB_XCOLS": "4"},  # ... with small column chunks: several passes over the packed rows per day
     {"FSB_NO_TMA": "1"},                        # register-ring pass (the path of non-default shapes) on the default shape
