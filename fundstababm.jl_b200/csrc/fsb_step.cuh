@@ -116,6 +116,7 @@ struct SmemLayout {
     int wsd;    // doubles of that region per warp (member lists of the stake sequence)
     int ndoubles, nints, nshorts;
     int off_ring, off_bars;  // byte offsets (pass kernel only)
+    int off_sort, sortn;     // byte offset / padded length of the CTA-wide rank sort (256 < K <= 2048; event kernels only)
     int bytes;
     // big shapes: byte offsets of cols / ratio / sellsum / pick inside the per-CTA global buffer, and its size
     long long big_cols, big_ratio, big_sellsum, big_pick, big_bytes;
@@ -172,6 +173,10 @@ __host__ __device__ constexpr inline SmemLayout make_layout(int K, int Mp, int N
     L.off_hor16 = h; h += lean ? 0 : ((N + 7) & ~7);
     L.nshorts = h;
     L.bytes = 1024 /* kCtxBytes */ + d * 8 + i * 4 + h * 2 + 2 * ((K + 15) & ~15);  // Ctx + arrays + stl[K], hz[K] bytes
+    L.sortn = 0;
+    if (!lean && K > 256 && K <= 2048) { L.sortn = 512; while (L.sortn < K) L.sortn <<= 1; }
+    L.off_sort = (L.bytes + 15) & ~15;
+    if (L.sortn > 0) L.bytes = L.off_sort + L.sortn * 10;  // keys (8 B) + fund indices (2 B)
     L.off_ring = (L.bytes + 127) & ~127;
     L.off_bars = L.off_ring + nwarps * ring_stages * kStageBytes;
     if (ring_stages > 0) L.bytes = L.off_bars + nwarps * ring_stages * 8 + nwarps * 8;  // + per-warp running stage counters
@@ -210,6 +215,7 @@ struct Ctx {
                          o_fsel = kFixBi + 4 * kFixL.off_fsel, o_isc = kFixBi + 4 * kFixL.off_isc;
     static constexpr int o_pos16 = kFixBs + 2 * kFixL.off_pos16, o_hor16 = kFixBs + 2 * kFixL.off_hor16, o_stl = kFixBs + 2 * kFixL.nshorts,
                          o_hz = o_stl + ((kFixK + 15) & ~15);
+    static constexpr int o_sort = 0, sortn = 0;
     int T, cmax, keep_history, cap_log, cap_trace, kc, slot, ring_stages;
     int o_ring, o_bars;
 #else
@@ -219,7 +225,7 @@ struct Ctx {
     // shared arrays: byte offsets into the dynamic shared memory (accessors below keep the address space known)
     int o_cols, o_ratio, o_sellsum, o_nav, o_d_stake, o_d_cash, o_r_inj, o_r_fval, o_r_ncap, o_scal;
     int o_rev, o_rfund, o_d_inv, o_d_fund, o_cash, o_r_choice, o_r_col, o_hcols, o_eggs, o_wl, o_wcnt, o_flags, o_nzf, o_pick, o_fmod, o_fsel, o_isc;
-    int o_pos16, o_hor16, o_stl, o_hz, o_ring, o_bars;
+    int o_pos16, o_hor16, o_stl, o_hz, o_ring, o_bars, o_sort, sortn;
 #endif
     unsigned long long *mbar;
     unsigned mbar_phase;
@@ -752,6 +758,37 @@ static __device__ __noinline__ void warp_rank_count(const unsigned long long *ke
         }
         prob[k] = __ldg(ranktab + rank);
     }
+}
+
+// Rank of 256 < K <= 2048 keys by the whole CTA: bitonic network over (key, fund index) pairs in shared memory,
+// ordered lexicographically -- the stable ascending order itself, so no repair pass.  P = K rounded up to a power
+// of two; the padding sorts last (largest key, indices >= K).  All threads of the CTA must call this.
+static __device__ __noinline__ void block_rank_sort(const unsigned long long *keys, int K, int P, unsigned long long *sk, unsigned short *si,
+                                                   double *prob, const double *ranktab)
+{
+    const int tid = threadIdx.x, NT = blockDim.x;
+    for (int e = tid; e < P; e += NT) {
+        sk[e] = (e < K) ? __ldcg(keys + e) : ~0ULL;
+        si[e] = static_cast<unsigned short>(e);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+#pragma unroll 1
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int p = tid; p < (P >> 1); p += NT) {
+                const int lo = ((p & ~(j - 1)) << 1) | (p & (j - 1)), hi = lo | j;
+                const bool up = ((lo & k2) == 0);
+                const unsigned long long a = sk[lo], b = sk[hi];
+                const unsigned short ia = si[lo], ib = si[hi];
+                const bool gt = (a > b) || (a == b && ia > ib);
+                if (gt == up) { sk[lo] = b; sk[hi] = a; si[lo] = ib; si[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int e = tid; e < K; e += NT) prob[si[e]] = __ldg(ranktab + e);  // prob may alias sk (not si): the last stage ended with a barrier
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1815,6 +1852,21 @@ __device__ FSB_FP_INLINE void phase_choice(const DevState &s, const int t, const
     if (selector == FSB_SEL_PROBABILISTIC) {
         // rank rule: p_k = rank_k / (K(K+1)/2) per column, into the warp's probability row
         double *prob_k = c.cols_() + (2 + warp) * c.cpk;
+        if (c.sortn > 0) {  // 256 < K <= 2048: the CTA ranks one column at a time (block_rank_sort), then samples its cash holders
+            unsigned long long *sk = reinterpret_cast<unsigned long long *>(fsb_smem + c.o_sort);
+            unsigned short *si = reinterpret_cast<unsigned short *>(sk + c.sortn);
+            double *prob = reinterpret_cast<double *>(sk);  // (the sorted keys are dead once the indices are in order)
+#pragma unroll 1
+            for (int jc = 0; jc < ncols; ++jc) {
+                block_rank_sort(G.keys + static_cast<long long>(jc) * c.kq, K, c.sortn, sk, si, prob, c.ranktab);
+                for (int i = tid; i < ncash; i += NT) {
+                    if (c.r_col_()[i] != jc) continue;
+                    c.r_choice_()[i] = select_fund_prob(c, t, c.cash_()[i], prob, nullptr);
+                }
+                __syncthreads();
+            }
+            FSB_MARK(11);
+        } else {
 #pragma unroll 1
         for (int jc = warp; jc < ncols; jc += nwarps) {
             const unsigned long long *keys = G.keys + static_cast<long long>(jc) * c.kq;
@@ -1856,6 +1908,7 @@ __device__ FSB_FP_INLINE void phase_choice(const DevState &s, const int t, const
             __syncwarp();
         }
         FSB_MARK(11);
+        }
     } else {
 #pragma unroll 1
         for (int i = warp; i < ncash; i += nwarps) {
@@ -2318,6 +2371,7 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         c.o_pos16 = bs + 2 * L.off_pos16; c.o_hor16 = bs + 2 * L.off_hor16;
         c.o_stl = bs + 2 * L.nshorts;
         c.o_hz = c.o_stl + ((s.K + 15) & ~15);
+        c.o_sort = L.off_sort; c.sortn = L.sortn;
 #endif
         c.big = nullptr;
 #if FSB_BIG

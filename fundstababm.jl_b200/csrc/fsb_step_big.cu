@@ -6,5 +6,18 @@
 #define FSB_STEP_THREADS 256
 #define FSB_E2_THREADS 256
 #define FSB_EV_CTAS 2
+#ifdef FSB_BIG_TIMING  // experiments: per-phase cycles of the big kernels (scripts/phase_cycles.py --config4)
+#define FSB_PHASE_TIMING 1
+#define g_phase_cycles g_phase_cycles_big
+#else
 #undef FSB_PHASE_TIMING
+#endif
 #include "fsb_step.cuh"
+#ifdef FSB_BIG_TIMING
+extern "C" int fsb_debug_big_phase_cycles(unsigned long long *out, int reset)
+{
+    if (cudaMemcpyFromSymbol(out, fsb::g_phase_cycles_big, 32 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[32] = {}; if (cudaMemcpyToSymbol(fsb::g_phase_cycles_big, z, sizeof(z)) != cudaSuccess) return -1; }
+    return 0;
+}
+#endif

@@ -23,19 +23,31 @@ ap.add_argument("--reps", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=8)
 ap.add_argument("--t0", type=int, default=300)
 ap.add_argument("--blocks-per-sm", type=int, default=0)
+ap.add_argument("--config4", action="store_true", help="BASELINE configs[3] (needs -DFSB_BIG_TIMING)")
 a = ap.parse_args()
 fsb = load_package()
 p = fsb.Params.default()
+if a.config4:
+    p = fsb.Params.default(bigk=2000, bigm=5000, bign=8000, bigt=1101, portfsizerange=(2500, 5000))
 with fsb.Engine(p, a.reps, blocks_per_sm=a.blocks_per_sm) as eng:
     eng.init_device(7)
     eng.run_async(102, a.t0 - 1)
     eng.sync()
     out = np.zeros(32, dtype=np.uint64)
     lib = fsb._lib.lib()
-    lib.fsb_debug_phase_cycles(eng.handle, out.ctypes.data, 1)
+
+    def read_marks():
+        if a.config4:
+            fn = C.CDLL(fsb._lib.so_path()).fsb_debug_big_phase_cycles
+            fn.argtypes = [C.c_void_p, C.c_int]
+            fn(out.ctypes.data, 1)
+        else:
+            lib.fsb_debug_phase_cycles(eng.handle, out.ctypes.data, 1)
+
+    read_marks()
     eng.run_async(a.t0, a.t0 + a.steps - 1)
     eng.sync()
-    lib.fsb_debug_phase_cycles(eng.handle, out.ctypes.data, 1)
+    read_marks()
     ms, _, n = eng.last_run_timing()
 tot = float(out[:32].sum())
 print(f"reps={a.reps} steps={a.steps} ms={ms:.3f} fund_steps_per_s={a.reps * p.bigk * a.steps / (ms * 1e-3):.4e}")
