@@ -283,7 +283,12 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     // big shapes: even the leanest events-1 layout (3 column slots) does not fit in shared memory
     d.big = (make_layout(d.K, d.Mp, d.N, d.cap_ev, 3, nw).bytes + 64 > smem_max || getenv("FSB_FORCE_BIG")) ? 1 : 0;
     if (d.big && cfg->block_threads <= 0) { e->block = e->block_e2 = kBigStepThreads; nw = nw2 = kBigStepThreads / 32; }
-    if (d.big) { d.ring_stages = 0; e->block_pass = getenv("FSB_BIG_PASS_THREADS") ? std::max(32, std::min(kPassThreads, (atoi(getenv("FSB_BIG_PASS_THREADS")) / 32) * 32)) : kPassThreads; }
+    // big shapes: ring_stages > 0 selects the tiled pass (big_pass_tiled; FSB_BIG_TILED=0: whole columns from the CTA's global buffer)
+    if (d.big) {
+        d.ring_stages = (getenv("FSB_BIG_TILED") && atoi(getenv("FSB_BIG_TILED")) == 0) ? 0 : 2;
+        const int dflt = d.ring_stages > 0 ? kBigPassThreads : kPassThreads;  // (tiled: the last warp only feeds the column ring)
+        e->block_pass = getenv("FSB_BIG_PASS_THREADS") ? std::max(64, std::min(dflt, (atoi(getenv("FSB_BIG_PASS_THREADS")) / 32) * 32)) : dflt;
+    }
     int want_ctas = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : (d.ring_stages ? 2 : 4);
     if (const char *ev = getenv("FSB_CTAS_PER_SM")) want_ctas = std::max(1, atoi(ev));
     const int budget = std::min(smem_max, smem_sm / want_ctas - 1024);

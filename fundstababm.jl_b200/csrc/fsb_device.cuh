@@ -236,6 +236,26 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long *bar)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// non-blocking probe (its ~150 cycles overlap with independent work when the result is used later)
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
     asm volatile(

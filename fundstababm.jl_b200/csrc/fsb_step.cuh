@@ -87,9 +87,14 @@ constexpr int kE2Threads = FSB_E2_THREADS;      // CTA of the events-2 kernel
 constexpr int kRingStages = FSB_RING_STAGES;  // per-warp ring of holdings stages (pass kernel, default shape)
 constexpr int kBigStepThreads = 256;   // CTA of the event kernels in the big-shape build (fsb_step_big.cu)
 constexpr int kPassThreads = 256;      // the pass kernel's CTA: 8 warps share the staged columns
+constexpr int kBigPassThreads = 288;   // big shapes, tiled pass: 8 consumer warps + the warp that feeds the column ring
 constexpr int kStageRowBytes = FSB_STAGE_ROW_BYTES;  // bytes of a holdings row per stage (128 per word step)
 constexpr int kStageBytes = 8 * kStageRowBytes;      // a stage = 8 rows
 constexpr int kStagesPerTrip = 2048 / kStageRowBytes;
+constexpr int kBigStages = 4;               // big shapes: column tiles in flight per pass CTA
+constexpr int kBigTileBytes = 1024;         // a tile = 128 assets (8 word steps) of one column
+constexpr int kBigStageBytes = 16 * kBigTileBytes;  // up to 16 columns per chunk
+constexpr int kBigHStages = 4;              // big shapes: per-warp ring of holdings stages (8 rows x kStageRowBytes each)
 #ifndef FSB_FP_INLINE
 #define FSB_FP_INLINE __forceinline__
 #endif
@@ -140,28 +145,29 @@ __host__ __device__ constexpr inline SmemLayout make_layout(int K, int Mp, int N
     L.off_ratio = d; d += (lean || big) ? 0 : L.cp;
     L.off_sellsum = d; d += (lean || big) ? 0 : L.cp;
     L.off_nav = d; d += L.kq;
-    L.off_dstake = d; d += cap;
-    L.off_dcash = d; d += cap;
-    L.off_rinj = d; d += cap;
-    L.off_rfval = d; d += cap;
-    L.off_rncap = d; d += cap;
+    const int ecap = lean ? 0 : cap;  // (the event lists: not used by the pass kernel, which keeps nav, hcols, fmod)
+    L.off_dstake = d; d += ecap;
+    L.off_dcash = d; d += ecap;
+    L.off_rinj = d; d += ecap;
+    L.off_rfval = d; d += ecap;
+    L.off_rncap = d; d += ecap;
     L.off_scal = d; d += 8;
     d = (d + 1) & ~1;
     L.ndoubles = d;
     int i = 0;
-    L.off_rev = i; i += cap;
-    L.off_rfund = i; i += cap;
-    L.off_dinv = i; i += cap;
-    L.off_dfund = i; i += cap;
-    L.off_cash = i; i += cap;
-    L.off_rchoice = i; i += cap;
-    L.off_rcol = i; i += cap;
+    L.off_rev = i; i += ecap;
+    L.off_rfund = i; i += ecap;
+    L.off_dinv = i; i += ecap;
+    L.off_dfund = i; i += ecap;
+    L.off_cash = i; i += ecap;
+    L.off_rchoice = i; i += ecap;
+    L.off_rcol = i; i += ecap;
     L.off_hcols = i; i += cap;
-    L.off_eggs = i; i += cap;
+    L.off_eggs = i; i += ecap;
     L.off_wl = i; i += lean ? 0 : nwarps * cap;
     L.off_wcnt = i; i += 2 * nwarps;
-    L.off_flags = i; i += cap;
-    L.off_nzf = i; i += cap;
+    L.off_flags = i; i += ecap;
+    L.off_nzf = i; i += ecap;
     L.off_pick = i; i += (lean || big) ? 0 : L.cp;
     L.off_fmod = i; i += (K + 31) / 32;
     L.off_fsel = i; i += (K + 31) / 32;
@@ -178,8 +184,10 @@ __host__ __device__ constexpr inline SmemLayout make_layout(int K, int Mp, int N
     L.off_sort = (L.bytes + 15) & ~15;
     if (L.sortn > 0) L.bytes = L.off_sort + L.sortn * 10;  // keys (8 B) + fund indices (2 B)
     L.off_ring = (L.bytes + 127) & ~127;
-    L.off_bars = L.off_ring + nwarps * ring_stages * kStageBytes;
-    if (ring_stages > 0) L.bytes = L.off_bars + nwarps * ring_stages * 8 + nwarps * 8;  // + per-warp running stage counters
+    // default shape: per-warp rings of holdings stages; big shapes: ONE ring of column tiles for the CTA (big_pass_tiled)
+    // (big_pass_tiled: the last warp of the CTA is the producer of the column ring and has no holdings ring)
+    L.off_bars = L.off_ring + (big ? (ring_stages > 0 ? kBigStages * kBigStageBytes + (nwarps - 1) * kBigHStages * kStageBytes : 0) : nwarps * ring_stages * kStageBytes);
+    if (ring_stages > 0) L.bytes = L.off_bars + (big ? (2 * kBigStages + (nwarps - 1) * kBigHStages) * 8 : nwarps * ring_stages * 8 + nwarps * 8);  // + per-warp running stage counters
     L.big_cols = 0;
     L.big_ratio = L.big_cols + 8LL * nslots * L.cpk;
     L.big_sellsum = L.big_ratio + 8LL * L.cp;
@@ -1070,6 +1078,166 @@ __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, con
     if (lane == 0) *gcount = gbase + static_cast<unsigned>(nstages);
     __syncwarp();
 }
+
+#if FSB_BIG
+// ------------------------------------------------------------------------------------------------
+// the holdings pass of big shapes (whole columns do not fit in shared memory): lane arrangement, chains and
+// epilogue of full_pass<C>, but the 2*C columns reach the warps through a CTA-wide ring of kBigStages tiles
+// in shared memory.  A tile = 128 assets (8 word steps) of every column, 1 KB per column, copied by the TMA
+// unit straight from the price ring / the opening prices (no staged copy of whole columns).  All warps walk
+// the tiles in the same order, each against its own 8 rows of the row block (nwarps * 8 rows); the holdings go
+// global -> registers as in full_pass.  full[slot]: the tile's bytes have landed; empty[slot]: every warp is
+// done with it.  The producer (lane 0 of warp 0) runs kBigStages - 2 tiles ahead of its own warp, so the warps
+// may drift apart by two tiles before anyone waits.
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, const int c0, const int cb, const int nreal, const int want_keys)
+{
+    constexpr int R = 4, NS = R * C, S = kBigStages, NC = 2 * C, TW = kBigTileBytes / 16;
+    constexpr int SH = kBigHStages, RW = kStageRowBytes / 16, QS = kStageRowBytes / 128, HPT = kBigTileBytes / kStageRowBytes;
+    static_assert(NC * kBigTileBytes <= kBigStageBytes, "a stage holds 16 column tiles");
+    static_assert((S & (S - 1)) == 0 && (SH & (SH - 1)) == 0 && HPT * kStageRowBytes == kBigTileBytes, "ring shapes");
+    Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
+    FSB_TH;
+    const int K = c.K, K4 = (K + 3) & ~3;
+    const int ntiles = c.Mp >> 7;
+    const int j = lane & 7, q4 = lane >> 3, qa = q4 >> 1, qb = q4 & 1;
+    const int ncw = nwarps - 1;  // consumer warps; warp ncw feeds the column ring
+    const int rows_per_block = 8 * ncw;
+    const int nblocks = (K4 + rows_per_block - 1) / rows_per_block;
+    const int total = nblocks * ntiles, htotal = total * HPT;
+    unsigned char *ring = fsb_smem + c.o_ring;
+    unsigned char *hring = ring + S * kBigStageBytes + warp * (SH * kStageBytes);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(fsb_smem + c.o_bars), *empty = full + S;
+    unsigned long long *hfull = full + 2 * S + warp * SH;
+    __shared__ const double *colsrc[16];
+    __syncthreads();  // the previous chunk is done with the rings and their barriers
+    if (tid < NC) {   // (spare columns re-read the opening prices: finite data, results dropped)
+        const int col = cb + tid;
+        const double *src = G.hand_p;
+        if (tid < nreal && col == 1) src = G.P + static_cast<long long>(pcol(c, t)) * c.Mp;
+        else if (tid < nreal && col >= 2) src = G.P + static_cast<long long>(pcol(c, t - c.hcols_()[c0 + col - 2])) * c.Mp;
+        colsrc[tid] = src;
+    }
+    if (tid == 0) {
+        for (int q = 0; q < 2 * S + ncw * SH; ++q) mbar_inval(full + q);
+        for (int q = 0; q < S; ++q) { mbar_init(full + q, 1); mbar_init(empty + q, ncw); }
+        for (int q = 0; q < ncw * SH; ++q) mbar_init(full + 2 * S + q, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    int is_ti = 0;  // (thread 0) tile index within the row of the next column tile to issue
+    auto issue = [&](int g) {  // column tile g of the CTA's sequence -> slot g % S (one thread)
+        const int slot = g & (S - 1), use = g / S;
+        if (use > 0) mbar_wait(empty + slot, (use - 1) & 1u);
+        mbar_expect_tx(full + slot, NC * kBigTileBytes);
+#pragma unroll 1
+        for (int q = 0; q < NC; ++q)
+            bulk_g2s(ring + slot * kBigStageBytes + q * kBigTileBytes, colsrc[q] + is_ti * (kBigTileBytes / 8), kBigTileBytes, full + slot);
+        if (++is_ti == ntiles) is_ti = 0;
+    };
+    if (warp == ncw) {  // the producer: every tile as soon as its slot is free
+        if (lane == 0)
+            for (int g = 0; g < total; ++g) issue(g);
+        __syncwarp();
+        return;
+    }
+    // the warp's holdings: stage h = 8 rows x kStageRowBytes, ONE tensor copy (rows past K4 - 1 belong to the next
+    // replication or are zero filled: their results are dropped).  (hi_col, hi_row): coordinates of the next stage to issue.
+    const CUtensorMap *const tm = c.tm_h;
+    int hi_col = 0, hi_row = static_cast<int>(c.r) * K4 + 8 * warp, hi_n = 0;
+    auto hissue = [&]() {
+        const int slot = hi_n & (SH - 1);
+        __syncwarp();  // every lane's loads from the slot's previous contents have returned
+        if (lane == 0) {
+            mbar_expect_tx(hfull + slot, kStageBytes);
+            tensor_g2s_2d(hring + slot * kStageBytes, tm, hi_col, hi_row, hfull + slot);
+        }
+        ++hi_n;
+        hi_col += kStageRowBytes / 8;
+        if (hi_col == c.Mp) { hi_col = 0; hi_row += rows_per_block; }
+    };
+#pragma unroll 1
+    for (int h = 0; h < SH - 1 && h < htotal; ++h) hissue();
+    const double *const keep_nav = c.nav_();
+    int g = 0, h = 0;
+    // the barriers are probed one stage ahead (mbar_test does not block and its latency hides behind the stage's FMAs);
+    // the blocking wait runs only when the probe said "not yet"
+    bool tile_ok = false, h_ok = false;
+#pragma unroll 1
+    for (int rb = 0; rb < nblocks; ++rb) {
+        double acc[NS];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) acc[q] = 0.0;
+#pragma unroll 1
+        for (int ti = 0; ti < ntiles; ++ti, ++g) {
+            const int slot = g & (S - 1);
+            if (!tile_ok) mbar_wait(full + slot, static_cast<unsigned>(g / S) & 1u);
+            tile_ok = (g + 1 < total) && mbar_test(full + ((g + 1) & (S - 1)), static_cast<unsigned>((g + 1) / S) & 1u);
+            const double2 *cp_t = reinterpret_cast<const double2 *>(ring + slot * kBigStageBytes) + qb * TW + j;
+#pragma unroll 1
+            for (int part = 0; part < HPT; ++part, ++h) {
+                if (hi_n < htotal) hissue();
+                const int hslot = h & (SH - 1);
+                if (!h_ok) mbar_wait(hfull + hslot, static_cast<unsigned>(h / SH) & 1u);
+                h_ok = (h + 1 < htotal) && mbar_test(hfull + ((h + 1) & (SH - 1)), static_cast<unsigned>((h + 1) / SH) & 1u);
+                const double2 *hs = reinterpret_cast<const double2 *>(hring + hslot * kStageBytes) + (R * qa) * RW + j;
+                const double2 *cp_i = cp_t + RW * part;
+#pragma unroll
+                for (int q = 0; q < QS; ++q) {
+                    double2 hv[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) hv[r] = hs[r * RW + 8 * q];
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) {
+                        const double2 p = cp_i[2 * cc * TW + 8 * q];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            acc[r + R * cc] = fma(hv[r].x, p.x, acc[r + R * cc]);
+                            acc[r + R * cc] = fma(hv[r].y, p.y, acc[r + R * cc]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);
+        }
+        // ---- epilogue of the row block (as full_pass) ----------------------------------------------
+        reduce8_transposed<NS>(acc, j);
+        constexpr int NF = (NS >= 8) ? NS / 8 : 1;
+        const int row0 = rb * rows_per_block + 8 * warp + R * qa;
+        int own[NF];
+#pragma unroll
+        for (int q = 0; q < NF; ++q) own[q] = owned_sum<NS>(j, q);
+        if (cb == 0) {  // column 1 first: the day's NAV is the numerator of every horizon return of the row
+#pragma unroll
+            for (int q = 0; q < NF; ++q) {
+                const int col = qb + 2 * (own[q] >> 2), k = row0 + (own[q] & 3);
+                if (k < K) {
+                    if (col == 0) {
+                        if (!((c.fmod_()[k >> 5] >> (k & 31)) & 1)) G.nav_open[k] = acc[q];
+                    } else if (col == 1) {
+                        c.nav_()[k] = acc[q];
+                        G.nav_close[k] = acc[q];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < NF; ++q) {
+            const int col = cb + qb + 2 * (own[q] >> 2), k = row0 + (own[q] & 3);
+            if (col >= 2 && col - cb < nreal && k < K) {
+                const double navk = keep_nav[k], v = acc[q];
+                const double rho = ddiv(navk - v, v);
+                const unsigned long long word = want_keys ? sort_key(rho) : static_cast<unsigned long long>(__double_as_longlong(rho));
+                __stcg(G.keys + static_cast<long long>(c0 + col - 2) * c.kq + k, word);
+            }
+        }
+    }
+}
+#endif
 
 // nc columns starting at cb are processed by the instantiation with C = 2, 4, 6 or 8 columns per lane
 // (spare columns of finite stale data are multiplied and dropped: cols[] always holds cmax + 2 columns).
@@ -2155,6 +2323,17 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
 #pragma unroll 1
         for (int c0 = 0; c0 == 0 || c0 < ncols; c0 += (c0 == 0 ? cmax : cmax - 2)) {
             const int nc = min(c0 == 0 ? cmax : cmax - 2, ncols - c0);
+#if FSB_BIG
+            if (c.ring_stages > 0) {  // column tiles through shared memory (no staged copy of whole columns)
+                const int cb = c0 == 0 ? 0 : 2, nreal = c0 == 0 ? 2 + nc : nc;
+                if (nreal <= 4) big_pass_tiled<2>(s, t, c0, cb, nreal, want_keys);
+                else if (nreal <= 8) big_pass_tiled<4>(s, t, c0, cb, nreal, want_keys);
+                else if (nreal <= 12) big_pass_tiled<6>(s, t, c0, cb, nreal, want_keys);
+                else big_pass_tiled<8>(s, t, c0, cb, nreal, want_keys);
+                FSB_MARK(10);
+                continue;
+            }
+#endif
             phase_stage_columns(s, t, c0, nc, c0 == 0, false);
             full_pass_dispatch(s, c, c0 == 0 ? 0 : 2, c0 == 0 ? 2 + nc : nc, want_keys, c0);
             __syncthreads();  // (the next chunk overwrites the staged columns)
@@ -2387,11 +2566,19 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         c.ranktab = s.ranktab;
         c.rng.k0 = static_cast<uint32_t>(s.seed); c.rng.k1 = static_cast<uint32_t>(s.seed >> 32);
         mbar_init(&mbar_sh, 1);
+#if FSB_BIG
+        if (KIND == KIND_PASS && s.ring_stages > 0) {  // full[kBigStages], empty[kBigStages]: re-armed by every big_pass_tiled call
+            unsigned long long *rb = reinterpret_cast<unsigned long long *>(fsb_smem + L.off_bars);
+            for (int q = 0; q < kBigStages; ++q) { mbar_init(rb + q, 1); mbar_init(rb + kBigStages + q, nwarps - 1); }
+            for (int q = 0; q < (nwarps - 1) * kBigHStages; ++q) mbar_init(rb + 2 * kBigStages + q, 1);
+        }
+#else
         if (KIND == KIND_PASS && s.ring_stages > 0) {
             unsigned long long *rb = reinterpret_cast<unsigned long long *>(fsb_smem + L.off_bars);
             for (int q = 0; q < nwarps * s.ring_stages; ++q) mbar_init(rb + q, 1);
             for (int q = 0; q < nwarps; ++q) rb[nwarps * s.ring_stages + q] = 0ULL;
         }
+#endif
         fence_mbar_init();
     }
     for (int q = threadIdx.x; q < L.ndoubles; q += blockDim.x) sd[q] = 0.0;  // zero pads once
@@ -2459,7 +2646,12 @@ __global__ void __launch_bounds__(kStepThreads, FSB_EV_CTAS) fsb_events1_kernel(
 {
     phase_kernel_body<KIND_EVENTS1>(s, a, launch_parity, nullptr);
 }
-__global__ void __launch_bounds__(kPassThreads, 2) fsb_pass_kernel(const DevState s, const StepArgs a, const int launch_parity, const __grid_constant__ CUtensorMap tm_h)
+#if FSB_BIG
+__global__ void __launch_bounds__(kBigPassThreads, 1) fsb_pass_kernel(
+#else
+__global__ void __launch_bounds__(kPassThreads, 2) fsb_pass_kernel(
+#endif
+    const DevState s, const StepArgs a, const int launch_parity, const __grid_constant__ CUtensorMap tm_h)
 {
     phase_kernel_body<KIND_PASS>(s, a, launch_parity, &tm_h);
 }
