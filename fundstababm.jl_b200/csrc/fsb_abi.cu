@@ -393,7 +393,8 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
         if (!fn || qres != cudaDriverEntryPointSuccess) return cleanup(fail(FSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver"));
         const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d.Mp), static_cast<cuuint64_t>(R) * ((d.K + 3) & ~3)};
         const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(d.Mp) * 8};
-        const cuuint32_t box[2] = {static_cast<cuuint32_t>(kStageRowBytes / 8), 8}, estr[2] = {1, 1};
+        // (default shape: 8 rows x kStageRowBytes; big shapes: the trip of big_pass_tiled)
+        const cuuint32_t box[2] = {static_cast<cuuint32_t>((d.big ? kBigStageRowBytes : kStageRowBytes) / 8), static_cast<cuuint32_t>(d.big ? kBigStageRows : 8)}, estr[2] = {1, 1};
         const CUresult cr = reinterpret_cast<encode_fn>(fn)(&e->tm_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d.H, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return cleanup(fail(FSB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(cr)));

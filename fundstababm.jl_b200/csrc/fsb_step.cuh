@@ -94,7 +94,14 @@ constexpr int kStagesPerTrip = 2048 / kStageRowBytes;
 constexpr int kBigStages = 4;               // big shapes: column tiles in flight per pass CTA
 constexpr int kBigTileBytes = 1024;         // a tile = 128 assets (8 word steps) of one column
 constexpr int kBigStageBytes = 16 * kBigTileBytes;  // up to 16 columns per chunk
-constexpr int kBigHStages = 4;              // big shapes: per-warp ring of holdings stages (8 rows x kStageRowBytes each)
+#ifndef FSB_BIG_R
+#define FSB_BIG_R 4
+#endif
+constexpr int kBigR = FSB_BIG_R;            // rows per lane in big_pass_tiled: a warp's trip = 2 * kBigR rows
+constexpr int kBigStageRows = 2 * kBigR;    // a holdings stage = kBigStageRows rows x kBigStageRowBytes (one tensor copy)
+constexpr int kBigStageRowBytes = 512;
+constexpr int kBigHStageBytes = kBigStageRows * kBigStageRowBytes;
+constexpr int kBigHStages = 16384 / kBigHStageBytes;  // per-warp ring of holdings stages: 16 KB per warp
 #ifndef FSB_FP_INLINE
 #define FSB_FP_INLINE __forceinline__
 #endif
@@ -186,7 +193,7 @@ __host__ __device__ constexpr inline SmemLayout make_layout(int K, int Mp, int N
     L.off_ring = (L.bytes + 127) & ~127;
     // default shape: per-warp rings of holdings stages; big shapes: ONE ring of column tiles for the CTA (big_pass_tiled)
     // (big_pass_tiled: the last warp of the CTA is the producer of the column ring and has no holdings ring)
-    L.off_bars = L.off_ring + (big ? (ring_stages > 0 ? kBigStages * kBigStageBytes + (nwarps - 1) * kBigHStages * kStageBytes : 0) : nwarps * ring_stages * kStageBytes);
+    L.off_bars = L.off_ring + (big ? (ring_stages > 0 ? kBigStages * kBigStageBytes + (nwarps - 1) * kBigHStages * kBigHStageBytes : 0) : nwarps * ring_stages * kStageBytes);
     if (ring_stages > 0) L.bytes = L.off_bars + (big ? (2 * kBigStages + (nwarps - 1) * kBigHStages) * 8 : nwarps * ring_stages * 8 + nwarps * 8);  // + per-warp running stage counters
     L.big_cols = 0;
     L.big_ratio = L.big_cols + 8LL * nslots * L.cpk;
@@ -1093,10 +1100,11 @@ __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, con
 template <int C>
 __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, const int c0, const int cb, const int nreal, const int want_keys)
 {
-    constexpr int R = 4, NS = R * C, S = kBigStages, NC = 2 * C, TW = kBigTileBytes / 16;
-    constexpr int SH = kBigHStages, RW = kStageRowBytes / 16, QS = kStageRowBytes / 128, HPT = kBigTileBytes / kStageRowBytes;
+    constexpr int R = kBigR, LR = (R == 8) ? 3 : 2, NS = R * C, S = kBigStages, NC = 2 * C, TW = kBigTileBytes / 16;
+    constexpr int SH = kBigHStages, RW = kBigStageRowBytes / 16, QS = kBigStageRowBytes / 128, HPT = kBigTileBytes / kBigStageRowBytes;
+    static_assert(R == 4 || R == 8, "rows per lane");
     static_assert(NC * kBigTileBytes <= kBigStageBytes, "a stage holds 16 column tiles");
-    static_assert((S & (S - 1)) == 0 && (SH & (SH - 1)) == 0 && HPT * kStageRowBytes == kBigTileBytes, "ring shapes");
+    static_assert((S & (S - 1)) == 0 && (SH & (SH - 1)) == 0 && HPT * kBigStageRowBytes == kBigTileBytes, "ring shapes");
     Ctx &c = ctx();
     const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
@@ -1104,11 +1112,11 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
     const int ntiles = c.Mp >> 7;
     const int j = lane & 7, q4 = lane >> 3, qa = q4 >> 1, qb = q4 & 1;
     const int ncw = nwarps - 1;  // consumer warps; warp ncw feeds the column ring
-    const int rows_per_block = 8 * ncw;
+    const int rows_per_block = 2 * R * ncw;
     const int nblocks = (K4 + rows_per_block - 1) / rows_per_block;
     const int total = nblocks * ntiles, htotal = total * HPT;
     unsigned char *ring = fsb_smem + c.o_ring;
-    unsigned char *hring = ring + S * kBigStageBytes + warp * (SH * kStageBytes);
+    unsigned char *hring = ring + S * kBigStageBytes + warp * (SH * kBigHStageBytes);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(fsb_smem + c.o_bars), *empty = full + S;
     unsigned long long *hfull = full + 2 * S + warp * SH;
     __shared__ const double *colsrc[16];
@@ -1143,19 +1151,19 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
         __syncwarp();
         return;
     }
-    // the warp's holdings: stage h = 8 rows x kStageRowBytes, ONE tensor copy (rows past K4 - 1 belong to the next
+    // the warp's holdings: stage h = 2 R rows x kBigStageRowBytes, ONE tensor copy (rows past K4 - 1 belong to the next
     // replication or are zero filled: their results are dropped).  (hi_col, hi_row): coordinates of the next stage to issue.
     const CUtensorMap *const tm = c.tm_h;
-    int hi_col = 0, hi_row = static_cast<int>(c.r) * K4 + 8 * warp, hi_n = 0;
+    int hi_col = 0, hi_row = static_cast<int>(c.r) * K4 + 2 * R * warp, hi_n = 0;
     auto hissue = [&]() {
         const int slot = hi_n & (SH - 1);
         __syncwarp();  // every lane's loads from the slot's previous contents have returned
         if (lane == 0) {
-            mbar_expect_tx(hfull + slot, kStageBytes);
-            tensor_g2s_2d(hring + slot * kStageBytes, tm, hi_col, hi_row, hfull + slot);
+            mbar_expect_tx(hfull + slot, kBigHStageBytes);
+            tensor_g2s_2d(hring + slot * kBigHStageBytes, tm, hi_col, hi_row, hfull + slot);
         }
         ++hi_n;
-        hi_col += kStageRowBytes / 8;
+        hi_col += kBigStageRowBytes / 8;
         if (hi_col == c.Mp) { hi_col = 0; hi_row += rows_per_block; }
     };
 #pragma unroll 1
@@ -1182,7 +1190,7 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
                 const int hslot = h & (SH - 1);
                 if (!h_ok) mbar_wait(hfull + hslot, static_cast<unsigned>(h / SH) & 1u);
                 h_ok = (h + 1 < htotal) && mbar_test(hfull + ((h + 1) & (SH - 1)), static_cast<unsigned>((h + 1) / SH) & 1u);
-                const double2 *hs = reinterpret_cast<const double2 *>(hring + hslot * kStageBytes) + (R * qa) * RW + j;
+                const double2 *hs = reinterpret_cast<const double2 *>(hring + hslot * kBigHStageBytes) + (R * qa) * RW + j;
                 const double2 *cp_i = cp_t + RW * part;
 #pragma unroll
                 for (int q = 0; q < QS; ++q) {
@@ -1206,14 +1214,14 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
         // ---- epilogue of the row block (as full_pass) ----------------------------------------------
         reduce8_transposed<NS>(acc, j);
         constexpr int NF = (NS >= 8) ? NS / 8 : 1;
-        const int row0 = rb * rows_per_block + 8 * warp + R * qa;
+        const int row0 = rb * rows_per_block + 2 * R * warp + R * qa;
         int own[NF];
 #pragma unroll
         for (int q = 0; q < NF; ++q) own[q] = owned_sum<NS>(j, q);
         if (cb == 0) {  // column 1 first: the day's NAV is the numerator of every horizon return of the row
 #pragma unroll
             for (int q = 0; q < NF; ++q) {
-                const int col = qb + 2 * (own[q] >> 2), k = row0 + (own[q] & 3);
+                const int col = qb + 2 * (own[q] >> LR), k = row0 + (own[q] & (R - 1));
                 if (k < K) {
                     if (col == 0) {
                         if (!((c.fmod_()[k >> 5] >> (k & 31)) & 1)) G.nav_open[k] = acc[q];
@@ -1227,7 +1235,7 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
         }
 #pragma unroll
         for (int q = 0; q < NF; ++q) {
-            const int col = cb + qb + 2 * (own[q] >> 2), k = row0 + (own[q] & 3);
+            const int col = cb + qb + 2 * (own[q] >> LR), k = row0 + (own[q] & (R - 1));
             if (col >= 2 && col - cb < nreal && k < K) {
                 const double navk = keep_nav[k], v = acc[q];
                 const double rho = ddiv(navk - v, v);
@@ -1244,7 +1252,7 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
 // c.fast: Mp == 256 and K <= 256 (the default shape): strides and trip counts are compile-time constants.
 __device__ __forceinline__ void full_pass_dispatch(const DevState &s, Ctx &c, int cb, int nc, int want_keys, int kcol0)
 {
-    if (c.fast && c.ring_stages > 0) {
+    if (!FSB_BIG && c.fast && c.ring_stages > 0) {
         if (nc <= 4) full_pass_tma<2>(s, cb, nc, want_keys, kcol0, 0);
         else if (nc <= 8) full_pass_tma<4>(s, cb, nc, want_keys, kcol0, 0);
         else if (nc <= 12) full_pass_tma<6>(s, cb, nc, want_keys, kcol0, 0);
@@ -2313,7 +2321,7 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
     __syncthreads();
     if (open_day) {  // nav_open = nav_close = H * p_open
         phase_stage_columns(s, t, 0, 0, true, true);
-        if (c.fast && c.ring_stages > 0) full_pass_tma<2>(s, 0, 1, 0, 0, 1);
+        if (!FSB_BIG && c.fast && c.ring_stages > 0) full_pass_tma<2>(s, 0, 1, 0, 0, 1);  // (big build: ring_stages marks the tiled pass)
         else if (c.fast) full_pass<1, true, true>(s, 0, 1, 0, 0);
         else full_pass<1, true, false>(s, 0, 1, 0, 0);
     } else {

@@ -578,7 +578,7 @@ def test_large_shapes_general_path(fsb, orc, shape):
 
 @pytest.mark.parametrize("shape,R", [
     (dict(bigk=64, bign=256, bigm=5000, bigt=125, portfsizerange=(2500, 5000), reviewprobability=0.1), 3),
-    (dict(bigk=2000, bign=8000, bigm=5000, bigt=104, portfsizerange=(2500, 5000)), 1),
+    (dict(bigk=2000, bign=8000, bigm=5000, bigt=110, portfsizerange=(2500, 5000)), 1),
 ], ids=["K64_M5000", "config4_K2000_M5000_N8000"])
 def test_big_shapes_per_asset_arrays_in_global_memory(fsb, orc, shape, R):
     """BASELINE.json configs[3] (2000 funds x 5000 assets, dense overlapping portfolios, N = 4K investors, W = 100)
