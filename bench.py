@@ -265,10 +265,11 @@ def roofline(params, R, steps, m, world, value):
     achieved = reps_per_launch * K * b_alg_pass(K, M, N) / (per_launch_ms * 1e-3) / 1e9
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
-    if os.path.exists(tr_path) and (K, M) == (250, 250):
+    if os.path.exists(tr_path) and (K, M) in ((250, 250), (2000, 5000)):
         try:
             with open(tr_path) as f:
-                traffic = json.load(f)["dram_bytes_per_replication_step"] * reps_per_launch
+                tj = json.load(f)
+            traffic = (tj if K == 250 else tj["config4"])["dram_bytes_per_replication_step"] * reps_per_launch
         except Exception:
             traffic = None
     whole = value / world * b_alg(K, M, N) / 1e9

@@ -33,6 +33,7 @@ struct DevState {
     unsigned char *bigbuf; // [2 * batches][scratch_ctas][big_stride]
     int scan_choice;       // FSB_SCAN_CHOICE=1: the rank rule is sampled by the floating-point scan only (no integer shortcut; tests)
     int ring_stages;       // per-warp holdings ring of the pass kernel (kRingStages on the default shape, else 0)
+    int pass_parts;        // big shapes, tiled pass: a replication's rows are split into this many work units (>= 1)
     int n_points;
     long long R, rep_offset, reps_per_point;
     long long h_stride;  // doubles per replication in H

@@ -274,6 +274,7 @@ struct Ctx {
     fsb_trace_rec *tr_recs;
     int *tr_n;
     long long r;
+    int part, nparts;  // big shapes, tiled pass: this CTA's share of the replication's row blocks
     long long tmark;
     // accessors
 #if FSB_BIG
@@ -485,7 +486,7 @@ static __device__ __noinline__ void trace_phase(int t, int which, int n0, int n1
     } else if (which == 2) {
         for (int m = tid; m < c.M; m += NT) c.tr_presp[m + c.M * col] = p_cur(c)[m];
     } else if (which == 3) {
-        for (int k = tid; k < c.K; k += NT) c.tr_nav[k + c.K * col] = c.nav_open[k];
+        for (int k = n0 + tid; k < (n1 > 0 ? n1 : c.K); k += NT) c.tr_nav[k + c.K * col] = c.nav_open[k];  // (n1 > 0: rows [n0, n1) only)
     } else if (which == 4) {
         if (tid == 0)
             for (int i = 0; i < n0; ++i) trace_emit(c, t, FSB_EV_CHOICE, c.cash_()[i], c.r_choice_()[i], c.r_inj_()[i]);
@@ -1113,7 +1114,9 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
     const int j = lane & 7, q4 = lane >> 3, qa = q4 >> 1, qb = q4 & 1;
     const int ncw = nwarps - 1;  // consumer warps; warp ncw feeds the column ring
     const int rows_per_block = 2 * R * ncw;
-    const int nblocks = (K4 + rows_per_block - 1) / rows_per_block;
+    const int nblocks_all = (K4 + rows_per_block - 1) / rows_per_block;
+    const int rb_begin = (c.part * nblocks_all) / c.nparts, rb_end = ((c.part + 1) * nblocks_all) / c.nparts;  // this work unit's row blocks
+    const int nblocks = rb_end - rb_begin;
     const int total = nblocks * ntiles, htotal = total * HPT;
     unsigned char *ring = fsb_smem + c.o_ring;
     unsigned char *hring = ring + S * kBigStageBytes + warp * (SH * kBigHStageBytes);
@@ -1154,7 +1157,7 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
     // the warp's holdings: stage h = 2 R rows x kBigStageRowBytes, ONE tensor copy (rows past K4 - 1 belong to the next
     // replication or are zero filled: their results are dropped).  (hi_col, hi_row): coordinates of the next stage to issue.
     const CUtensorMap *const tm = c.tm_h;
-    int hi_col = 0, hi_row = static_cast<int>(c.r) * K4 + 2 * R * warp, hi_n = 0;
+    int hi_col = 0, hi_row = static_cast<int>(c.r) * K4 + rb_begin * rows_per_block + 2 * R * warp, hi_n = 0;
     auto hissue = [&]() {
         const int slot = hi_n & (SH - 1);
         __syncwarp();  // every lane's loads from the slot's previous contents have returned
@@ -1174,7 +1177,7 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
     // the blocking wait runs only when the probe said "not yet"
     bool tile_ok = false, h_ok = false;
 #pragma unroll 1
-    for (int rb = 0; rb < nblocks; ++rb) {
+    for (int rb = rb_begin; rb < rb_end; ++rb) {
         double acc[NS];
 #pragma unroll
         for (int q = 0; q < NS; ++q) acc[q] = 0.0;
@@ -2320,6 +2323,9 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
     for (int q = tid; q < ncols; q += NT) c.hcols_()[q] = hi[HI_FMOD + nf + q];
     __syncthreads();
     if (open_day) {  // nav_open = nav_close = H * p_open
+#if FSB_BIG
+        if (c.part != 0) return;  // (one column: the first work unit of the replication takes all rows)
+#endif
         phase_stage_columns(s, t, 0, 0, true, true);
         if (!FSB_BIG && c.fast && c.ring_stages > 0) full_pass_tma<2>(s, 0, 1, 0, 0, 1);  // (big build: ring_stages marks the tiled pass)
         else if (c.fast) full_pass<1, true, true>(s, 0, 1, 0, 0);
@@ -2327,29 +2333,44 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
     } else {
         const int cmax = c.cmax;
         const int want_keys = (selector == FSB_SEL_PROBABILISTIC) ? 1 : 0;
-        // first chunk: the two price columns + up to cmax horizons; later chunks: up to cmax - 2 horizons
-#pragma unroll 1
-        for (int c0 = 0; c0 == 0 || c0 < ncols; c0 += (c0 == 0 ? cmax : cmax - 2)) {
-            const int nc = min(c0 == 0 ? cmax : cmax - 2, ncols - c0);
 #if FSB_BIG
-            if (c.ring_stages > 0) {  // column tiles through shared memory (no staged copy of whole columns)
+        if (c.ring_stages > 0) {
+            // column tiles through shared memory (no staged copy of whole columns); chunks of up to 16 columns: the two
+            // price columns + 14 horizons, then 16 horizons per chunk (every chunk re-reads the holdings)
+#pragma unroll 1
+            for (int c0 = 0; c0 == 0 || c0 < ncols;) {
+                const int nc = min(c0 == 0 ? 14 : 16, ncols - c0);
                 const int cb = c0 == 0 ? 0 : 2, nreal = c0 == 0 ? 2 + nc : nc;
                 if (nreal <= 4) big_pass_tiled<2>(s, t, c0, cb, nreal, want_keys);
                 else if (nreal <= 8) big_pass_tiled<4>(s, t, c0, cb, nreal, want_keys);
                 else if (nreal <= 12) big_pass_tiled<6>(s, t, c0, cb, nreal, want_keys);
                 else big_pass_tiled<8>(s, t, c0, cb, nreal, want_keys);
                 FSB_MARK(10);
-                continue;
+                c0 += (nc > 0) ? nc : 1;
             }
+        } else
 #endif
-            phase_stage_columns(s, t, c0, nc, c0 == 0, false);
-            full_pass_dispatch(s, c, c0 == 0 ? 0 : 2, c0 == 0 ? 2 + nc : nc, want_keys, c0);
-            __syncthreads();  // (the next chunk overwrites the staged columns)
-            FSB_MARK(10);
+        {
+            // first chunk: the two price columns + up to cmax horizons; later chunks: up to cmax - 2 horizons
+#pragma unroll 1
+            for (int c0 = 0; c0 == 0 || c0 < ncols; c0 += (c0 == 0 ? cmax : cmax - 2)) {
+                const int nc = min(c0 == 0 ? cmax : cmax - 2, ncols - c0);
+                phase_stage_columns(s, t, c0, nc, c0 == 0, false);
+                full_pass_dispatch(s, c, c0 == 0 ? 0 : 2, c0 == 0 ? 2 + nc : nc, want_keys, c0);
+                __syncthreads();  // (the next chunk overwrites the staged columns)
+                FSB_MARK(10);
+            }
         }
     }
     if (c.trace >= 0) {
         __syncthreads();
+#if FSB_BIG
+        if (!open_day && c.ring_stages > 0 && c.nparts > 1) {  // this work unit's rows (the others are written by other CTAs)
+            const int rpb = 2 * kBigR * (nwarps - 1), nb = (((c.K + 3) & ~3) + rpb - 1) / rpb;
+            const int k0 = ((c.part * nb) / c.nparts) * rpb, k1 = min(c.K, (((c.part + 1) * nb) / c.nparts) * rpb);
+            if (k1 > k0) trace_phase(t, 3, k0, k1);
+        } else
+#endif
         trace_phase(t, 3, 0, 0);
     }
 }
@@ -2603,7 +2624,13 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
     for (;;) {
         if (threadIdx.x == 0) r_sh = atomicAdd(&queue[launch_parity], 1);
         __syncthreads();
+#if FSB_BIG
+        const int nparts = (KIND == KIND_PASS && s.ring_stages > 0) ? s.pass_parts : 1;  // pass: (replication, part) work units
+        const long long r = a.r_begin + r_sh / nparts;
+        if (threadIdx.x == 0) { c.part = static_cast<int>(r_sh % nparts); c.nparts = nparts; }
+#else
         const long long r = a.r_begin + r_sh;
+#endif
         if (r >= a.r_end) break;
         const int frozen = s.err[r] & ~FSB_REP_TRACE_OVERFLOW;
         if (threadIdx.x < kRepPtrs && !frozen) {  // one lane per pointer: base + r * stride
