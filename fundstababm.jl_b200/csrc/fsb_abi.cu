@@ -290,9 +290,9 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
         e->block_pass = getenv("FSB_BIG_PASS_THREADS") ? std::max(64, std::min(dflt, (atoi(getenv("FSB_BIG_PASS_THREADS")) / 32) * 32)) : dflt;
     }
     d.pass_parts = 1;
-    if (d.big && d.ring_stages > 0) {  // up to 4 work units per replication (whole row blocks each): an even finish of the pass kernel's persistent CTAs
+    if (d.big && d.ring_stages > 0) {  // up to 8 work units per replication (whole row blocks each): an even finish of the pass kernel's persistent CTAs
         const int rpb = 2 * kBigR * (e->block_pass / 32 - 1), nblocks = (((d.K + 3) & ~3) + rpb - 1) / rpb;
-        d.pass_parts = std::max(1, std::min(getenv("FSB_PASS_PARTS") ? atoi(getenv("FSB_PASS_PARTS")) : 4, nblocks));
+        d.pass_parts = std::max(1, std::min(getenv("FSB_PASS_PARTS") ? atoi(getenv("FSB_PASS_PARTS")) : 8, nblocks));
     }
     int want_ctas = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : (d.ring_stages ? 2 : 4);
     if (const char *ev = getenv("FSB_CTAS_PER_SM")) want_ctas = std::max(1, atoi(ev));
