@@ -290,9 +290,11 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
         e->block_pass = getenv("FSB_BIG_PASS_THREADS") ? std::max(64, std::min(dflt, (atoi(getenv("FSB_BIG_PASS_THREADS")) / 32) * 32)) : dflt;
     }
     d.pass_parts = 1;
-    if (d.big && d.ring_stages > 0) {  // up to 8 work units per replication (whole row blocks each): an even finish of the pass kernel's persistent CTAs
-        const int rpb = 2 * kBigR * (e->block_pass / 32 - 1), nblocks = (((d.K + 3) & ~3) + rpb - 1) / rpb;
-        d.pass_parts = std::max(1, std::min(getenv("FSB_PASS_PARTS") ? atoi(getenv("FSB_PASS_PARTS")) : 8, nblocks));
+    d.pass_chunks = 1;
+    if (d.big && d.ring_stages > 0) {  // up to 9 work units per replication (whole row blocks each): an even finish of the pass kernel's persistent CTAs
+        const int rpb = 2 * kBigR * (e->block_pass / 32 - kBigProd), nblocks = (((d.K + 3) & ~3) + rpb - 1) / rpb;  // (config 4: 36 blocks of 56 rows)
+        d.pass_parts = std::max(1, std::min(getenv("FSB_PASS_PARTS") ? atoi(getenv("FSB_PASS_PARTS")) : 9, nblocks));
+        d.pass_chunks = std::max(1, std::min(getenv("FSB_PASS_CHUNKS") ? atoi(getenv("FSB_PASS_CHUNKS")) : 3, 8));
     }
     int want_ctas = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : (d.ring_stages ? 2 : 4);
     if (const char *ev = getenv("FSB_CTAS_PER_SM")) want_ctas = std::max(1, atoi(ev));
@@ -333,10 +335,11 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
             if (cfg->blocks_per_sm > 0 && k == 1) occ = std::min(occ, cfg->blocks_per_sm);
             if (const char *ev = getenv(k == 1 ? "FSB_PASS_CTAS" : "FSB_EVENT_CTAS")) occ = std::min(occ, std::max(1, atoi(ev)));
             e->occ[k] = occ;
-            e->grid[k] = static_cast<int>(std::min<long long>(d.R * (k == 1 ? d.pass_parts : 1), static_cast<long long>(sms) * occ));
+            e->grid[k] = static_cast<int>(std::min<long long>(d.R * (k == 1 ? d.pass_parts * d.pass_chunks : 1), static_cast<long long>(sms) * occ));
         }
     }
     d.scan_choice = (getenv("FSB_SCAN_CHOICE") && atoi(getenv("FSB_SCAN_CHOICE")) > 0) ? 1 : 0;
+    d.smem_sort = (getenv("FSB_SMEM_SORT") && atoi(getenv("FSB_SMEM_SORT")) > 0) ? 1 : 0;
     e->fast = (d.K <= 256);
     // the default Params shape exactly: the event and choice kernels of the fixed-shape build (FSB_NO_FIXED=1: generic build)
     e->fixed = (!d.big && d.K == kFixedK && d.M == kFixedM && d.N == kFixedN && d.W == kFixedW && d.cap_ev == kFixedCap && d.slots_a == kFixedSlots &&
@@ -800,7 +803,7 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                     CU(cudaMemcpyAsync(e->st_zstock + a.r_begin * d.M, ht->z_stock + a.r_begin * d.M, rb * d.M * 8, cudaMemcpyHostToDevice, st));
                     CU(cudaMemcpyAsync(e->st_urev + a.r_begin * d.N, ht->u_review + a.r_begin * d.N, rb * d.N * 8, cudaMemcpyHostToDevice, st));
                 }
-                const unsigned g1 = static_cast<unsigned>(std::min<long long>(rb, e->grid[0])), g2 = static_cast<unsigned>(std::min<long long>(rb * d.pass_parts, e->grid[1])),
+                const unsigned g1 = static_cast<unsigned>(std::min<long long>(rb, e->grid[0])), g2 = static_cast<unsigned>(std::min<long long>(rb * d.pass_parts * d.pass_chunks, e->grid[1])),
                                g3 = static_cast<unsigned>(std::min<long long>(rb, e->grid[2]));
 #if FSB_SPLIT_CHOICE
                 if (!d.big) fsb_draws_kernel<<<static_cast<unsigned>(std::min<long long>((rb + 7) / 8, static_cast<long long>(e->sms) * 8)), 256, 0, st>>>(d, a);

@@ -32,8 +32,10 @@ struct DevState {
     long long big_stride;  // bytes of a CTA's global buffer for those arrays
     unsigned char *bigbuf; // [2 * batches][scratch_ctas][big_stride]
     int scan_choice;       // FSB_SCAN_CHOICE=1: the rank rule is sampled by the floating-point scan only (no integer shortcut; tests)
+    int smem_sort;         // FSB_SMEM_SORT=1: 256 < K <= 2048 ranks by the shared-memory network only (no register network; tests)
     int ring_stages;       // per-warp holdings ring of the pass kernel (kRingStages on the default shape, else 0)
     int pass_parts;        // big shapes, tiled pass: a replication's rows are split into this many work units (>= 1)
+    int pass_chunks;       // ... and a day's column chunks into this many (>= 1; 1: every work unit loops over all chunks)
     int n_points;
     long long R, rep_offset, reps_per_point;
     long long h_stride;  // doubles per replication in H

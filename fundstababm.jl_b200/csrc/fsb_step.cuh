@@ -87,21 +87,48 @@ constexpr int kE2Threads = FSB_E2_THREADS;      // CTA of the events-2 kernel
 constexpr int kRingStages = FSB_RING_STAGES;  // per-warp ring of holdings stages (pass kernel, default shape)
 constexpr int kBigStepThreads = 256;   // CTA of the event kernels in the big-shape build (fsb_step_big.cu)
 constexpr int kPassThreads = 256;      // the pass kernel's CTA: 8 warps share the staged columns
-constexpr int kBigPassThreads = 288;   // big shapes, tiled pass: 8 consumer warps + the warp that feeds the column ring
+#ifndef FSB_BIG_PASS_THREADS
+#define FSB_BIG_PASS_THREADS 256
+#endif
+#ifndef FSB_BIG_NCOLS
+#define FSB_BIG_NCOLS 16
+#endif
+#ifndef FSB_BIG_TILE_BYTES
+#define FSB_BIG_TILE_BYTES 1024
+#endif
+// big shapes, tiled pass: 7 consumer warps + the warp that feeds the column ring.  (Eight warps = two per scheduler leave a
+// thread 255 registers, nine would leave 168: the 48 accumulators of a 24-column chunk need the former.)
+constexpr int kBigPassThreads = FSB_BIG_PASS_THREADS;
+#ifndef FSB_BIG_NOPROD
+#define FSB_BIG_NOPROD 0
+#endif
+// FSB_BIG_NOPROD=1: no producer warp -- the warp that arrives LAST at a column tile issues the copies of the tile that takes
+// its slot (a shared-memory counter per slot instead of the `empty` barrier), so all 8 warps of a 256-thread CTA compute
+constexpr int kBigProd = FSB_BIG_NOPROD ? 0 : 1;
 constexpr int kStageRowBytes = FSB_STAGE_ROW_BYTES;  // bytes of a holdings row per stage (128 per word step)
 constexpr int kStageBytes = 8 * kStageRowBytes;      // a stage = 8 rows
 constexpr int kStagesPerTrip = 2048 / kStageRowBytes;
-constexpr int kBigStages = 4;               // big shapes: column tiles in flight per pass CTA
-constexpr int kBigTileBytes = 1024;         // a tile = 128 assets (8 word steps) of one column
-constexpr int kBigStageBytes = 16 * kBigTileBytes;  // up to 16 columns per chunk
+#ifndef FSB_BIG_STAGES
+#define FSB_BIG_STAGES 4
+#endif
+constexpr int kBigStages = FSB_BIG_STAGES;  // big shapes: column tiles in flight per pass CTA
+constexpr int kBigTileBytes = FSB_BIG_TILE_BYTES;   // a tile = 64 assets (4 word steps) of one column
+constexpr int kBigCols = FSB_BIG_NCOLS;             // columns per chunk = per read of the holdings (a multiple of 4, <= 24)
+constexpr int kBigStageBytes = kBigCols * kBigTileBytes;
 #ifndef FSB_BIG_R
-#define FSB_BIG_R 4
+#define FSB_BIG_R 8
 #endif
 constexpr int kBigR = FSB_BIG_R;            // rows per lane in big_pass_tiled: a warp's trip = 2 * kBigR rows
 constexpr int kBigStageRows = 2 * kBigR;    // a holdings stage = kBigStageRows rows x kBigStageRowBytes (one tensor copy)
-constexpr int kBigStageRowBytes = 512;
+#ifndef FSB_BIG_ROW_BYTES
+#define FSB_BIG_ROW_BYTES 512
+#endif
+#ifndef FSB_BIG_HRING_BYTES
+#define FSB_BIG_HRING_BYTES 16384
+#endif
+constexpr int kBigStageRowBytes = FSB_BIG_ROW_BYTES;
 constexpr int kBigHStageBytes = kBigStageRows * kBigStageRowBytes;
-constexpr int kBigHStages = 16384 / kBigHStageBytes;  // per-warp ring of holdings stages: 16 KB per warp
+constexpr int kBigHStages = FSB_BIG_HRING_BYTES / kBigHStageBytes;  // per-warp ring of holdings stages: 16 KB per warp
 #ifndef FSB_FP_INLINE
 #define FSB_FP_INLINE __forceinline__
 #endif
@@ -193,8 +220,8 @@ __host__ __device__ constexpr inline SmemLayout make_layout(int K, int Mp, int N
     L.off_ring = (L.bytes + 127) & ~127;
     // default shape: per-warp rings of holdings stages; big shapes: ONE ring of column tiles for the CTA (big_pass_tiled)
     // (big_pass_tiled: the last warp of the CTA is the producer of the column ring and has no holdings ring)
-    L.off_bars = L.off_ring + (big ? (ring_stages > 0 ? kBigStages * kBigStageBytes + (nwarps - 1) * kBigHStages * kBigHStageBytes : 0) : nwarps * ring_stages * kStageBytes);
-    if (ring_stages > 0) L.bytes = L.off_bars + (big ? (2 * kBigStages + (nwarps - 1) * kBigHStages) * 8 : nwarps * ring_stages * 8 + nwarps * 8);  // + per-warp running stage counters
+    L.off_bars = L.off_ring + (big ? (ring_stages > 0 ? kBigStages * kBigStageBytes + (nwarps - kBigProd) * kBigHStages * kBigHStageBytes : 0) : nwarps * ring_stages * kStageBytes);
+    if (ring_stages > 0) L.bytes = L.off_bars + (big ? (2 * kBigStages + (nwarps - kBigProd) * kBigHStages) * 8 : nwarps * ring_stages * 8 + nwarps * 8);  // + per-warp running stage counters
     L.big_cols = 0;
     L.big_ratio = L.big_cols + 8LL * nslots * L.cpk;
     L.big_sellsum = L.big_ratio + 8LL * L.cp;
@@ -275,6 +302,7 @@ struct Ctx {
     int *tr_n;
     long long r;
     int part, nparts;  // big shapes, tiled pass: this CTA's share of the replication's row blocks
+    int chunk, nchunks;  // ... and of the day's column chunks (work units of one (replication, part) run side by side: L2 reuse)
     long long tmark;
     // accessors
 #if FSB_BIG
@@ -643,7 +671,7 @@ __device__ __forceinline__ int select_fund_prob(Ctx &c, int t, int inv, const do
     const int K = c.K;
     if (cum) {
         const double x = u * (0.5 * static_cast<double>(K) * static_cast<double>(K + 1));
-        if (fabs(x - rint(x)) > 1e-6) {
+        if (fabs(x - rint(x)) > 1e-6) {  // (K <= 256 here: the bound above is 4e-9)
             int lo = 0, hi = K - 1;
 #pragma unroll 1
             while (lo < hi) {
@@ -779,8 +807,7 @@ static __device__ __noinline__ void warp_rank_count(const unsigned long long *ke
 // Rank of 256 < K <= 2048 keys by the whole CTA: bitonic network over (key, fund index) pairs in shared memory,
 // ordered lexicographically -- the stable ascending order itself, so no repair pass.  P = K rounded up to a power
 // of two; the padding sorts last (largest key, indices >= K).  All threads of the CTA must call this.
-static __device__ __noinline__ void block_rank_sort(const unsigned long long *keys, int K, int P, unsigned long long *sk, unsigned short *si,
-                                                   double *prob, const double *ranktab)
+static __device__ __noinline__ void block_rank_sort(const unsigned long long *keys, int K, int P, unsigned long long *sk, unsigned short *si)
 {
     const int tid = threadIdx.x, NT = blockDim.x;
     for (int e = tid; e < P; e += NT) {
@@ -803,8 +830,151 @@ static __device__ __noinline__ void block_rank_sort(const unsigned long long *ke
             __syncthreads();
         }
     }
-    for (int e = tid; e < K; e += NT) prob[si[e]] = __ldg(ranktab + e);  // prob may alias sk (not si): the last stage ended with a barrier
+}
+
+// lexicographic order of (key, fund index) pairs: the stable ascending order of the keys
+__device__ __forceinline__ bool pair_less(unsigned long long ka, unsigned ia, unsigned long long kb, unsigned ib)
+{
+    return ka < kb || (ka == kb && ia < ib);
+}
+
+// The same network for P == 8 * blockDim.x with the pairs in REGISTERS: thread tid owns the positions 8 tid .. 8 tid + 7, so
+// the strides 1, 2, 4 stay inside a thread, 8 .. 128 cross lanes (shuffles) and only the strides >= 256 (6 of the 66 stages at
+// P = 2048) cross warps through shared memory (xk / xi: P words each, position-of-thread major, conflict free).  Ends with
+// the RANKS in fund order: rk16[k] = rank_k (1-based).  rk16 may alias xk.  All threads of the CTA must call this.
+static __device__ __noinline__ void block_rank_sort_reg(const unsigned long long *keys, int K, unsigned long long *xk, unsigned short *xi,
+                                                       unsigned short *rk16)
+{
+    const int tid = threadIdx.x, NT = blockDim.x, P = 8 * NT;
+    unsigned long long kk[8];
+    unsigned ii[8];
+    {
+        const ulonglong2 *k2p = reinterpret_cast<const ulonglong2 *>(keys) + tid * 4;  // key rows are padded to a multiple of 4 entries
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = tid * 8 + 2 * r;
+            ulonglong2 w = make_ulonglong2(~0ULL, ~0ULL);
+            if (e < K) w = __ldcg(k2p + r);
+            kk[2 * r] = (e < K) ? w.x : ~0ULL;
+            kk[2 * r + 1] = (e + 1 < K) ? w.y : ~0ULL;
+            ii[2 * r] = static_cast<unsigned>(e);
+            ii[2 * r + 1] = static_cast<unsigned>(e + 1);
+        }
+    }
+#pragma unroll 1
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        const bool up_t = (((tid * 8) & k2) == 0);  // (k2 >= 8: the direction is the thread's)
+#pragma unroll 1
+        for (int tm = k2 >> 4; tm > 0; tm >>= 1) {  // tm = stride / 8: the partner is thread tid ^ tm, same slot r
+            const bool keepmin = (((tid & tm) == 0) == up_t);
+            if (tm >= 32) {
+                __syncthreads();  // (the previous exchange has been read)
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { xk[r * NT + tid] = kk[r]; xi[r * NT + tid] = static_cast<unsigned short>(ii[r]); }
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const unsigned long long ok = xk[r * NT + (tid ^ tm)];
+                    const unsigned oi = xi[r * NT + (tid ^ tm)];
+                    const bool take = (pair_less(ok, oi, kk[r], ii[r]) == keepmin);
+                    kk[r] = take ? ok : kk[r];
+                    ii[r] = take ? oi : ii[r];
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, kk[r], tm);
+                    const unsigned oi = __shfl_xor_sync(0xffffffffu, ii[r], tm);
+                    const bool take = (pair_less(ok, oi, kk[r], ii[r]) == keepmin);
+                    kk[r] = take ? ok : kk[r];
+                    ii[r] = take ? oi : ii[r];
+                }
+            }
+        }
+#pragma unroll
+        for (int j2 = 4; j2 > 0; j2 >>= 1) {
+            if (j2 < k2) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    if ((r & j2) == 0) {
+                        const bool up = (k2 >= 8) ? up_t : ((r & k2) == 0);
+                        const bool sw = (pair_less(kk[r | j2], ii[r | j2], kk[r], ii[r]) == up);
+                        const unsigned long long xk_ = kk[r], yk = kk[r | j2];
+                        const unsigned xi_ = ii[r], yi = ii[r | j2];
+                        kk[r] = sw ? yk : xk_; kk[r | j2] = sw ? xk_ : yk;
+                        ii[r] = sw ? yi : xi_; ii[r | j2] = sw ? xi_ : yi;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();  // (the last exchange has been read: rk16 may alias xk)
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        if (ii[r] < static_cast<unsigned>(K)) rk16[ii[r]] = static_cast<unsigned short>(tid * 8 + r + 1);
     __syncthreads();
+}
+
+// Exact integer prefix sums of the ranks in fund order, by the whole CTA: cum[q] = rank_0 + .. + rank_q (<= K (K + 1) / 2 < 2^31).
+// Thread tid owns the funds per * tid .. per * tid + per - 1 (per = P / blockDim.x); wtot: one word per warp.
+static __device__ __noinline__ void block_rank_prefix(const unsigned short *rk16, int K, int P, int *cum, int *wtot)
+{
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, per = P / NT;
+    const int k0 = tid * per;
+    int tot = 0;
+    for (int q = 0; q < per; ++q) tot += (k0 + q < K) ? static_cast<int>(rk16[k0 + q]) : 0;
+    int incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += x;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    int base = incl - tot;
+    for (int w = 0; w < warp; ++w) base += wtot[w];
+    for (int q = 0; q < per; ++q) {
+        if (k0 + q < K) { base += static_cast<int>(rk16[k0 + q]); cum[k0 + q] = base; }
+    }
+    __syncthreads();
+}
+
+// select_fund_prob for the CTA-ranked columns (256 < K <= 2048): the ranks in fund order (rk16) and their exact prefix sums.
+// The bound of select_fund_prob in units of C is (K + 1) 2^-53 S = 4.4e-7 at K = 2000, so the guard grows with K; the draws
+// inside the guard (and FSB_SCAN_CHOICE=1) take the reference's scan over p_k = ranktab[rank_k - 1].
+__device__ __forceinline__ int select_fund_ranked(Ctx &c, int t, int inv, const unsigned short *rk16, const int *cum, const bool scan_only)
+{
+    double forced;
+    if (c.tape && tape_lookup(c, FSB_TAPE_CHOICE_IDX, t, inv, 0, &forced)) return static_cast<int>(forced);
+    double u;
+    if (c.tape) {
+        if (!tape_lookup(c, FSB_TAPE_CHOICE_U, t, inv, 0, &u)) { atomicOr(&c.isc_()[I_ERR], FSB_REP_TAPE_MISSING); return 0; }
+    } else {
+        const uint4 w = draw_block_s(c.rng, SITE_CHOICE, static_cast<uint32_t>(t), 0, static_cast<uint32_t>(inv));
+        u = u52(w.x, w.y);
+    }
+    const int K = c.K;
+    if (!scan_only) {
+        const double S = 0.5 * static_cast<double>(K) * static_cast<double>(K + 1);
+        const double x = u * S, guard = fmax(1e-6, 4.0 * static_cast<double>(K + 1) * 1.1102230246251565e-16 * S);
+        if (fabs(x - rint(x)) > guard) {
+            int lo = 0, hi = K - 1;
+#pragma unroll 1
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (static_cast<double>(cum[mid]) >= x) hi = mid; else lo = mid + 1;
+            }
+            return lo;
+        }
+    }
+    double cp = 0.0;
+    int i = 0;
+#pragma unroll 1
+    while (cp < u && i < K) {
+        cp = cp + __ldg(c.ranktab + (static_cast<int>(rk16[i]) - 1));
+        ++i;
+    }
+    return (i > 0) ? i - 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1099,20 +1269,22 @@ __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, con
 // may drift apart by two tiles before anyone waits.
 // ------------------------------------------------------------------------------------------------
 template <int C>
-__device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, const int c0, const int cb, const int nreal, const int want_keys)
+__device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, const int c0, const int later, const int nreal, const int want_keys)
 {
+    // local columns: chunk 0: 0 = opening prices, 1 = the day's prices (NAV), 2.. = horizons c0..; later chunks: 0 = the day's prices, 1.. = horizons c0..
+    const int navlc = later ? 0 : 1;
     constexpr int R = kBigR, LR = (R == 8) ? 3 : 2, NS = R * C, S = kBigStages, NC = 2 * C, TW = kBigTileBytes / 16;
     constexpr int SH = kBigHStages, RW = kBigStageRowBytes / 16, QS = kBigStageRowBytes / 128, HPT = kBigTileBytes / kBigStageRowBytes;
     static_assert(R == 4 || R == 8, "rows per lane");
-    static_assert(NC * kBigTileBytes <= kBigStageBytes, "a stage holds 16 column tiles");
+    static_assert(NC * kBigTileBytes <= kBigStageBytes, "a stage holds kBigCols column tiles");
     static_assert((S & (S - 1)) == 0 && (SH & (SH - 1)) == 0 && HPT * kBigStageRowBytes == kBigTileBytes, "ring shapes");
     Ctx &c = ctx();
     const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     FSB_TH;
     const int K = c.K, K4 = (K + 3) & ~3;
-    const int ntiles = c.Mp >> 7;
+    const int ntiles = c.Mp / (kBigTileBytes / 8);  // (Mp is a multiple of 128 assets)
     const int j = lane & 7, q4 = lane >> 3, qa = q4 >> 1, qb = q4 & 1;
-    const int ncw = nwarps - 1;  // consumer warps; warp ncw feeds the column ring
+    const int ncw = nwarps - kBigProd;  // consumer warps; warp ncw (if any) feeds the column ring
     const int rows_per_block = 2 * R * ncw;
     const int nblocks_all = (K4 + rows_per_block - 1) / rows_per_block;
     const int rb_begin = (c.part * nblocks_all) / c.nparts, rb_end = ((c.part + 1) * nblocks_all) / c.nparts;  // this work unit's row blocks
@@ -1122,22 +1294,37 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
     unsigned char *hring = ring + S * kBigStageBytes + warp * (SH * kBigHStageBytes);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(fsb_smem + c.o_bars), *empty = full + S;
     unsigned long long *hfull = full + 2 * S + warp * SH;
-    __shared__ const double *colsrc[16];
+    __shared__ const double *colsrc[kBigCols];
     __syncthreads();  // the previous chunk is done with the rings and their barriers
     if (tid < NC) {   // (spare columns re-read the opening prices: finite data, results dropped)
-        const int col = cb + tid;
         const double *src = G.hand_p;
-        if (tid < nreal && col == 1) src = G.P + static_cast<long long>(pcol(c, t)) * c.Mp;
-        else if (tid < nreal && col >= 2) src = G.P + static_cast<long long>(pcol(c, t - c.hcols_()[c0 + col - 2])) * c.Mp;
+        if (tid < nreal && tid == navlc) src = G.P + static_cast<long long>(pcol(c, t)) * c.Mp;
+        else if (tid < nreal && tid > navlc) src = G.P + static_cast<long long>(pcol(c, t - c.hcols_()[c0 + tid - navlc - 1])) * c.Mp;
         colsrc[tid] = src;
     }
     if (tid == 0) {
-        for (int q = 0; q < 2 * S + ncw * SH; ++q) mbar_inval(full + q);
-        for (int q = 0; q < S; ++q) { mbar_init(full + q, 1); mbar_init(empty + q, ncw); }
+        for (int q = 0; q < 2 * S + ncw * SH; ++q)
+            if (kBigProd || q < S || q >= 2 * S) mbar_inval(full + q);  // (without a producer warp the `empty` words are plain counters)
+        for (int q = 0; q < S; ++q) { mbar_init(full + q, 1); if (kBigProd) mbar_init(empty + q, ncw); }
         for (int q = 0; q < ncw * SH; ++q) mbar_init(full + 2 * S + q, 1);
         fence_mbar_init();
     }
     __syncthreads();
+#if FSB_BIG_NOPROD
+    int *const done = reinterpret_cast<int *>(empty);  // per slot: warps that are done with the tile in it
+    auto issue = [&](int g) {  // column tile g of the CTA's sequence -> slot g % S (one thread; the slot is free)
+        const int slot = g & (S - 1), ti = g % ntiles;
+        mbar_expect_tx(full + slot, NC * kBigTileBytes);
+#pragma unroll 1
+        for (int q = 0; q < NC; ++q)
+            bulk_g2s(ring + slot * kBigStageBytes + q * kBigTileBytes, colsrc[q] + ti * (kBigTileBytes / 8), kBigTileBytes, full + slot);
+    };
+    if (tid == 0) {
+        for (int q = 0; q < S; ++q) done[2 * q] = 0;
+        for (int g = 0; g < S && g < total; ++g) issue(g);
+    }
+    __syncthreads();
+#else
     int is_ti = 0;  // (thread 0) tile index within the row of the next column tile to issue
     auto issue = [&](int g) {  // column tile g of the CTA's sequence -> slot g % S (one thread)
         const int slot = g & (S - 1), use = g / S;
@@ -1154,6 +1341,7 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
         __syncwarp();
         return;
     }
+#endif
     // the warp's holdings: stage h = 2 R rows x kBigStageRowBytes, ONE tensor copy (rows past K4 - 1 belong to the next
     // replication or are zero filled: their results are dropped).  (hi_col, hi_row): coordinates of the next stage to issue.
     const CUtensorMap *const tm = c.tm_h;
@@ -1212,7 +1400,17 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
                 }
             }
             __syncwarp();
+#if FSB_BIG_NOPROD
+            if (lane == 0) {  // the last warp to finish the tile refills its slot
+                __threadfence_block();
+                if (atomicAdd(done + 2 * slot, 1) == ncw - 1) {
+                    atomicExch(done + 2 * slot, 0);
+                    if (g + S < total) { fence_proxy_async(); issue(g + S); }
+                }
+            }
+#else
             if (lane == 0) mbar_arrive(empty + slot);
+#endif
         }
         // ---- epilogue of the row block (as full_pass) ----------------------------------------------
         reduce8_transposed<NS>(acc, j);
@@ -1221,16 +1419,16 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
         int own[NF];
 #pragma unroll
         for (int q = 0; q < NF; ++q) own[q] = owned_sum<NS>(j, q);
-        if (cb == 0) {  // column 1 first: the day's NAV is the numerator of every horizon return of the row
+        {   // the NAV column first: the day's NAV is the numerator of every horizon return of the row
 #pragma unroll
             for (int q = 0; q < NF; ++q) {
-                const int col = qb + 2 * (own[q] >> LR), k = row0 + (own[q] & (R - 1));
+                const int lc = qb + 2 * (own[q] >> LR), k = row0 + (own[q] & (R - 1));
                 if (k < K) {
-                    if (col == 0) {
-                        if (!((c.fmod_()[k >> 5] >> (k & 31)) & 1)) G.nav_open[k] = acc[q];
-                    } else if (col == 1) {
+                    if (lc == navlc) {
                         c.nav_()[k] = acc[q];
-                        G.nav_close[k] = acc[q];
+                        if (!later) G.nav_close[k] = acc[q];
+                    } else if (lc == 0) {  // (chunk 0)
+                        if (!((c.fmod_()[k >> 5] >> (k & 31)) & 1)) G.nav_open[k] = acc[q];
                     }
                 }
             }
@@ -1238,12 +1436,12 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
         }
 #pragma unroll
         for (int q = 0; q < NF; ++q) {
-            const int col = cb + qb + 2 * (own[q] >> LR), k = row0 + (own[q] & (R - 1));
-            if (col >= 2 && col - cb < nreal && k < K) {
+            const int lc = qb + 2 * (own[q] >> LR), k = row0 + (own[q] & (R - 1));
+            if (lc > navlc && lc < nreal && k < K) {
                 const double navk = keep_nav[k], v = acc[q];
                 const double rho = ddiv(navk - v, v);
                 const unsigned long long word = want_keys ? sort_key(rho) : static_cast<unsigned long long>(__double_as_longlong(rho));
-                __stcg(G.keys + static_cast<long long>(c0 + col - 2) * c.kq + k, word);
+                __stcg(G.keys + static_cast<long long>(c0 + lc - navlc - 1) * c.kq + k, word);
             }
         }
     }
@@ -2032,19 +2230,31 @@ __device__ FSB_FP_INLINE void phase_choice(const DevState &s, const int t, const
         // rank rule: p_k = rank_k / (K(K+1)/2) per column, into the warp's probability row
         double *prob_k = c.cols_() + (2 + warp) * c.cpk;
         if (c.sortn > 0) {  // 256 < K <= 2048: the CTA ranks one column at a time (block_rank_sort), then samples its cash holders
+            // the sort buffers (sortn * 10 bytes) are reused once the order is known: ranks in fund order (sortn * 2 bytes), their
+            // integer prefix sums (sortn * 4) and one word per warp behind them
             unsigned long long *sk = reinterpret_cast<unsigned long long *>(fsb_smem + c.o_sort);
             unsigned short *si = reinterpret_cast<unsigned short *>(sk + c.sortn);
-            double *prob = reinterpret_cast<double *>(sk);  // (the sorted keys are dead once the indices are in order)
+            unsigned short *rk16 = reinterpret_cast<unsigned short *>(sk);
+            int *cum = reinterpret_cast<int *>(rk16 + c.sortn), *wtot = cum + c.sortn;
+            const bool reg_sort = (c.sortn == 8 * NT) && !s.smem_sort;
 #pragma unroll 1
             for (int jc = 0; jc < ncols; ++jc) {
-                block_rank_sort(G.keys + static_cast<long long>(jc) * c.kq, K, c.sortn, sk, si, prob, c.ranktab);
+                const unsigned long long *keys = G.keys + static_cast<long long>(jc) * c.kq;
+                if (reg_sort) block_rank_sort_reg(keys, K, sk, si, rk16);
+                else {
+                    block_rank_sort(keys, K, c.sortn, sk, si);
+                    for (int e = tid; e < K; e += NT) rk16[si[e]] = static_cast<unsigned short>(e + 1);  // (the sorted keys are dead)
+                    __syncthreads();
+                }
+                FSB_MARK(23);
+                if (!s.scan_choice) block_rank_prefix(rk16, K, c.sortn, cum, wtot);
                 for (int i = tid; i < ncash; i += NT) {
                     if (c.r_col_()[i] != jc) continue;
-                    c.r_choice_()[i] = select_fund_prob(c, t, c.cash_()[i], prob, nullptr);
+                    c.r_choice_()[i] = select_fund_ranked(c, t, c.cash_()[i], rk16, cum, s.scan_choice != 0);
                 }
                 __syncthreads();
+                FSB_MARK(11);
             }
-            FSB_MARK(11);
         } else {
 #pragma unroll 1
         for (int jc = warp; jc < ncols; jc += nwarps) {
@@ -2324,7 +2534,7 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
     __syncthreads();
     if (open_day) {  // nav_open = nav_close = H * p_open
 #if FSB_BIG
-        if (c.part != 0) return;  // (one column: the first work unit of the replication takes all rows)
+        if (c.part != 0 || c.chunk != 0) return;  // (one column: the first work unit of the replication takes all rows)
 #endif
         phase_stage_columns(s, t, 0, 0, true, true);
         if (!FSB_BIG && c.fast && c.ring_stages > 0) full_pass_tma<2>(s, 0, 1, 0, 0, 1);  // (big build: ring_stages marks the tiled pass)
@@ -2335,18 +2545,26 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
         const int want_keys = (selector == FSB_SEL_PROBABILISTIC) ? 1 : 0;
 #if FSB_BIG
         if (c.ring_stages > 0) {
-            // column tiles through shared memory (no staged copy of whole columns); chunks of up to 16 columns: the two
-            // price columns + 14 horizons, then 16 horizons per chunk (every chunk re-reads the holdings)
+            // column tiles through shared memory (no staged copy of whole columns); chunks of up to kBigCols columns.  Chunk 0:
+            // the two price columns + up to kBigCols - 2 horizons; later chunks: the day's price column again (the NAV is the
+            // numerator of every horizon return) + up to kBigCols - 1 horizons.  The horizons are spread evenly over the chunks
+            // (equal work: the CTAs that take the chunks of a part stay together); this unit takes the chunks c.chunk,
+            // c.chunk + c.nchunks, ...
+            int nch = 1;
+            while ((kBigCols - 2) + (kBigCols - 1) * (nch - 1) < ncols) ++nch;
+            const int hbase = ncols / nch, hrem = ncols % nch;  // chunk i: hbase horizons, the last hrem chunks one more
 #pragma unroll 1
-            for (int c0 = 0; c0 == 0 || c0 < ncols;) {
-                const int nc = min(c0 == 0 ? 14 : 16, ncols - c0);
-                const int cb = c0 == 0 ? 0 : 2, nreal = c0 == 0 ? 2 + nc : nc;
-                if (nreal <= 4) big_pass_tiled<2>(s, t, c0, cb, nreal, want_keys);
-                else if (nreal <= 8) big_pass_tiled<4>(s, t, c0, cb, nreal, want_keys);
-                else if (nreal <= 12) big_pass_tiled<6>(s, t, c0, cb, nreal, want_keys);
-                else big_pass_tiled<8>(s, t, c0, cb, nreal, want_keys);
+            for (int ch = c.chunk; ch < nch; ch += c.nchunks) {
+                const int c0 = ch * hbase + max(0, ch - (nch - hrem)), nc = hbase + (ch >= nch - hrem ? 1 : 0);
+                const int later = ch > 0 ? 1 : 0, nreal = (later ? 1 : 2) + nc;
+                static_assert(kBigCols == 16, "the dispatch below");
+                if (nreal <= 4) big_pass_tiled<2>(s, t, c0, later, nreal, want_keys);
+                else if (nreal <= 8) big_pass_tiled<4>(s, t, c0, later, nreal, want_keys);
+                else if (nreal <= 10) big_pass_tiled<5>(s, t, c0, later, nreal, want_keys);
+                else if (nreal <= 12) big_pass_tiled<6>(s, t, c0, later, nreal, want_keys);
+                else if (nreal <= 14) big_pass_tiled<7>(s, t, c0, later, nreal, want_keys);
+                else big_pass_tiled<8>(s, t, c0, later, nreal, want_keys);
                 FSB_MARK(10);
-                c0 += (nc > 0) ? nc : 1;
             }
         } else
 #endif
@@ -2365,8 +2583,9 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
     if (c.trace >= 0) {
         __syncthreads();
 #if FSB_BIG
-        if (!open_day && c.ring_stages > 0 && c.nparts > 1) {  // this work unit's rows (the others are written by other CTAs)
-            const int rpb = 2 * kBigR * (nwarps - 1), nb = (((c.K + 3) & ~3) + rpb - 1) / rpb;
+        if (!open_day && c.ring_stages > 0 && c.nparts * c.nchunks > 1) {  // this work unit's rows (the others are written by other CTAs)
+            if (c.chunk != 0) return;
+            const int rpb = 2 * kBigR * (nwarps - kBigProd), nb = (((c.K + 3) & ~3) + rpb - 1) / rpb;
             const int k0 = ((c.part * nb) / c.nparts) * rpb, k1 = min(c.K, (((c.part + 1) * nb) / c.nparts) * rpb);
             if (k1 > k0) trace_phase(t, 3, k0, k1);
         } else
@@ -2598,8 +2817,8 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
 #if FSB_BIG
         if (KIND == KIND_PASS && s.ring_stages > 0) {  // full[kBigStages], empty[kBigStages]: re-armed by every big_pass_tiled call
             unsigned long long *rb = reinterpret_cast<unsigned long long *>(fsb_smem + L.off_bars);
-            for (int q = 0; q < kBigStages; ++q) { mbar_init(rb + q, 1); mbar_init(rb + kBigStages + q, nwarps - 1); }
-            for (int q = 0; q < (nwarps - 1) * kBigHStages; ++q) mbar_init(rb + 2 * kBigStages + q, 1);
+            for (int q = 0; q < kBigStages; ++q) { mbar_init(rb + q, 1); if (kBigProd) mbar_init(rb + kBigStages + q, nwarps - 1); }
+            for (int q = 0; q < (nwarps - kBigProd) * kBigHStages; ++q) mbar_init(rb + 2 * kBigStages + q, 1);
         }
 #else
         if (KIND == KIND_PASS && s.ring_stages > 0) {
@@ -2625,9 +2844,15 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         if (threadIdx.x == 0) r_sh = atomicAdd(&queue[launch_parity], 1);
         __syncthreads();
 #if FSB_BIG
-        const int nparts = (KIND == KIND_PASS && s.ring_stages > 0) ? s.pass_parts : 1;  // pass: (replication, part) work units
-        const long long r = a.r_begin + r_sh / nparts;
-        if (threadIdx.x == 0) { c.part = static_cast<int>(r_sh % nparts); c.nparts = nparts; }
+        // pass: (replication, part, chunk) work units, the chunk fastest: the CTAs that take the chunks of one part stream the
+        // same holdings rows at the same time, so all but the first read of a line hit L2
+        const int nparts = (KIND == KIND_PASS && s.ring_stages > 0) ? s.pass_parts : 1;
+        const int nchunks = (KIND == KIND_PASS && s.ring_stages > 0) ? s.pass_chunks : 1;
+        const long long r = a.r_begin + r_sh / (nparts * nchunks);
+        if (threadIdx.x == 0) {
+            const int u = static_cast<int>(r_sh % (nparts * nchunks));
+            c.part = u / nchunks; c.nparts = nparts; c.chunk = u % nchunks; c.nchunks = nchunks;
+        }
 #else
         const long long r = a.r_begin + r_sh;
 #endif

@@ -12,6 +12,7 @@ ap.add_argument("--steps", type=int, default=8)
 ap.add_argument("--t0", type=int, default=102)
 ap.add_argument("--blocks-per-sm", type=int, default=0)
 ap.add_argument("--block-threads", type=int, default=0)
+ap.add_argument("--digest", action="store_true", help="also print a digest of the first and last replication's state (kernel variants must agree)")
 ap.add_argument("--config4", action="store_true", help="BASELINE.json configs[3]: 2000 funds x 5000 assets, N = 8000, dense portfolios")
 a = ap.parse_args()
 fsb = load_package()
@@ -30,3 +31,11 @@ with fsb.Engine(p, a.reps, blocks_per_sm=a.blocks_per_sm,
     nerr = int((eng.rep_status() != 0).sum())
     print(f"reps={a.reps} steps={a.steps} launches={n} total_ms={ms:.3f} per_launch_ms={ms / n:.4f} "
           f"fund_steps_per_s={a.reps * p.bigk * a.steps / (ms * 1e-3):.4e} frozen_reps={nerr} pass_ms={pass_ms:.3f}")
+    if a.digest:
+        import hashlib
+        h = hashlib.sha256()
+        for r in (0, a.reps - 1):
+            st = eng.download_compact(r)
+            for k in sorted(st):
+                h.update(st[k].tobytes())
+        print("digest", h.hexdigest()[:16])

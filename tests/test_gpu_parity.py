@@ -576,6 +576,34 @@ def test_large_shapes_general_path(fsb, orc, shape):
             w.close()
 
 
+@pytest.mark.parametrize("shape,env", [
+    (dict(bigk=600, bign=2000, bigm=40, bigt=50), {}),                          # generic build: 1024 = 8 x 128 threads, register network
+    (dict(bigk=600, bign=2000, bigm=40, bigt=50), {"FSB_SMEM_SORT": "1"}),      # ... the shared-memory network
+    (dict(bigk=600, bign=2000, bigm=40, bigt=50), {"FSB_SCAN_CHOICE": "1"}),    # ... sampled by the reference's scan only
+    (dict(bigk=1100, bign=3300, bigm=48, bigt=28), {"FSB_FORCE_BIG": "1"}),     # big build: 2048 = 8 x 256 threads, register network
+    (dict(bigk=1100, bign=3300, bigm=48, bigt=28), {"FSB_FORCE_BIG": "1", "FSB_SMEM_SORT": "1", "FSB_SCAN_CHOICE": "1"}),
+], ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()) or "default")
+def test_cta_ranked_columns(fsb, orc, shape, env, monkeypatch):
+    """256 < K <= 2048: the CTA ranks a horizon column with a bitonic network (pairs in registers when the padded length is
+    8 per thread, else in shared memory) and samples the rank rule through exact integer prefix sums; both networks and the
+    reference's floating-point scan must give the oracle's choices bit for bit."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    p = fsb.Params.default(reviewprobability=0.12, invcaprange=(10, 1000), perfwindow=(1, 8), portfsizerange=(3, 20), **shape)
+    R = 2 if p.bigk < 1000 else 1
+    with fsb.Engine(p, R, keep_history=True) as eng:
+        eng.init_device(SEED)
+        eng.run(selector="probabilistic")
+        assert not eng.rep_status().any()
+        for r in range(R):
+            w = H.oracle_world(orc, p, SEED, r, trace=False)
+            assert w.modelrun(selector="probabilistic") == 0
+            w.finalise_fund_value(p.bigt)
+            H.assert_state_equal(eng.download_state(r), w)
+            H.assert_log_equal(eng.download_log(r), w.log())
+            w.close()
+
+
 @pytest.mark.parametrize("shape,R", [
     (dict(bigk=64, bign=256, bigm=5000, bigt=125, portfsizerange=(2500, 5000), reviewprobability=0.1), 3),
     (dict(bigk=2000, bign=8000, bigm=5000, bigt=110, portfsizerange=(2500, 5000)), 1),
