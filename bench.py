@@ -331,7 +331,7 @@ def main():
         fsb.Params.default(bigk=2000, bigm=5000, bign=8000, bigt=1101, portfsizerange=(2500, 5000))
     K, M, N = params.bigk, params.bigm, params.bign
     if args.config == 4 and args.reps_per_gpu == 100_000:
-        args.reps_per_gpu = 4 * torch.cuda.get_device_properties(local).multi_processor_count  # (86 MB per replication; one pass CTA per SM: whole waves)
+        args.reps_per_gpu = 1000  # BASELINE.json configs[3]: 10^3 replications (86 MB each; the pass kernel's work units are (replication, part, chunk))
     total = args.reps_per_gpu * (world if args.scaling == "weak" else 1)
     lo, hi = (rank * total) // world, ((rank + 1) * total) // world
     R = hi - lo
