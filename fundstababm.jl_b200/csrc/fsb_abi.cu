@@ -24,7 +24,8 @@
 
 namespace fsb {  // the FSB_BIG build of the step kernels (fsb_step_big.cu)
 __global__ void fsb_big_events1_kernel(const DevState s, const StepArgs a, const int launch_parity);
-__global__ void fsb_big_pass_kernel(const DevState s, const StepArgs a, const int launch_parity, const __grid_constant__ CUtensorMap tm_h);
+__global__ void fsb_big_pass_kernel(const DevState s, const StepArgs a, const int launch_parity, const __grid_constant__ CUtensorMap tm_h,
+                                    const __grid_constant__ CUtensorMap tm_h16);
 __global__ void fsb_big_events2_kernel(const DevState s, const StepArgs a, const int launch_parity);
 }  // namespace fsb
 
@@ -107,6 +108,7 @@ static int32_t nccl_load()
 // ------------------------------------------------------------------------------------------------
 struct fsb_engine {
     CUtensorMap tm_h{};  // 2-D view of the holdings of ALL replications: [R * K4 rows][Mp], box = 8 rows x one stage (pass kernel)
+    CUtensorMap tm_h16{};  // the same view with a box of 16 rows x half a stage row (full_pass_tma16)
     DevState d{};
     fsb_config cfg{};
     std::vector<DevPoint> points;
@@ -340,6 +342,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     }
     d.scan_choice = (getenv("FSB_SCAN_CHOICE") && atoi(getenv("FSB_SCAN_CHOICE")) > 0) ? 1 : 0;
     d.smem_sort = (getenv("FSB_SMEM_SORT") && atoi(getenv("FSB_SMEM_SORT")) > 0) ? 1 : 0;
+    d.pass16 = (getenv("FSB_PASS16") && atoi(getenv("FSB_PASS16")) == 0) ? 0 : 1;
     e->fast = (d.K <= 256);
     // the default Params shape exactly: the event and choice kernels of the fixed-shape build (FSB_NO_FIXED=1: generic build)
     e->fixed = (!d.big && d.K == kFixedK && d.M == kFixedM && d.N == kFixedN && d.W == kFixedW && d.cap_ev == kFixedCap && d.slots_a == kFixedSlots &&
@@ -406,6 +409,13 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
         const CUresult cr = reinterpret_cast<encode_fn>(fn)(&e->tm_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d.H, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return cleanup(fail(FSB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(cr)));
+        e->tm_h16 = e->tm_h;
+        if (!d.big) {
+            const cuuint32_t box16[2] = {static_cast<cuuint32_t>(kStageBytes / 16 / 8), 16};
+            const CUresult cr2 = reinterpret_cast<encode_fn>(fn)(&e->tm_h16, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d.H, gdim, gstr, box16, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr2 != CUDA_SUCCESS) return cleanup(fail(FSB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(cr2)));
+        }
     }
     // the packed mirror of the holdings (fsb_passx.cuh), default shape only.  OPT-IN (FSB_PASS_PACKED=1): measured on a B200 it is
     // bit-identical to the dense TMA-fed pass and moves 0.4x its bytes, but runs at 0.77x its speed -- both are bound by
@@ -816,9 +826,9 @@ static int32_t run_enqueue(fsb_engine *e, int64_t t_first, int64_t t_last, int32
                     while (e->kev.size() < e->kev_used + 2) { cudaEvent_t ev = nullptr; CU(cudaEventCreate(&ev)); e->kev.push_back(ev); }
                     CU(cudaEventRecord(e->kev[e->kev_used], st));
                 }
-                if (d.big) fsb_big_pass_kernel<<<g2, e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity, e->tm_h);
+                if (d.big) fsb_big_pass_kernel<<<g2, e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity, e->tm_h, e->tm_h16);
                 else if (e->usex) fsb_passx_kernel<<<static_cast<unsigned>(std::min<long long>(rb, e->grid_x)), kXThreads, sizeof(XShared), st>>>(d, a, e->launch_parity);
-                else fsb_pass_kernel<<<g2, e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity, e->tm_h);
+                else fsb_pass_kernel<<<g2, e->block_pass, e->smem_bytes[1], st>>>(d, a, e->launch_parity, e->tm_h, e->tm_h16);
                 if (timed) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st)); e->kev_used += 2; }
                 if (ht && ht->nav_open_out)  // the NAVs of :460 are final after the pass: device -> host while events-2 runs
                     CU(cudaMemcpyAsync(ht->nav_open_out + a.r_begin * d.K, d.nav_open + a.r_begin * d.K, rb * d.K * 8, cudaMemcpyDeviceToHost, st));

@@ -273,6 +273,7 @@ struct Ctx {
     unsigned mbar_phase;
     unsigned char *big;       // FSB_BIG: this CTA's global buffer for the per-asset arrays
     const CUtensorMap *tm_h;  // pass kernel: the holdings of all replications as one 2-D tensor (kernel parameter space)
+    const CUtensorMap *tm_h16;  // ... with a box of 16 rows x 256 bytes (full_pass_tma16)
     // replication: kRepPtrs pointers = base + r * stride, filled by kRepPtrs lanes from DevState::ptr_table
     // (same order there; they serve the out-of-line cold paths, the inlined phases use rep_ptrs)
     double *H, *P, *beta, *vol, *impact, *volume, *market, *stake, *amount, *threshold, *nav_open, *nav_close;
@@ -1257,6 +1258,117 @@ __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, con
     __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same pass for chunks of at most 8 columns (most days: the two price columns + ~6 horizons), in the 4 x 1
+// arrangement: a trip = 16 rows, group qa owns the rows 4 qa .. 4 qa + 3 and ALL CC columns, so a lane issues 4 holdings
+// loads and CC column loads per word step for 8 CC FMAs -- (4 + CC) wavefronts per 2 CC FMAs instead of the 2 x 2
+// arrangement's (4 + CC/2) per CC (8 columns: 0.75 wavefronts per FMA instead of 1.0; the pass is bound by them).
+// A stage = 16 rows x 256 bytes (the same 4 KB, second tensor map tm_h16: box 16 x 32), 8 stages per trip; ring,
+// barriers and the running stage counter are those of full_pass_tma, chains and sums are unchanged (a lane's chain
+// still walks the words j, j + 8, ... of its row in order).
+// ------------------------------------------------------------------------------------------------
+template <int CC>
+__device__ FSB_FP_INLINE void full_pass_tma16(const DevState &s, const int cb, const int nreal, const int want_keys, const int kcol0, const int open_day)
+{
+    constexpr int R = 4, NS = R * CC, S = kRingStages, RB = kStageBytes / 16, PT = 2048 / RB, RW = RB / 16, QS = RB / 128;
+    static_assert(RB >= 128 && (RB % 128) == 0, "a stage row holds whole word steps");
+    Ctx &c = ctx();
+    const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
+    FSB_TH;
+    const int K = c.K, K4 = (K + 3) & ~3;
+    const int j = lane & 7, qa = lane >> 3;
+    const int ntrips = (K4 + 15) >> 4;
+    const int my_trips = (ntrips - warp + nwarps - 1) / nwarps;
+    if (my_trips <= 0) return;
+    const int nstages = my_trips * PT;
+    unsigned char *ring = fsb_smem + c.o_ring + warp * (S * kStageBytes);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(fsb_smem + c.o_bars) + warp * S;
+    static_assert((S & (S - 1)) == 0, "the ring needs a power-of-two number of stages");
+    constexpr int LS = (S == 1) ? 0 : (S == 2) ? 1 : (S == 4) ? 2 : 3;
+    unsigned *gcount = reinterpret_cast<unsigned *>(fsb_smem + c.o_bars + nwarps * S * 8) + 2 * warp;
+    const unsigned gbase = *gcount;
+    const CUtensorMap *const tm = c.tm_h16;
+    const int grow0 = static_cast<int>(c.r) * K4;
+    auto issue = [&](int g) {  // stage g of this warp's sequence -> slot g % S: ONE tensor copy of 16 rows x RB bytes
+        const int slot = static_cast<int>((gbase + g) & (S - 1)), tg = warp + (g / PT) * nwarps, part = g % PT;
+        __syncwarp();  // (write after read: see full_pass_tma)
+        if (lane == 0) {
+            mbar_expect_tx(bars + slot, kStageBytes);
+            tensor_g2s_2d(ring + slot * kStageBytes, tm, part * (RB / 8), grow0 + 16 * tg, bars + slot);
+        }
+    };
+#pragma unroll 1
+    for (int g = 0; g < S - 1 && g < nstages; ++g) issue(g);
+    const double2 *colp = reinterpret_cast<const double2 *>(c.cols_()) + cb * 128 + j;
+    const double *const keep_nav = c.nav_();
+#pragma unroll 1
+    for (int g0 = 0; g0 < nstages; g0 += PT) {
+        double acc[NS];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) acc[q] = 0.0;
+#pragma unroll 1
+        for (int part = 0; part < PT; ++part) {
+            const int g = g0 + part;
+            if (g + S - 1 < nstages) issue(g + S - 1);
+            const int slot = static_cast<int>((gbase + g) & (S - 1));
+            mbar_wait(bars + slot, ((gbase + g) >> LS) & 1u);
+            const double2 *hs = reinterpret_cast<const double2 *>(ring + slot * kStageBytes) + (R * qa) * RW + j;
+            const double2 *cp_i = colp + RW * part;
+#pragma unroll
+            for (int q = 0; q < QS; ++q) {
+                double2 h[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) h[r] = hs[r * RW + 8 * q];
+#pragma unroll
+                for (int cc = 0; cc < CC; ++cc) {
+                    const double2 p = cp_i[cc * 128 + 8 * q];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        acc[r + R * cc] = fma(h[r].x, p.x, acc[r + R * cc]);
+                        acc[r + R * cc] = fma(h[r].y, p.y, acc[r + R * cc]);
+                    }
+                }
+            }
+        }
+        // ---- epilogue of the trip (as full_pass_tma; sum index = row + 4 * column) ---------------------
+        reduce8_transposed<NS>(acc, j);
+        constexpr int NF = NS / 8;
+        const int row0 = 16 * (warp + (g0 / PT) * nwarps) + R * qa;
+        int own[NF];
+#pragma unroll
+        for (int q = 0; q < NF; ++q) own[q] = owned_sum<NS>(j, q);
+        if (cb == 0) {  // column 1 first: the day's NAV is the numerator of every horizon return of the row
+#pragma unroll
+            for (int q = 0; q < NF; ++q) {
+                const int col = own[q] >> 2, k = row0 + (own[q] & 3);
+                if (k < K) {
+                    if (col == 0) {
+                        if (!((c.fmod_()[k >> 5] >> (k & 31)) & 1)) G.nav_open[k] = acc[q];
+                        if (open_day) G.nav_close[k] = acc[q];
+                    } else if (col == 1 && !open_day) {
+                        c.nav_()[k] = acc[q];
+                        G.nav_close[k] = acc[q];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < NF; ++q) {
+            const int col = cb + (own[q] >> 2), k = row0 + (own[q] & 3);
+            if (col >= 2 && col - cb < nreal && k < K) {
+                const double navk = keep_nav[k], v = acc[q];
+                const double rho = ddiv(navk - v, v);
+                const unsigned long long word = want_keys ? sort_key(rho) : static_cast<unsigned long long>(__double_as_longlong(rho));
+                __stcg(G.keys + static_cast<long long>(kcol0 + col - 2) * c.kq + k, word);
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *gcount = gbase + static_cast<unsigned>(nstages);
+    __syncwarp();
+}
+
 #if FSB_BIG
 // ------------------------------------------------------------------------------------------------
 // the holdings pass of big shapes (whole columns do not fit in shared memory): lane arrangement, chains and
@@ -1453,7 +1565,12 @@ __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, con
 // c.fast: Mp == 256 and K <= 256 (the default shape): strides and trip counts are compile-time constants.
 __device__ __forceinline__ void full_pass_dispatch(const DevState &s, Ctx &c, int cb, int nc, int want_keys, int kcol0)
 {
-    if (!FSB_BIG && c.fast && c.ring_stages > 0) {
+    if (!FSB_BIG && c.fast && c.ring_stages > 0 && nc <= 8 && s.pass16) {  // (at most 8 columns: the 4 x 1 arrangement)
+        if (nc <= 2) full_pass_tma16<2>(s, cb, nc, want_keys, kcol0, 0);
+        else if (nc <= 4) full_pass_tma16<4>(s, cb, nc, want_keys, kcol0, 0);
+        else if (nc <= 6) full_pass_tma16<6>(s, cb, nc, want_keys, kcol0, 0);
+        else full_pass_tma16<8>(s, cb, nc, want_keys, kcol0, 0);
+    } else if (!FSB_BIG && c.fast && c.ring_stages > 0) {
         if (nc <= 4) full_pass_tma<2>(s, cb, nc, want_keys, kcol0, 0);
         else if (nc <= 8) full_pass_tma<4>(s, cb, nc, want_keys, kcol0, 0);
         else if (nc <= 12) full_pass_tma<6>(s, cb, nc, want_keys, kcol0, 0);
@@ -2537,7 +2654,8 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
         if (c.part != 0 || c.chunk != 0) return;  // (one column: the first work unit of the replication takes all rows)
 #endif
         phase_stage_columns(s, t, 0, 0, true, true);
-        if (!FSB_BIG && c.fast && c.ring_stages > 0) full_pass_tma<2>(s, 0, 1, 0, 0, 1);  // (big build: ring_stages marks the tiled pass)
+        if (!FSB_BIG && c.fast && c.ring_stages > 0 && s.pass16) full_pass_tma16<2>(s, 0, 1, 0, 0, 1);
+        else if (!FSB_BIG && c.fast && c.ring_stages > 0) full_pass_tma<2>(s, 0, 1, 0, 0, 1);  // (big build: ring_stages marks the tiled pass)
         else if (c.fast) full_pass<1, true, true>(s, 0, 1, 0, 0);
         else full_pass<1, true, false>(s, 0, 1, 0, 0);
     } else {
@@ -2765,7 +2883,7 @@ __device__ __forceinline__ void step_choice(const DevState &s, Ctx &c, const int
 // kernels: persistent CTAs pull replications from a work counter (one counter pair per kernel kind)
 // ------------------------------------------------------------------------------------------------
 template <int KIND>
-__device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepArgs &a, const int launch_parity, const CUtensorMap *tm_h)
+__device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepArgs &a, const int launch_parity, const CUtensorMap *tm_h, const CUtensorMap *tm_h16 = nullptr)
 {
     static_assert(sizeof(Ctx) <= kCtxBytes, "Ctx outgrew its shared-memory slot");
     Ctx &c = ctx();
@@ -2808,6 +2926,7 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
 #endif
         c.mbar = &mbar_sh; c.mbar_phase = 0;
         c.tm_h = tm_h;
+        c.tm_h16 = tm_h16;
         c.tmark = clock64();
         c.slot = 2 * a.batch + (KIND == KIND_EVENTS2 ? 1 : 0);  // concurrently running event kernels get disjoint per-CTA scratch
         c.scratch = s.scratch + (static_cast<long long>(c.slot) * s.scratch_ctas + blockIdx.x) * (static_cast<long long>(s.cap_ev) * s.Mp);
@@ -2911,9 +3030,9 @@ __global__ void __launch_bounds__(kBigPassThreads, 1) fsb_pass_kernel(
 #else
 __global__ void __launch_bounds__(kPassThreads, 2) fsb_pass_kernel(
 #endif
-    const DevState s, const StepArgs a, const int launch_parity, const __grid_constant__ CUtensorMap tm_h)
+    const DevState s, const StepArgs a, const int launch_parity, const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_h16)
 {
-    phase_kernel_body<KIND_PASS>(s, a, launch_parity, &tm_h);
+    phase_kernel_body<KIND_PASS>(s, a, launch_parity, &tm_h, &tm_h16);
 }
 #ifndef FSB_E2_CTAS
 #define FSB_E2_CTAS FSB_EV_CTAS
