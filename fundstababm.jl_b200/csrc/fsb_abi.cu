@@ -343,6 +343,7 @@ extern "C" int32_t fsb_create(const fsb_params *pts, int32_t n_points, const fsb
     d.scan_choice = (getenv("FSB_SCAN_CHOICE") && atoi(getenv("FSB_SCAN_CHOICE")) > 0) ? 1 : 0;
     d.smem_sort = (getenv("FSB_SMEM_SORT") && atoi(getenv("FSB_SMEM_SORT")) > 0) ? 1 : 0;
     d.pass16 = (getenv("FSB_PASS16") && atoi(getenv("FSB_PASS16")) == 0) ? 0 : 1;
+    d.pass_ahead = (getenv("FSB_PASS_AHEAD") && atoi(getenv("FSB_PASS_AHEAD")) == 0) ? 0 : 1;
     e->fast = (d.K <= 256);
     // the default Params shape exactly: the event and choice kernels of the fixed-shape build (FSB_NO_FIXED=1: generic build)
     e->fixed = (!d.big && d.K == kFixedK && d.M == kFixedM && d.N == kFixedN && d.W == kFixedW && d.cap_ev == kFixedCap && d.slots_a == kFixedSlots &&

@@ -33,6 +33,7 @@ struct DevState {
     unsigned char *bigbuf; // [2 * batches][scratch_ctas][big_stride]
     int scan_choice;       // FSB_SCAN_CHOICE=1: the rank rule is sampled by the floating-point scan only (no integer shortcut; tests)
     int pass16;            // default shape: chunks of <= 8 columns take the 4 x 1 arrangement (full_pass_tma16); FSB_PASS16=0: never
+    int pass_ahead;        // default shape: warp 0 of a pass CTA prepares the CTA's next replication during the current one (PassAhead); FSB_PASS_AHEAD=0: off
     int smem_sort;         // FSB_SMEM_SORT=1: 256 < K <= 2048 ranks by the shared-memory network only (no register network; tests)
     int ring_stages;       // per-warp holdings ring of the pass kernel (kRingStages on the default shape, else 0)
     int pass_parts;        // big shapes, tiled pass: a replication's rows are split into this many work units (>= 1)

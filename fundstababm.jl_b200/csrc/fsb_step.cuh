@@ -271,6 +271,14 @@ struct Ctx {
 #endif
     unsigned long long *mbar;
     unsigned mbar_phase;
+    // pass kernel, default shape: the look-ahead for the CTA's NEXT replication (PassAhead), its two barriers (one per half of the
+    // column slots) with their phases, the CTA's work counter and replication range
+    struct PassAhead *nx;
+    unsigned long long *mbar_ah;
+    unsigned ah_phase[2];
+    int ahead_on, have_nx;
+    int *queue_ctr;
+    long long r_begin, r_end;
     unsigned char *big;       // FSB_BIG: this CTA's global buffer for the per-asset arrays
     const CUtensorMap *tm_h;  // pass kernel: the holdings of all replications as one 2-D tensor (kernel parameter space)
     const CUtensorMap *tm_h16;  // ... with a box of 16 rows x 256 bytes (full_pass_tma16)
@@ -367,6 +375,19 @@ enum { I_ND = 0, I_NCASH, I_NEGGS, I_ERR, I_TMP0, I_TMP1, I_TMP2, I_NCOLS, I_IDL
 // inlined phase: pointers derived from kernel parameters are KNOWN to be global memory, so loads through
 // them neither alias the shared-memory stores in between (they can be hoisted and overlapped) nor need
 // generic addressing.  (The copies in Ctx serve the out-of-line cold paths.)
+// events-1's hand-over header in hand_i (layout: see step_events1)
+enum { HI_T = 0, HI_OPEN, HI_NCOLS, HI_NCASH, HI_FMOD = 8 };
+
+// What warp 0 of a pass CTA learns about the CTA's next replication while the current one is being multiplied
+// (full_pass_tma16): its place in the queue, events-1's hand-over header and, when it needs at most 8 columns, the
+// columns themselves, already on their way into the half of the column slots the current replication does not read.
+struct PassAhead {
+    int state;  // 0: nothing (the CTA pulls from the queue), 1: filled in
+    int idx, frozen, stamp_ok, open_day, ncols, staged, half;
+    unsigned fmod[8];
+    int hcols[32];
+};
+
 struct Rep {
     double *H, *P, *beta, *vol, *impact, *volume, *market, *stake, *amount, *threshold, *nav_open, *nav_close;
     int *pos, *horizon, *cnt;
@@ -1268,8 +1289,13 @@ __device__ FSB_FP_INLINE void full_pass_tma(const DevState &s, const int cb, con
 // still walks the words j, j + 8, ... of its row in order).
 // ------------------------------------------------------------------------------------------------
 template <int CC>
-__device__ FSB_FP_INLINE void full_pass_tma16(const DevState &s, const int cb, const int nreal, const int want_keys, const int kcol0, const int open_day)
+__device__ FSB_FP_INLINE void full_pass_tma16(const DevState &s, const int cb, const int nreal, const int want_keys, const int kcol0, const int open_day,
+                                              const int cslot0 = 0, const bool la = false, const int la_half = 0, const int t = 0)
 {
+    // cslot0: the first column slot of this replication's staged columns (0 or 8).  la (warp 0 only): look ahead for the CTA's
+    // next replication in three steps, one per stage of the first trip, so that no step waits for the loads of the one before:
+    // 0: take the next index of the work queue; 1: load its error flag and events-1's header; 2: publish them (PassAhead) and,
+    // if it needs at most 8 columns, start the bulk copies of its columns into the slots from 8 * la_half.
     constexpr int R = 4, NS = R * CC, S = kRingStages, RB = kStageBytes / 16, PT = 2048 / RB, RW = RB / 16, QS = RB / 128;
     static_assert(RB >= 128 && (RB % 128) == 0, "a stage row holds whole word steps");
     Ctx &c = ctx();
@@ -1299,8 +1325,9 @@ __device__ FSB_FP_INLINE void full_pass_tma16(const DevState &s, const int cb, c
     };
 #pragma unroll 1
     for (int g = 0; g < S - 1 && g < nstages; ++g) issue(g);
-    const double2 *colp = reinterpret_cast<const double2 *>(c.cols_()) + cb * 128 + j;
+    const double2 *colp = reinterpret_cast<const double2 *>(c.cols_()) + (cslot0 + cb) * 128 + j;
     const double *const keep_nav = c.nav_();
+    int la_idx = 0, la_err = 0, la_v = 0, la_h = 0;  // (look-ahead values in flight between the steps)
 #pragma unroll 1
     for (int g0 = 0; g0 < nstages; g0 += PT) {
         double acc[NS];
@@ -1310,6 +1337,51 @@ __device__ FSB_FP_INLINE void full_pass_tma16(const DevState &s, const int cb, c
         for (int part = 0; part < PT; ++part) {
             const int g = g0 + part;
             if (g + S - 1 < nstages) issue(g + S - 1);
+#if !FSB_BIG && !FSB_FIXED
+            if (la && g < 3) {
+                if (g == 0) {
+                    if (lane == 0) la_idx = atomicAdd(c.queue_ctr, 1);
+                } else if (g == 1) {
+                    la_idx = __shfl_sync(0xffffffffu, la_idx, 0);
+                    const long long rr = c.r_begin + la_idx;
+                    if (rr < c.r_end) {  // lane 0: error flag; lanes 1..3: stamp, open day, columns; 8..15: modified-fund bitmap; all: horizons
+                        const int *hi = rep_ptrs(s, rr, c.kq, c.slot).hand_i;
+                        const int nf = (K + 31) / 32;
+                        if (lane == 0) la_err = __ldcg(s.err + rr);
+                        else if (lane < 4) la_v = __ldcg(hi + (lane - 1));
+                        else if (lane >= 8 && lane < 8 + nf) la_v = __ldcg(hi + HI_FMOD + (lane - 8));
+                        if (lane < c.cap) la_h = __ldcg(hi + HI_FMOD + nf + lane);
+                    }
+                } else {
+                    PassAhead &nx = *c.nx;
+                    const long long rr = c.r_begin + la_idx;
+                    const int frozen = __shfl_sync(0xffffffffu, la_err, 0) & ~FSB_REP_TRACE_OVERFLOW;
+                    const int stamp = __shfl_sync(0xffffffffu, la_v, 1), od = __shfl_sync(0xffffffffu, la_v, 2), ncn = __shfl_sync(0xffffffffu, la_v, 3);
+                    const bool in = rr < c.r_end, ok = in && !frozen && stamp == t;
+                    const bool stage = ok && (od || ncn + 2 <= 8);
+                    if (lane >= 8 && lane < 16) nx.fmod[lane - 8] = static_cast<unsigned>(la_v);
+                    nx.hcols[lane] = la_h;
+                    if (lane == 0) {
+                        nx.idx = la_idx; nx.frozen = in ? frozen : 0; nx.stamp_ok = (in && stamp == t) ? 1 : 0;
+                        nx.open_day = od; nx.ncols = ncn; nx.staged = stage ? 1 : 0; nx.half = la_half;
+                        nx.state = 1;
+                    }
+                    if (stage) {
+                        const Rep Gn = rep_ptrs(s, rr, c.kq, c.slot);
+                        const int ncopies = od ? 1 : 2 + ncn;
+                        double *dst = c.cols_() + static_cast<long long>(8 * la_half) * c.cpk;
+                        unsigned long long *mb = c.mbar_ah + la_half;
+                        const double *src = Gn.hand_p;  // lane q copies column q: 0 opening prices, 1 the day's prices, 2.. the horizons
+                        if (lane == 1) src = Gn.P + static_cast<long long>(pcol(c, t)) * c.Mp;
+                        const int hq = __shfl_sync(0xffffffffu, la_h, (lane >= 2 && lane < 8) ? lane - 2 : 0);
+                        if (lane >= 2) src = Gn.P + static_cast<long long>(pcol(c, t - hq)) * c.Mp;
+                        if (lane == 0) { fence_proxy_async(); mbar_expect_tx(mb, static_cast<unsigned>(ncopies * c.Mp * 8)); }
+                        __syncwarp();
+                        if (lane < ncopies) bulk_g2s(dst + lane * c.cpk, src, static_cast<unsigned>(c.Mp * 8), mb);
+                    }
+                }
+            }
+#endif
             const int slot = static_cast<int>((gbase + g) & (S - 1));
             mbar_wait(bars + slot, ((gbase + g) >> LS) & 1u);
             const double2 *hs = reinterpret_cast<const double2 *>(ring + slot * kStageBytes) + (R * qa) * RW + j;
@@ -2582,7 +2654,6 @@ __device__ FSB_FP_INLINE void phase_store_prices(const DevState &s, const int t)
 //   hand_s [Mp]      the day's net sale per asset (keep_history only: Q3 volume bookkeeping)
 //   keys   [kc][kq]  horizon returns per column (pass -> events-2)
 // ------------------------------------------------------------------------------------------------
-enum { HI_T = 0, HI_OPEN, HI_NCOLS, HI_NCASH, HI_FMOD = 8 };
 __host__ __device__ inline int hand_ints(int K, int cap) { return ((HI_FMOD + (K + 31) / 32 + 4 * cap) + 3) & ~3; }
 
 enum { KIND_EVENTS1 = 0, KIND_PASS = 1, KIND_EVENTS2 = 2, KIND_CHOICE = 3 };
@@ -2644,20 +2715,58 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
     const Rep G = rep_ptrs(s, c.r, c.kq, c.slot);
     const int nf = (c.K + 31) / 32;
     const int *hi = G.hand_i;
-    if (hi[HI_T] != t) return;  // (events-1 stopped this replication: its error flag is set)
-    const int open_day = hi[HI_OPEN], ncols = hi[HI_NCOLS];
-    for (int q = tid; q < nf; q += NT) c.fmod_()[q] = hi[HI_FMOD + q];
-    for (int q = tid; q < ncols; q += NT) c.hcols_()[q] = hi[HI_FMOD + nf + q];
+    // events-1's header: from the look-ahead of the CTA's previous replication (PassAhead) when there is one, else from global memory
+    const bool have_nx = !FSB_BIG && c.have_nx;
+    int stamp_ok, open_day, ncols, cur_staged = 0, cur_half = 0;
+    if (have_nx) {
+        const PassAhead &nx = *c.nx;
+        stamp_ok = nx.stamp_ok; open_day = nx.open_day; ncols = nx.ncols; cur_staged = nx.staged; cur_half = nx.half;
+        if (stamp_ok) {
+            for (int q = tid; q < nf; q += NT) c.fmod_()[q] = nx.fmod[q];
+            for (int q = tid; q < ncols; q += NT) c.hcols_()[q] = (q < 32) ? nx.hcols[q] : hi[HI_FMOD + nf + q];
+        }
+    } else {
+        stamp_ok = (hi[HI_T] == t) ? 1 : 0;
+        open_day = stamp_ok ? hi[HI_OPEN] : 0; ncols = stamp_ok ? hi[HI_NCOLS] : 0;
+        if (stamp_ok) {
+            for (int q = tid; q < nf; q += NT) c.fmod_()[q] = hi[HI_FMOD + q];
+            for (int q = tid; q < ncols; q += NT) c.hcols_()[q] = hi[HI_FMOD + nf + q];
+        }
+    }
     __syncthreads();
+    if (have_nx && tid == 0) c.nx->state = 0;  // consumed (thread 0 is also the one that fills it in again)
+    if (!stamp_ok) return;  // (events-1 stopped this replication: its error flag is set)
+    // the look-ahead runs inside full_pass_tma16, i.e. on days of at most 8 columns; it stages into the half of the column slots
+    // this replication does not read (its own columns: half cur_half if they were staged ahead, else the slots from 0)
+    const bool small = !FSB_BIG && c.fast && c.ring_stages > 0 && s.pass16 && (open_day || ncols + 2 <= 8);
+    const bool la = small && c.ahead_on && warp == 0;
+    const int la_half = cur_staged ? 1 - cur_half : 1, cslot0 = cur_staged ? 8 * cur_half : 0;
+    auto columns_ahead = [&]() {  // this replication's columns were started by the look-ahead: wait for them
+        mbar_wait(c.mbar_ah + cur_half, c.ah_phase[cur_half]);
+        __syncthreads();
+        if (tid == 0) c.ah_phase[cur_half] ^= 1u;
+        FSB_MARK(9);
+    };
     if (open_day) {  // nav_open = nav_close = H * p_open
 #if FSB_BIG
         if (c.part != 0 || c.chunk != 0) return;  // (one column: the first work unit of the replication takes all rows)
 #endif
-        phase_stage_columns(s, t, 0, 0, true, true);
-        if (!FSB_BIG && c.fast && c.ring_stages > 0 && s.pass16) full_pass_tma16<2>(s, 0, 1, 0, 0, 1);
+        if (cur_staged) columns_ahead();
+        else phase_stage_columns(s, t, 0, 0, true, true);
+        if (small) full_pass_tma16<2>(s, 0, 1, 0, 0, 1, cslot0, la, la_half, t);
         else if (!FSB_BIG && c.fast && c.ring_stages > 0) full_pass_tma<2>(s, 0, 1, 0, 0, 1);  // (big build: ring_stages marks the tiled pass)
         else if (c.fast) full_pass<1, true, true>(s, 0, 1, 0, 0);
         else full_pass<1, true, false>(s, 0, 1, 0, 0);
+    } else if (small) {  // one chunk of at most 8 columns
+        const int want_keys = (selector == FSB_SEL_PROBABILISTIC) ? 1 : 0, nc = 2 + ncols;
+        if (cur_staged) columns_ahead();
+        else phase_stage_columns(s, t, 0, ncols, true, false);
+        if (nc <= 2) full_pass_tma16<2>(s, 0, nc, want_keys, 0, 0, cslot0, la, la_half, t);
+        else if (nc <= 4) full_pass_tma16<4>(s, 0, nc, want_keys, 0, 0, cslot0, la, la_half, t);
+        else if (nc <= 6) full_pass_tma16<6>(s, 0, nc, want_keys, 0, 0, cslot0, la, la_half, t);
+        else full_pass_tma16<8>(s, 0, nc, want_keys, 0, 0, cslot0, la, la_half, t);
+        __syncthreads();
+        FSB_MARK(10);
     } else {
         const int cmax = c.cmax;
         const int want_keys = (selector == FSB_SEL_PROBABILISTIC) ? 1 : 0;
@@ -2889,7 +2998,12 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
     Ctx &c = ctx();
     __shared__ long long r_sh;
     __shared__ __align__(8) unsigned long long mbar_sh;
+    __shared__ __align__(8) unsigned long long mbar_ah_sh[2];
+    __shared__ PassAhead nx_sh;
     const int nwarps = blockDim.x >> 5;
+    // the look-ahead of the pass kernel (PassAhead): default shape, TMA-fed pass, 16 column slots (two halves of 8)
+    const bool ahead_on = (KIND == KIND_PASS) && !FSB_BIG && !FSB_FIXED && s.pass_ahead && s.pass16 && s.ring_stages > 0 && s.K <= 256 && s.Mp == 256 &&
+                          s.cmax + 2 >= 16 && s.cap_ev >= 32;
     const int nslots = (KIND == KIND_PASS) ? s.cmax + 2 : (KIND == KIND_EVENTS1 ? s.slots_a : s.slots_c);
     const SmemLayout L = make_layout(s.K, s.Mp, s.N, s.cap_ev, nslots, nwarps, (KIND == KIND_PASS) ? s.ring_stages : 0, FSB_BIG != 0);
     double *sd = reinterpret_cast<double *>(fsb_smem + kCtxBytes);
@@ -2925,6 +3039,12 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         c.big = s.bigbuf + (static_cast<long long>(2 * a.batch + (KIND == KIND_EVENTS2 ? 1 : 0)) * s.scratch_ctas + blockIdx.x) * s.big_stride;
 #endif
         c.mbar = &mbar_sh; c.mbar_phase = 0;
+        c.nx = &nx_sh; c.mbar_ah = mbar_ah_sh; c.ah_phase[0] = c.ah_phase[1] = 0;
+        c.ahead_on = ahead_on ? 1 : 0; c.have_nx = 0;
+        c.queue_ctr = s.queue + 2 * (4 * a.batch + KIND) + launch_parity;
+        c.r_begin = a.r_begin; c.r_end = a.r_end;
+        nx_sh.state = 0;
+        mbar_init(&mbar_ah_sh[0], 1); mbar_init(&mbar_ah_sh[1], 1);
         c.tm_h = tm_h;
         c.tm_h16 = tm_h16;
         c.tmark = clock64();
@@ -2960,8 +3080,9 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
     int *const queue = s.queue + 2 * (4 * a.batch + KIND);
     if (blockIdx.x == 0 && threadIdx.x == 0) queue[launch_parity ^ 1] = 0;  // reset the next launch's counter
     for (;;) {
-        if (threadIdx.x == 0) r_sh = atomicAdd(&queue[launch_parity], 1);
+        if (threadIdx.x == 0) r_sh = (ahead_on && nx_sh.state == 1) ? nx_sh.idx : atomicAdd(&queue[launch_parity], 1);
         __syncthreads();
+        const bool have_nx = ahead_on && nx_sh.state == 1;  // (uniform: the state changes only behind the next barrier)
 #if FSB_BIG
         // pass: (replication, part, chunk) work units, the chunk fastest: the CTAs that take the chunks of one part stream the
         // same holdings rows at the same time, so all but the first read of a line hit L2
@@ -2976,7 +3097,8 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
         const long long r = a.r_begin + r_sh;
 #endif
         if (r >= a.r_end) break;
-        const int frozen = s.err[r] & ~FSB_REP_TRACE_OVERFLOW;
+        const int frozen = have_nx ? nx_sh.frozen : (s.err[r] & ~FSB_REP_TRACE_OVERFLOW);
+        if (threadIdx.x == 0) c.have_nx = have_nx ? 1 : 0;
         if (threadIdx.x < kRepPtrs && !frozen) {  // one lane per pointer: base + r * stride
             const ulonglong2 e = __ldg(s.ptr_table + threadIdx.x);
             reinterpret_cast<unsigned long long *>(&c.H)[threadIdx.x] = e.x + static_cast<unsigned long long>(r) * e.y;
@@ -3006,7 +3128,10 @@ __device__ __forceinline__ void phase_kernel_body(const DevState &s, const StepA
             }
         }
         __syncthreads();  // context visible; also keeps r_sh stable until every thread has read it
-        if (frozen) continue;  // frozen replication (uniform)
+        if (frozen) {  // frozen replication (uniform)
+            if (threadIdx.x == 0) nx_sh.state = 0;  // (every thread has read the look-ahead before the barrier above)
+            continue;
+        }
         FSB_MARK(0);
         if (KIND == KIND_EVENTS1) step_events1(s, c, a.t_first, a.flags);
         else if (KIND == KIND_PASS) step_pass(s, c, a.t_first, a.selector);

@@ -499,6 +499,7 @@ def test_stakeless_fund_with_holdings_keeps_the_volume_quirk(fsb, orc):
     {"FSB_SCAN_CHOICE": "1"},                   # the rank rule sampled by the floating-point scan alone (no integer shortcut)
     {"FSB_PASS_PACKED": "1"},                   # the pass over the packed mirror of the holdings (fsb_passx.cuh, opt-in)
     {"FSB_PASS_PACKED": "1", "FSB_XCOLS": "4"},  # ... with small column chunks: several passes over the packed rows per day
+    {"FSB_PASS_AHEAD": "0"},                    # no look-ahead for the pass CTA's next replication (header + columns staged on demand)
     {"FSB_PASS16": "0"},                        # chunks of <= 8 columns in the 2 x 2 lane arrangement too (8-row trips only)
     {"FSB_PASS16": "0", "FSB_CMAX": "6"},
     {"FSB_NO_TMA": "1"},                        # register-ring pass (the path of non-default shapes) on the default shape
