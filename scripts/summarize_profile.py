@@ -83,10 +83,15 @@ for kname in ("draws", "events1", "pass", "choice", "events2"):
     lines += ["", f"DRAM bytes per replication-step: {dram / reps / 1e3:.1f} KB; warp instructions per replication-step: {inst / reps:.0f}", ""]
 if traffic:
     open(os.path.join(prof, f"{tag}_step_kernels.md"), "w").write("\n".join(lines) + "\n")
+    tpath = os.path.join(prof, "traffic_per_launch.json")
+    keep = {}
+    if os.path.exists(tpath):  # (the config-4 entry comes from its own capture: profiles/*_config4.md)
+        keep = {k: v for k, v in json.load(open(tpath)).items() if k == "config4"}
     json.dump({"tag": tag, "kernel": "fsb_pass_kernel", "dram_bytes_per_replication_step": traffic.get("pass"),
                "all_kernels": traffic,
-               "source": f"profiles/{tag}_step_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum over {reps} replication-steps per launch)"},
-              open(os.path.join(prof, "traffic_per_launch.json"), "w"), indent=1)
+               "source": f"profiles/{tag}_step_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum over {reps} replication-steps per launch)",
+               **keep},
+              open(tpath, "w"), indent=1)
     print("wrote", f"profiles/{tag}_step_kernels.md", {k: round(v / 1e3, 1) for k, v in traffic.items()})
 
 # ---- the bench line itself ---------------------------------------------------------------------
