@@ -5,7 +5,9 @@
 // wider event CTAs: the per-asset loops are 20x longer than on the default shape, and only 2 CTAs fit per SM
 #define FSB_STEP_THREADS 256
 #define FSB_E2_THREADS 256
-#define FSB_EV_CTAS 2
+#ifndef FSB_EV_CTAS
+#define FSB_EV_CTAS 2  // (the event kernels' 107 KB of shared memory at the config-4 shape allow two CTAs per SM)
+#endif
 #ifdef FSB_BIG_TIMING  // experiments: per-phase cycles of the big kernels (scripts/phase_cycles.py --config4)
 #define FSB_PHASE_TIMING 1
 #define g_phase_cycles g_phase_cycles_big
