@@ -33,7 +33,7 @@ EXPORTS = (
     "fsb_sync", "fsb_download_state", "fsb_download_compact", "fsb_download_log", "fsb_download_trace",
     "fsb_rep_status", "fsb_stylised_facts", "fsb_comm_unique_id", "fsb_comm_init_rank", "fsb_comm_init_all", "fsb_stats", "fsb_stats_local", "fsb_stats_all",
     "fsb_stats_words_per_point", "fsb_last_run_timing", "fsb_last_pass_launches", "fsb_last_facts_timing", "fsb_device_bytes", "fsb_debug_redzones", "fsb_next_day", "fsb_debug_draws", "fsb_debug_dot",
-    "fsb_debug_phase_cycles",
+    "fsb_debug_phase_cycles", "fsb_debug_pass_chunks",
 )
 
 
@@ -126,6 +126,7 @@ def lib():
                                       C.c_uint32, vp]
         L.fsb_debug_dot.argtypes = [vp, vp, vp, i64, vp]
         L.fsb_debug_phase_cycles.argtypes = [vp, vp, i32]
+        L.fsb_debug_pass_chunks.argtypes = [i32, vp, vp, i32]
         _LIB = L
     return _LIB
 

@@ -1248,6 +1248,21 @@ extern "C" int32_t fsb_stats_all(fsb_engine **engines, int32_t n, uint64_t *out)
 // ---- debug --------------------------------------------------------------------------------------
 // FSB_REDZONE=1 engines: number of device buffers whose guard bands (256 bytes before, >= 256 after) no longer hold
 // the fill pattern, i.e. that some kernel wrote outside of; -1 in *n_buffers when the engine was created without red zones
+// the column chunks the big-shape pass makes of a day with ncols distinct horizons (fsb_step.cuh: big_chunk_count / big_chunk,
+// the functions the kernel itself calls): first[i], count[i] for chunk i; returns the number of chunks (<= cap, else -1)
+extern "C" int32_t fsb_debug_pass_chunks(int32_t ncols, int32_t *first, int32_t *count, int32_t cap)
+{
+    if (ncols < 0 || !first || !count) return -1;
+    const int nch = big_chunk_count(ncols);
+    if (nch > cap) return -1;
+    for (int ch = 0; ch < nch; ++ch) {
+        int c0 = 0, nc = 0;
+        big_chunk(ncols, nch, ch, &c0, &nc);
+        first[ch] = c0; count[ch] = nc;
+    }
+    return nch;
+}
+
 extern "C" int32_t fsb_debug_redzones(fsb_engine *e, int64_t *n_buffers, int64_t *n_damaged)
 {
     if (!e || !n_buffers || !n_damaged) return fail(FSB_ERR_BAD_PARAMS, "null argument");

@@ -1441,6 +1441,23 @@ __device__ FSB_FP_INLINE void full_pass_tma16(const DevState &s, const int cb, c
     __syncwarp();
 }
 
+// The column chunks of a big-shape day with ncols distinct horizons (host-testable: fsb_debug_pass_chunks).  Chunk 0 holds the two
+// price columns + up to kBigCols - 2 horizons, every later chunk the day's price column + up to kBigCols - 1 horizons; the
+// horizons are spread evenly: chunk i takes ncols / nch of them, the last ncols % nch chunks one more.
+__host__ __device__ inline int big_chunk_count(int ncols)
+{
+    int nch = 1;
+    while ((kBigCols - 2) + (kBigCols - 1) * (nch - 1) < ncols) ++nch;
+    return nch;
+}
+__host__ __device__ inline void big_chunk(int ncols, int nch, int ch, int *c0, int *nc)
+{
+    const int hbase = ncols / nch, hrem = ncols % nch;
+    const int extra = ch - (nch - hrem);
+    *c0 = ch * hbase + (extra > 0 ? extra : 0);
+    *nc = hbase + (ch >= nch - hrem ? 1 : 0);
+}
+
 #if FSB_BIG
 // ------------------------------------------------------------------------------------------------
 // the holdings pass of big shapes (whole columns do not fit in shared memory): lane arrangement, chains and
@@ -2777,12 +2794,11 @@ __device__ __forceinline__ void step_pass(const DevState &s, Ctx &c, const int t
             // numerator of every horizon return) + up to kBigCols - 1 horizons.  The horizons are spread evenly over the chunks
             // (equal work: the CTAs that take the chunks of a part stay together); this unit takes the chunks c.chunk,
             // c.chunk + c.nchunks, ...
-            int nch = 1;
-            while ((kBigCols - 2) + (kBigCols - 1) * (nch - 1) < ncols) ++nch;
-            const int hbase = ncols / nch, hrem = ncols % nch;  // chunk i: hbase horizons, the last hrem chunks one more
+            const int nch = big_chunk_count(ncols);
 #pragma unroll 1
             for (int ch = c.chunk; ch < nch; ch += c.nchunks) {
-                const int c0 = ch * hbase + max(0, ch - (nch - hrem)), nc = hbase + (ch >= nch - hrem ? 1 : 0);
+                int c0, nc;
+                big_chunk(ncols, nch, ch, &c0, &nc);
                 const int later = ch > 0 ? 1 : 0, nreal = (later ? 1 : 2) + nc;
                 static_assert(kBigCols == 16, "the dispatch below");
                 if (nreal <= 4) big_pass_tiled<2>(s, t, c0, later, nreal, want_keys);

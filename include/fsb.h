@@ -237,6 +237,10 @@ int64_t fsb_device_bytes(const fsb_engine *e);
 /* engines created under FSB_REDZONE=1 keep guard bands around every device buffer: counts the buffers some kernel
  * wrote outside of (n_buffers = -1 without red zones) */
 int32_t fsb_debug_redzones(fsb_engine *e, int64_t *n_buffers, int64_t *n_damaged);
+/* (tests) the column chunks the big-shape pass kernel makes of a day with ncols distinct reinvestor horizons
+ * (src/functions.jl:335-379 asks for one horizon return per fund and distinct horizon): first[i] / count[i] horizons of
+ * chunk i; returns the number of chunks, -1 if it exceeds cap */
+int32_t fsb_debug_pass_chunks(int32_t ncols, int32_t *first, int32_t *count, int32_t cap);
 /* the day fsb_run / fsb_run_async / fsb_run_step_hosttape must start with next (perf_hi+2 on a fresh state) */
 int64_t fsb_next_day(const fsb_engine *e);
 /* RNG building blocks evaluated ON THE DEVICE, for cross-checks against the oracle */

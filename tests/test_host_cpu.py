@@ -49,6 +49,27 @@ def test_tape_key_layout(fsb):
     assert lib.fsb_tape_key(3, 1234, 17, 5) == (3 << 56) | (1234 << 32) | (17 << 16) | 5
 
 
+def test_big_shape_column_chunks_cover_every_horizon_once(fsb):
+    """The big-shape pass (config 4) splits a day's distinct horizons into chunks that different CTAs take at the same time
+    (DESIGN.md 4 'Big shapes'); the split is computed by the functions the kernel itself calls (fsb_debug_pass_chunks): every
+    horizon exactly once and in order, chunk 0 at most 14 of them (next to the two price columns), later chunks at most 15
+    (next to the day's price column), sizes within one of each other, as few chunks as the capacities allow."""
+    import ctypes as C
+    lib = fsb._lib.lib()
+    first, count = (C.c_int32 * 16)(), (C.c_int32 * 16)()
+    for ncols in range(0, 180):
+        nch = lib.fsb_debug_pass_chunks(ncols, first, count, 16)
+        assert nch >= 1
+        assert 14 + 15 * (nch - 1) >= ncols and (nch == 1 or 14 + 15 * (nch - 2) < ncols)
+        nxt = 0
+        for ch in range(nch):
+            assert first[ch] == nxt and 0 <= count[ch] <= (14 if ch == 0 else 15)
+            nxt += count[ch]
+        assert nxt == ncols
+        assert max(count[:nch]) - min(count[:nch]) <= 1
+    assert lib.fsb_debug_pass_chunks(500, first, count, 16) == -1
+
+
 def test_no_cpu_fallback_without_a_device(fsb):
     """On a box without a GPU every compute entry point must fail, never compute on the host."""
     import torch
