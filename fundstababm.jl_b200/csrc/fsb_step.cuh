@@ -13,11 +13,12 @@
 //                       T2 stake sequence, sale orders, net supply per asset, price impact, cash-outs
 //                       T3 respawn (0.23 per step)    T4 the cash holders and their distinct horizons
 //   fsb_pass_kernel     the K x M holdings cross HBM ONCE: up to cmax history columns + the day's two price
-//                          columns staged in shared memory by bulk asynchronous copies; 8-row trips per warp, the
-//                          four 8-lane groups in a 2 x 2 (rows x columns) arrangement, holdings through a per-warp
-//                          ring of shared-memory stages fed by 2-D tensor copies (register ring for other shapes).  Results:
-//                          NAV at the opening prices, NAV at the post-impact prices, back-cast returns per horizon
-//                          as order-preserving sort keys
+//                          columns staged in shared memory by bulk asynchronous copies; holdings through a per-warp
+//                          ring of shared-memory stages fed by 2-D tensor copies (register ring for other shapes);
+//                          the four 8-lane groups of a warp in a 4 x 1 (16-row trips, <= 8 columns: most days) or
+//                          2 x 2 (8-row trips, up to 16 columns) rows x columns arrangement; warp 0 prepares the
+//                          CTA's next replication meanwhile (PassAhead).  Results: NAV at the opening prices, NAV at
+//                          the post-impact prices, back-cast returns per horizon as order-preserving sort keys
 //   fsb_choice_kernel   ranks per horizon by an in-register bitonic sort, fund choice of the day's cash holders
 //                          (inside fsb_events2_kernel in the big-shape build)
 //   fsb_events2_kernel  stake dilution, buy orders, impact, share disbursement
@@ -33,7 +34,9 @@
 // FSB_BIG (fsb_step_big.cu): a second build of the same code for shapes whose per-asset arrays do not fit in
 // shared memory (BASELINE.json configs[3]: K = 2000, M = 5000).  The price / order / probability rows, the
 // impact ratio, the net supply and the respawn pick table then live in a per-CTA global buffer (L2 resident);
-// only the accessors and the column staging differ, every arithmetic statement is shared.
+// only the accessors and the column staging differ, every arithmetic statement is shared.  Its pass kernel
+// (big_pass_tiled) streams column TILES through a CTA-wide TMA ring fed by a producer warp, with 8 x 8 accumulators
+// per lane and (replication, rows, column chunk) work units; 256 < K <= 2048 ranks by a CTA-wide bitonic network.
 #pragma once
 #include <cuda.h>  // CUtensorMap (type only)
 #ifndef FSB_BIG
@@ -1461,13 +1464,15 @@ __host__ __device__ inline void big_chunk(int ncols, int nch, int ch, int *c0, i
 #if FSB_BIG
 // ------------------------------------------------------------------------------------------------
 // the holdings pass of big shapes (whole columns do not fit in shared memory): lane arrangement, chains and
-// epilogue of full_pass<C>, but the 2*C columns reach the warps through a CTA-wide ring of kBigStages tiles
-// in shared memory.  A tile = 128 assets (8 word steps) of every column, 1 KB per column, copied by the TMA
-// unit straight from the price ring / the opening prices (no staged copy of whole columns).  All warps walk
-// the tiles in the same order, each against its own 8 rows of the row block (nwarps * 8 rows); the holdings go
-// global -> registers as in full_pass.  full[slot]: the tile's bytes have landed; empty[slot]: every warp is
-// done with it.  The producer (lane 0 of warp 0) runs kBigStages - 2 tiles ahead of its own warp, so the warps
-// may drift apart by two tiles before anyone waits.
+// epilogue of full_pass<C> with kBigR rows per lane, but the 2*C columns reach the warps through a CTA-wide ring of
+// kBigStages tiles in shared memory.  A tile = kBigTileBytes / 8 assets of every column, copied by the TMA unit
+// straight from the price ring / the opening prices (no staged copy of whole columns).  All computing warps walk
+// the tiles in the same order, each against its own 2 * kBigR rows of the row block; a warp's holdings arrive
+// through its own ring of kBigHStages stages (2 * kBigR rows x kBigStageRowBytes, one 2-D tensor copy each).
+// full[slot]: the tile's bytes have landed; empty[slot]: every computing warp is done with it.  The LAST warp of
+// the CTA is the producer: it waits on `empty` and issues, nothing else (FSB_BIG_NOPROD=1: no producer warp, the
+// last warp to finish a tile refills its slot -- measured slower).  One call = one column chunk of one work unit
+// (replication, part of the row blocks, chunk): see step_pass and big_chunk.
 // ------------------------------------------------------------------------------------------------
 template <int C>
 __device__ FSB_FP_INLINE void big_pass_tiled(const DevState &s, const int t, const int c0, const int later, const int nreal, const int want_keys)
